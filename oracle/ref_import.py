@@ -1,0 +1,64 @@
+"""Import the UNMODIFIED reference planner from /root/reference (authoring container only).
+
+TEST INFRASTRUCTURE.  Recipe from SURVEY.md Appendix C: (1) bypass
+``vlnce_baselines/__init__.py`` (imports Habitat) by pre-registering namespace packages,
+(2) patch the transformers-4.x ``init_weights`` idiom used at ``vilmodel_cmt.py:673`` for
+transformers 5.x.  No reference file is modified or copied.
+"""
+import os
+import sys
+import types
+
+REF = os.environ.get("ETPNAV_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF, "vlnce_baselines/models/etp/vilmodel_cmt.py"))
+
+
+def load_vilmodel():
+    for name, sub in [("vlnce_baselines", ""), ("vlnce_baselines.common", "/common"),
+                      ("vlnce_baselines.models", "/models"), ("vlnce_baselines.models.etp", "/models/etp")]:
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [REF + "/vlnce_baselines" + sub]
+            sys.modules[name] = m
+    sys.dont_write_bytecode = True  # /root/reference is read-only
+    from transformers import PreTrainedModel
+    from vlnce_baselines.models.etp import vilmodel_cmt as V
+    _orig = PreTrainedModel.init_weights
+
+    def _init_weights_compat(self):
+        return self.post_init() if not hasattr(self, "all_tied_weights_keys") else _orig(self)
+
+    V.GlocalTextPathNavCMT.init_weights = _init_weights_compat
+    return V
+
+
+def build_reference(cfg, state_dict=None):
+    """Instantiate the reference ``GlocalTextPathNavCMT`` (vilmodel_cmt.py:663) for a PlannerConfig."""
+    from transformers import PretrainedConfig
+    V = load_vilmodel()
+    name = "bert-base-uncased" if cfg.layer_norm_eps == 1e-12 else "xlm-roberta-base"
+    hf = PretrainedConfig.from_pretrained(REF + "/bert_config/" + name)
+    hf.type_vocab_size = cfg.type_vocab_size
+    hf.layer_norm_eps = cfg.layer_norm_eps
+    hf.vocab_size = cfg.vocab_size                      # tests shrink the vocab to keep fixtures small
+    hf.max_position_embeddings = cfg.max_position_embeddings
+    hf.hidden_dropout_prob = cfg.hidden_dropout_prob
+    hf.attention_probs_dropout_prob = cfg.attention_probs_dropout_prob
+    for k, v in dict(max_action_steps=cfg.max_action_steps, image_feat_size=cfg.image_feat_size,
+                     use_depth_embedding=cfg.use_depth_embedding, depth_feat_size=cfg.depth_feat_size,
+                     angle_feat_size=cfg.angle_feat_size, num_l_layers=cfg.num_l_layers,
+                     num_pano_layers=cfg.num_pano_layers, num_x_layers=cfg.num_x_layers,
+                     graph_sprels=cfg.graph_sprels, glocal_fuse="global",
+                     fix_lang_embedding=cfg.fix_lang_embedding, fix_pano_embedding=cfg.fix_pano_embedding,
+                     update_lang_bert=cfg.update_lang_bert, output_attentions=True,
+                     pred_head_dropout_prob=cfg.pred_head_dropout_prob, use_lang2visn_attn=False).items():
+        setattr(hf, k, v)
+    model = V.GlocalTextPathNavCMT(hf)
+    if state_dict is not None:
+        missing, unexpected = model.load_state_dict(state_dict, strict=False)
+        assert not unexpected, unexpected
+        assert all("position_ids" in m for m in missing), missing
+    return model

@@ -1,0 +1,43 @@
+"""Shared helpers for the parity tests (TEST code: may import oracle/)."""
+import glob
+import os
+
+import torch
+
+from etpnav_b200.config import PlannerConfig
+from etpnav_b200.synth import make_inputs, make_weights
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+
+
+def load_case(name):
+    """Returns (golden dict, cfg, weights, inputs) with weights/inputs rebuilt from the seeds."""
+    gold = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    c = gold["case"]
+    cfg = PlannerConfig(**c["cfg"])
+    sd = make_weights(cfg, seed=c["wseed"])
+    inp = make_inputs(cfg, c["B"], c["V"], c["N"], c["L"], seed=c["iseed"], ragged=c["ragged"])
+    return gold, cfg, sd, inp
+
+
+def slim(gold, t):
+    s = gold["case"].get("slim")
+    return t[:, ::s] if (s and t.dim() == 3) else t
+
+
+def grad_sig(t):
+    t = t.detach().double().flatten()
+    return torch.cat([t.sum()[None], t.norm()[None], t[:8]]).float()
+
+
+def golden_loss(gold, pano, pmask, gmap_embeds, logits, inp):
+    """The scalar the fixtures differentiate (oracle/make_golden.py:run_case)."""
+    g = torch.Generator().manual_seed(77)
+    pw = (torch.randn(pano.shape, generator=g) * pmask.cpu()[..., None]).to(pano)
+    gw = (torch.randn(gmap_embeds.shape, generator=g) * inp["gmap_masks"][..., None]).to(gmap_embeds)
+    return (torch.nn.functional.cross_entropy(logits, inp["labels"].to(logits.device), reduction="sum")
+            + (pano * pw).sum() * 0.01 + (gmap_embeds * gw).sum() * 0.01)
