@@ -1,0 +1,105 @@
+// extern "C" surface of libetpnav_b200.so (declared in include/etpnav_b200.h).
+#include "../../include/etpnav_b200.h"
+
+#include "host.h"
+#include "ops.h"
+
+namespace etp {
+const char* last_error_cstr();
+}
+
+using namespace etp;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define ETP_API __attribute__((visibility("default")))
+extern "C" {
+
+ETP_API int etp_version(void) { return 100; }
+ETP_API const char* etp_last_error(void) { return last_error_cstr(); }
+
+ETP_API int etp_check_device(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(ETP_ERR_NO_DEVICE, "no CUDA device");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(ETP_ERR_NO_DEVICE, "cannot query CUDA device");
+  if (prop.major != 10) return fail(ETP_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) +
+                                                             std::to_string(prop.minor) + ", kernels are sm_100a only");
+  return ETP_OK;
+}
+
+ETP_API int etp_gemm(const etp_gemm_args* g, void* stream) {
+  ETP_REQUIRE(g != nullptr, "etp_gemm: null args");
+  GemmArgs a;
+  a.M = g->M; a.N = g->N; a.K = g->K;
+  a.A = static_cast<const bf16*>(g->A); a.lda = g->lda; a.a_mn = g->a_mn;
+  a.B = static_cast<const bf16*>(g->B); a.ldb = g->ldb; a.b_mn = g->b_mn;
+  a.alpha = g->alpha; a.bias = g->bias; a.act = g->act; a.aux_mode = g->aux_mode;
+  a.aux = static_cast<const bf16*>(g->aux); a.ld_aux = g->ld_aux;
+  a.resid = g->resid; a.ld_resid = g->ld_resid;
+  a.out_f32 = g->out_f32; a.ld_f32 = g->ld_f32; a.atomic = g->atomic;
+  a.out_bf16 = static_cast<bf16*>(g->out_bf16); a.ld_bf16 = g->ld_bf16;
+  a.out_pre = static_cast<bf16*>(g->out_pre); a.ld_pre = g->ld_pre;
+  a.k_splits = g->k_splits < 1 ? 1 : g->k_splits; a.block_n = g->block_n;
+  return gemm(a, S(stream));
+}
+
+ETP_API int etp_attention_fwd(const etp_attn_args* g, void* stream) {
+  ETP_REQUIRE(g != nullptr, "etp_attention_fwd: null args");
+  AttnArgs a;
+  a.B = g->B; a.heads = g->heads; a.Sq = g->Sq; a.Sk = g->Sk;
+  a.q = static_cast<const bf16*>(g->q); a.ldq = g->ldq;
+  a.k = static_cast<const bf16*>(g->k); a.ldk = g->ldk;
+  a.v = static_cast<const bf16*>(g->v); a.ldv = g->ldv;
+  a.scale = g->scale; a.key_valid = g->key_valid; a.mask_value = g->mask_value;
+  a.pair = g->pair; a.pair_w = g->pair_w; a.pair_b = g->pair_b;
+  a.out = static_cast<bf16*>(g->out); a.ldo = g->ldo; a.lse = g->lse;
+  return attention_fwd(a, S(stream));
+}
+
+ETP_API int etp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t H,
+                      float* y_f32, void* y_bf16, float* mean, float* rstd, void* stream) {
+  return layernorm_fwd(x, gamma, beta, eps, rows, H, y_f32, static_cast<bf16*>(y_bf16), mean, rstd, S(stream));
+}
+ETP_API int etp_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                      int32_t rows, int32_t H, float* dx_f32, int32_t accumulate_dx, void* dx_bf16, float* dgamma,
+                      float* dbeta, void* stream) {
+  return layernorm_bwd(dy, x, gamma, mean, rstd, rows, H, dx_f32, accumulate_dx, static_cast<bf16*>(dx_bf16), dgamma,
+                       dbeta, S(stream));
+}
+ETP_API int etp_colsum_bf16(const void* x, int32_t rows, int32_t cols, int32_t ld, float* out, void* stream) {
+  return colsum_bf16(static_cast<const bf16*>(x), rows, cols, ld, out, S(stream));
+}
+ETP_API int etp_colsum_f32(const float* x, int32_t rows, int32_t cols, int32_t ld, float* out, void* stream) {
+  return colsum_f32(x, rows, cols, ld, out, S(stream));
+}
+ETP_API int etp_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  return cast_f32_to_bf16(x, static_cast<bf16*>(y), n, S(stream));
+}
+
+ETP_API int etp_pano_pack_fwd(const etp_pano_pack_args* g, void* stream) {
+  ETP_REQUIRE(g != nullptr, "etp_pano_pack_fwd: null args");
+  PanoPackArgs a;
+  a.rows = g->rows; a.rgb_lin = g->rgb_lin; a.dep_lin = g->dep_lin; a.loc_fts = g->loc_fts; a.nav_types = g->nav_types;
+  a.loc_w = g->loc_w; a.loc_b = g->loc_b; a.img_g = g->img_g; a.img_b = g->img_b; a.dep_g = g->dep_g; a.dep_b = g->dep_b;
+  a.loc_g = g->loc_g; a.loc_bb = g->loc_bb; a.out_g = g->out_g; a.out_b = g->out_b; a.nav_emb = g->nav_emb;
+  a.tok_emb1 = g->tok_emb1; a.x_f32 = g->x_f32; a.loc_lin = g->loc_lin; a.sum_pre = g->sum_pre; a.stats = g->stats;
+  return pano_pack_fwd(a, S(stream));
+}
+
+ETP_API int etp_node_pack_fwd(const etp_node_pack_args* g, void* stream) {
+  ETP_REQUIRE(g != nullptr, "etp_node_pack_fwd: null args");
+  NodePackArgs a;
+  a.rows = g->rows; a.img_fts = g->img_fts; a.step_ids = g->step_ids; a.pos_fts = g->pos_fts;
+  a.pos_w = g->pos_w; a.pos_b = g->pos_b; a.pos_g = g->pos_g; a.pos_bb = g->pos_bb; a.step_emb = g->step_emb;
+  a.x_f32 = g->x_f32; a.x_bf16 = static_cast<bf16*>(g->x_bf16); a.pos_lin = g->pos_lin; a.stats = g->stats;
+  return node_pack_fwd(a, S(stream));
+}
+
+ETP_API int etp_sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, const float* w4, const float* b4,
+                     const uint8_t* visited, const uint8_t* valid, int32_t rows, int32_t H, float* logits,
+                     float* mean, float* rstd, void* stream) {
+  return sap_tail_fwd(relu_out, gamma, beta, w4, b4, visited, valid, rows, H, logits, mean, rstd, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,253 @@
+// Row-wise HBM-bound kernels: LayerNorm forward/backward, column sums (bias gradients), casts.
+// One warp owns one 768-wide row: 24 values per lane as six 128-bit loads, warp-shuffle reductions,
+// fp32 statistics.  Replaces torch.nn.LayerNorm / BertLayerNorm on the reference path
+// (vilmodel_cmt.py:24-28,151-153,190-192; common/transformer.py:144-145,174,178; common/ops.py:20).
+#include "common.cuh"
+#include "host.h"
+#include "ops.h"
+
+namespace etp {
+
+constexpr int kH = 768;
+constexpr int kVec = kH / 128;  // float4 per lane
+
+ETP_DEVICE void load_row(const float* p, int lane, float (&v)[24]) {
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(p + (i * 32 + lane) * 4);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+ETP_DEVICE void store_row(float* p, int lane, const float (&v)[24]) {
+#pragma unroll
+  for (int i = 0; i < kVec; ++i)
+    *reinterpret_cast<float4*>(p + (i * 32 + lane) * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+ETP_DEVICE void store_row_bf16(bf16* p, int lane, const float (&v)[24]) {
+#pragma unroll
+  for (int i = 0; i < kVec; ++i)
+    *reinterpret_cast<uint2*>(p + (i * 32 + lane) * 4) =
+        make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3]));
+}
+// mean and 1/sqrt(var + eps) of a row held across the warp (two-pass: exact like torch's LayerNorm)
+ETP_DEVICE void row_stats(const float (&v)[24], float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s += v[i];
+  mean = warp_sum(s) * (1.0f / kH);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { const float d = v[i] - mean; q += d * d; }
+  rstd = rsqrtf(warp_sum(q) * (1.0f / kH) + eps);
+}
+
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps, int rows,
+                                                             float* __restrict__ y_f32, bf16* __restrict__ y_bf16,
+                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[24], g[24], b[24];
+  load_row(x + static_cast<size_t>(row) * kH, lane, v);
+  load_row(gamma, lane, g);
+  load_row(beta, lane, b);
+  float mean, rstd;
+  row_stats(v, eps, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) v[i] = (v[i] - mean) * rstd * g[i] + b[i];
+  if (y_f32) store_row(y_f32 + static_cast<size_t>(row) * kH, lane, v);
+  if (y_bf16) store_row_bf16(y_bf16 + static_cast<size_t>(row) * kH, lane, v);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int rows, int H, float* y_f32,
+                  bf16* y_bf16, float* mean, float* rstd, cudaStream_t stream) {
+  ETP_REQUIRE(H == kH, "layernorm: hidden size must be 768");
+  if (rows <= 0) return ETP_OK;
+  layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, eps, rows, y_f32, y_bf16, mean, rstd);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+
+// Backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd.
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy: per-lane register partials over a grid-stride loop
+// of rows, reduced across the CTA's 8 warps in shared memory, one atomicAdd per column per CTA.
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, int rows, float* __restrict__ dx_f32,
+                                                             int accumulate_dx, bf16* __restrict__ dx_bf16,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[8][kH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float g[24], dg[24], db[24];
+  load_row(gamma, lane, g);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    float d[24], v[24];
+    load_row(dy + static_cast<size_t>(row) * kH, lane, d);
+    load_row(x + static_cast<size_t>(row) * kH, lane, v);
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      v[i] = (v[i] - mu) * rs;       // xhat
+      dg[i] += d[i] * v[i];
+      db[i] += d[i];
+      d[i] *= g[i];                  // g
+      s1 += d[i];
+      s2 += d[i] * v[i];
+    }
+    s1 = warp_sum(s1) * (1.0f / kH);
+    s2 = warp_sum(s2) * (1.0f / kH);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) d[i] = rs * (d[i] - s1 - v[i] * s2);
+    float* o = dx_f32 + static_cast<size_t>(row) * kH;
+    if (accumulate_dx) {
+      float prev[24];
+      load_row(o, lane, prev);
+#pragma unroll
+      for (int i = 0; i < 24; ++i) d[i] += prev[i];
+    }
+    store_row(o, lane, d);
+    if (dx_bf16) store_row_bf16(dx_bf16 + static_cast<size_t>(row) * kH, lane, d);
+  }
+  if (dgamma == nullptr) return;
+  // CTA reduction of the per-warp partials
+#pragma unroll
+  for (int i = 0; i < kVec; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[warp][(i * 32 + lane) * 4 + j] = dg[4 * i + j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < kH; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(dgamma + c, s);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kVec; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[warp][(i * 32 + lane) * 4 + j] = db[4 * i + j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < kH; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(dbeta + c, s);
+  }
+}
+
+int layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int rows,
+                  int H, float* dx_f32, int accumulate_dx, bf16* dx_bf16, float* dgamma, float* dbeta,
+                  cudaStream_t stream) {
+  ETP_REQUIRE(H == kH, "layernorm: hidden size must be 768");
+  if (rows <= 0) return ETP_OK;
+  int grid = (rows + 7) / 8;
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  layernorm_bwd_kernel<<<grid, 256, 0, stream>>>(dy, x, gamma, mean, rstd, rows, dx_f32, accumulate_dx, dx_bf16, dgamma,
+                                                 dbeta);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+
+// out[c] += sum_r x[r, c].  Each CTA covers 64 columns x a slab of rows; threads (32 x 8): lane-pairs of columns,
+// 8 row lanes; shared-memory reduce over the 8 row lanes; one atomicAdd per column per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int rows, int cols, int ld, int rows_per_cta,
+                                                      float* __restrict__ out) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + tx * 2;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < cols) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const T* p = x + static_cast<size_t>(r) * ld + c;
+      if constexpr (sizeof(T) == 2) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+        s0 += f.x; s1 += f.y;
+      } else {
+        const float2 f = *reinterpret_cast<const float2*>(p);
+        s0 += f.x; s1 += f.y;
+      }
+    }
+  }
+  red[ty][tx * 2] = s0;
+  red[ty][tx * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < cols) atomicAdd(out + cc, s);
+  }
+}
+
+template <typename T>
+static int colsum_impl(const T* x, int rows, int cols, int ld, float* out, cudaStream_t stream) {
+  ETP_REQUIRE(cols % 2 == 0 && ld % 2 == 0, "colsum: even cols/ld required");
+  if (rows <= 0) return ETP_OK;
+  const int gx = (cols + 63) / 64;
+  int gy = (2 * num_sms() + gx - 1) / gx;
+  int rpc = (rows + gy - 1) / gy;
+  if (rpc < 64) rpc = 64;
+  gy = (rows + rpc - 1) / rpc;
+  colsum_kernel<T><<<dim3(gx, gy), 256, 0, stream>>>(x, rows, cols, ld, rpc, out);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+int colsum_bf16(const bf16* x, int rows, int cols, int ld, float* out, cudaStream_t stream) {
+  return colsum_impl<bf16>(x, rows, cols, ld, out, stream);
+}
+int colsum_f32(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream) {
+  return colsum_impl<float>(x, rows, cols, ld, out, stream);
+}
+
+__global__ void cast_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n4) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 t = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+  }
+}
+__global__ void cast_tail_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t start, int64_t n) {
+  const int64_t i = start + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16(x[i]);
+}
+int cast_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return ETP_OK;
+  ETP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "cast: alignment");
+  const int64_t n4 = n / 4;
+  if (n4 > 0) {
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    cast_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, n4);
+  }
+  if (n4 * 4 < n) cast_tail_kernel<<<1, 32, 0, stream>>>(x, y, n4 * 4, n);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+
+__global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] += src[i];
+}
+int add_f32(float* dst, const float* src, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return ETP_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  add_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dst, src, n);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+
+}  // namespace etp

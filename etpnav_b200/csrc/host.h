@@ -1,0 +1,46 @@
+// Host-side plumbing shared by the launchers: error reporting for the C ABI, the TMA tensor-map
+// encoder (driver entry point resolved through cudart so the library loads without libcuda.so).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace etp {
+
+// error codes (same values as include/etpnav_b200.h)
+#ifndef ETP_OK
+#define ETP_OK 0
+#define ETP_ERR_INVALID (-1)   // bad argument / unsupported shape
+#define ETP_ERR_CUDA (-2)      // CUDA runtime / driver error
+#define ETP_ERR_NO_DEVICE (-3) // no sm_100 device
+#endif
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define ETP_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::etp::fail(ETP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define ETP_REQUIRE(cond, msg)                                                     \
+  do {                                                                             \
+    if (!(cond)) return ::etp::fail(ETP_ERR_INVALID, std::string(msg));     \
+  } while (0)
+
+// 2-D bf16 tensor map: global [rows, cols] with row pitch ld (elements), box [box_rows, box_cols],
+// 128-byte swizzle (box_cols * 2 bytes must be 128).  Cached by (ptr, shape, box).
+int get_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+                CUtensorMap* out);
+// 3-D bf16 tensor map: global [d2, d1, d0] (d0 contiguous) with pitches ld1 (elements between d1 rows),
+// ld2 (elements between d2 slabs); box [1, box1, box0]; 128-byte swizzle.
+int get_tmap_3d(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1, uint64_t ld2, uint32_t box0,
+                uint32_t box1, CUtensorMap* out);
+
+int num_sms();
+
+}  // namespace etp

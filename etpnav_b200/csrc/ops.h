@@ -1,0 +1,116 @@
+// Internal C++ interface of the kernel launchers (the public C ABI is include/etpnav_b200.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace etp {
+
+typedef __nv_bfloat16 bf16;
+
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const bf16* A = nullptr;  // a_mn == 0: [M, K] row-major (pitch lda);  a_mn == 1: [K, M] row-major
+  int lda = 0;
+  int a_mn = 0;
+  const bf16* B = nullptr;  // b_mn == 0: [N, K] row-major (pitch ldb);  b_mn == 1: [K, N] row-major
+  int ldb = 0;
+  int b_mn = 0;
+  float alpha = 1.0f;
+  const float* bias = nullptr;  // [N]
+  int act = 0;                  // 0 none, 1 gelu(erf), 2 relu
+  int aux_mode = 0;             // 0 none, 1: *= gelu'(aux), 2: *= (aux > 0)
+  const bf16* aux = nullptr;
+  int ld_aux = 0;
+  const float* resid = nullptr;  // fp32 [M, N] added after activation
+  int ld_resid = 0;
+  float* out_f32 = nullptr;
+  int ld_f32 = 0;
+  int atomic = 0;  // out_f32 += result (atomicAdd); required for k_splits > 1
+  bf16* out_bf16 = nullptr;
+  int ld_bf16 = 0;
+  bf16* out_pre = nullptr;  // bf16 copy of the pre-activation value (alpha*acc + bias)
+  int ld_pre = 0;
+  int k_splits = 1;
+  int block_n = 0;  // 0 = auto, else 128 or 256
+};
+int gemm(const GemmArgs& a, cudaStream_t stream);
+
+// ---- row-wise kernels (elementwise.cu) ------------------------------------------------------------
+// y = LayerNorm(x) * gamma + beta over the last dim (H = 768), biased variance, eps inside sqrt.
+// Writes any of: y_f32, y_bf16; saves mean / rstd (fp32 [rows]) when non-null.
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int rows, int H, float* y_f32,
+                  bf16* y_bf16, float* mean, float* rstd, cudaStream_t stream);
+// dx = LN backward (dy fp32 [rows,H], x fp32, mean, rstd); accumulates dgamma/dbeta (fp32 [H], atomicAdd).
+// dx is written to dx_f32 (fp32; if accumulate_dx != 0 it is added to the existing content) and,
+// if non-null, a bf16 copy to dx_bf16.
+int layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int rows,
+                  int H, float* dx_f32, int accumulate_dx, bf16* dx_bf16, float* dgamma, float* dbeta,
+                  cudaStream_t stream);
+// out[c] += sum_r x[r, c]   (bias gradients)
+int colsum_bf16(const bf16* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
+int colsum_f32(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
+int cast_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream);
+int add_f32(float* dst, const float* src, int64_t n, cudaStream_t stream);  // dst += src
+
+// ---- token packing (pack.cu) ----------------------------------------------------------------------
+struct PanoPackArgs {
+  int rows = 0;                       // B*V
+  const float* rgb_lin = nullptr;     // [rows,768] = rgb_fts @ W_img^T + b (GEMM output)
+  const float* dep_lin = nullptr;     // [rows,768] or null (use_depth_embedding false)
+  const float* loc_fts = nullptr;     // [rows,4]
+  const int64_t* nav_types = nullptr; // [rows]
+  const float *loc_w = nullptr, *loc_b = nullptr;  // [768,4], [768]
+  const float *img_g = nullptr, *img_b = nullptr, *dep_g = nullptr, *dep_b = nullptr, *loc_g = nullptr,
+              *loc_bb = nullptr, *out_g = nullptr, *out_b = nullptr;
+  const float* nav_emb = nullptr;  // [2,768]
+  const float* tok_emb1 = nullptr; // token_type_embeddings row 1, [768]
+  float* x_f32 = nullptr;          // [rows,768] packed view tokens (fp32 residual stream)
+  // saved for backward (may be null in inference)
+  float* loc_lin = nullptr;  // [rows,768]
+  float* sum_pre = nullptr;  // [rows,768] value before the final layer_norm
+  float* stats = nullptr;    // [rows,8]: mean/rstd of img, dep, loc, out LayerNorms
+};
+int pano_pack_fwd(const PanoPackArgs& a, cudaStream_t stream);
+
+struct NodePackArgs {
+  int rows = 0;                         // B*N
+  const float* img_fts = nullptr;       // [rows,768]
+  const int64_t* step_ids = nullptr;    // [rows]
+  const float* pos_fts = nullptr;       // [rows,7]
+  const float *pos_w = nullptr, *pos_b = nullptr, *pos_g = nullptr, *pos_bb = nullptr;  // [768,7],[768],[768],[768]
+  const float* step_emb = nullptr;      // [100,768]
+  float* x_f32 = nullptr;
+  bf16* x_bf16 = nullptr;
+  float* pos_lin = nullptr;  // saved [rows,768] (null in inference)
+  float* stats = nullptr;    // saved [rows,2]
+};
+int node_pack_fwd(const NodePackArgs& a, cudaStream_t stream);
+
+// SAP head tail: h = LN_1e-12(relu_out) ; logit = h . w4 + b4 ; -inf where visited or padded.
+// (vilmodel_cmt.py:654-658 net.2..net.4, :742-744)
+int sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, const float* w4, const float* b4,
+                 const uint8_t* visited, const uint8_t* valid, int rows, int H, float* logits, float* mean,
+                 float* rstd, cudaStream_t stream);
+
+// ---- attention (attention.cu) ---------------------------------------------------------------------
+struct AttnArgs {
+  int B = 0, heads = 12, Sq = 0, Sk = 0;
+  const bf16* q = nullptr;  // [B, Sq, ldq] head h at column h*64
+  int ldq = 0;
+  const bf16* k = nullptr;  // [B, Sk, ldk]
+  int ldk = 0;
+  const bf16* v = nullptr;
+  int ldv = 0;
+  float scale = 0.125f;              // applied to q.k^T
+  const uint8_t* key_valid = nullptr;  // [B, Sk] 1 = real token
+  float mask_value = -10000.0f;        // added where key_valid == 0 (use -inf for nn.MultiheadAttention semantics)
+  const float* pair = nullptr;         // [B, Sq, Sk] or null: bias += pair_w * pair + pair_b
+  float pair_w = 0.0f, pair_b = 0.0f;
+  bf16* out = nullptr;  // [B, Sq, ldo]
+  int ldo = 0;
+  float* lse = nullptr;  // [B, heads, Sq] log-sum-exp of the biased scores (saved for backward), may be null
+};
+int attention_fwd(const AttnArgs& a, cudaStream_t stream);
+
+}  // namespace etp

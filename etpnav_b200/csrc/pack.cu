@@ -1,0 +1,191 @@
+// Token-packing kernels: panorama view tokens, graph-node tokens and the SAP-head tail.
+// One warp per 768-wide token row (24 values per lane, 128-bit accesses, warp-shuffle LayerNorm).
+//   pano_pack : vilmodel_cmt.py:695-711  (3 LayerNorms + nav-type / token-type embedding adds + LayerNorm;
+//               the K=4 loc_linear is done here on CUDA cores, the K=512/128 linears come from the GEMM)
+//   node_pack : vilmodel_cmt.py:728-730  (img_fts + step embedding + LN(Linear7(pos_fts)))
+//   sap_tail  : vilmodel_cmt.py:654-658 (net.2 LayerNorm, net.4 Linear 768->1) + :742-744 (-inf masks)
+#include "common.cuh"
+#include "host.h"
+#include "ops.h"
+
+namespace etp {
+
+constexpr int kH = 768;
+
+ETP_DEVICE void ld24(const float* p, int lane, float (&v)[24]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(p + (i * 32 + lane) * 4);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+ETP_DEVICE void st24(float* p, int lane, const float (&v)[24]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    *reinterpret_cast<float4*>(p + (i * 32 + lane) * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+ETP_DEVICE void st24_bf16(bf16* p, int lane, const float (&v)[24]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    *reinterpret_cast<uint2*>(p + (i * 32 + lane) * 4) =
+        make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3]));
+}
+ETP_DEVICE void stats24(const float (&v)[24], float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s += v[i];
+  mean = warp_sum(s) * (1.0f / kH);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { const float d = v[i] - mean; q += d * d; }
+  rstd = rsqrtf(warp_sum(q) * (1.0f / kH) + eps);
+}
+// acc += LN(v) * g + b ; returns stats
+ETP_DEVICE void ln_accum(const float (&v)[24], const float* g, const float* b, int lane, float eps, float (&acc)[24],
+                         float& mean, float& rstd) {
+  stats24(v, eps, mean, rstd);
+  float gg[24], bb[24];
+  ld24(g, lane, gg);
+  ld24(b, lane, bb);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) acc[i] += (v[i] - mean) * rstd * gg[i] + bb[i];
+}
+
+__global__ void __launch_bounds__(256) pano_pack_kernel(const PanoPackArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= a.rows) return;
+  float acc[24], v[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) acc[i] = 0.f;
+  float st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  ld24(a.rgb_lin + static_cast<size_t>(row) * kH, lane, v);
+  ln_accum(v, a.img_g, a.img_b, lane, 1e-12f, acc, st[0], st[1]);
+  if (a.dep_lin) {
+    ld24(a.dep_lin + static_cast<size_t>(row) * kH, lane, v);
+    ln_accum(v, a.dep_g, a.dep_b, lane, 1e-12f, acc, st[2], st[3]);
+  }
+  {
+    const float4 f = *reinterpret_cast<const float4*>(a.loc_fts + static_cast<size_t>(row) * 4);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = (i * 32 + lane) * 4 + j;
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.loc_w + c * 4));
+        v[4 * i + j] = f.x * w.x + f.y * w.y + f.z * w.z + f.w * w.w + __ldg(a.loc_b + c);
+      }
+    if (a.loc_lin) st24(a.loc_lin + static_cast<size_t>(row) * kH, lane, v);
+    ln_accum(v, a.loc_g, a.loc_bb, lane, 1e-12f, acc, st[4], st[5]);
+  }
+  {
+    const int nt = static_cast<int>(a.nav_types[row]);
+    float e[24], t[24];
+    ld24(a.nav_emb + nt * kH, lane, e);
+    ld24(a.tok_emb1, lane, t);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) acc[i] += e[i] + t[i];
+  }
+  if (a.sum_pre) st24(a.sum_pre + static_cast<size_t>(row) * kH, lane, acc);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) v[i] = 0.f;
+  ln_accum(acc, a.out_g, a.out_b, lane, 1e-12f, v, st[6], st[7]);
+  st24(a.x_f32 + static_cast<size_t>(row) * kH, lane, v);
+  if (a.stats && lane < 8) {
+    float s = st[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s = (lane == i) ? st[i] : s;
+    a.stats[static_cast<size_t>(row) * 8 + lane] = s;
+  }
+}
+
+int pano_pack_fwd(const PanoPackArgs& a, cudaStream_t stream) {
+  if (a.rows <= 0) return ETP_OK;
+  ETP_REQUIRE(a.rgb_lin && a.loc_fts && a.nav_types && a.x_f32, "pano_pack: null argument");
+  pano_pack_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+
+__global__ void __launch_bounds__(256) node_pack_kernel(const NodePackArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= a.rows) return;
+  float f[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) f[j] = a.pos_fts[static_cast<size_t>(row) * 7 + j];
+  float v[24], acc[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const int c = ((i >> 2) * 32 + lane) * 4 + (i & 3);
+    float s = __ldg(a.pos_b + c);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) s += f[j] * __ldg(a.pos_w + c * 7 + j);
+    v[i] = s;
+  }
+  if (a.pos_lin) st24(a.pos_lin + static_cast<size_t>(row) * kH, lane, v);
+  ld24(a.img_fts + static_cast<size_t>(row) * kH, lane, acc);
+  {
+    float e[24];
+    ld24(a.step_emb + static_cast<size_t>(a.step_ids[row]) * kH, lane, e);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) acc[i] += e[i];
+  }
+  float mean, rstd;
+  ln_accum(v, a.pos_g, a.pos_bb, lane, 1e-12f, acc, mean, rstd);
+  st24(a.x_f32 + static_cast<size_t>(row) * kH, lane, acc);
+  if (a.x_bf16) st24_bf16(a.x_bf16 + static_cast<size_t>(row) * kH, lane, acc);
+  if (a.stats && lane == 0) {
+    a.stats[static_cast<size_t>(row) * 2] = mean;
+    a.stats[static_cast<size_t>(row) * 2 + 1] = rstd;
+  }
+}
+
+int node_pack_fwd(const NodePackArgs& a, cudaStream_t stream) {
+  if (a.rows <= 0) return ETP_OK;
+  ETP_REQUIRE(a.img_fts && a.step_ids && a.pos_fts && a.x_f32, "node_pack: null argument");
+  node_pack_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+
+__global__ void __launch_bounds__(256) sap_tail_kernel(const float* __restrict__ relu_out, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ w4,
+                                                        const float* __restrict__ b4, const uint8_t* __restrict__ visited,
+                                                        const uint8_t* __restrict__ valid, int rows,
+                                                        float* __restrict__ logits, float* __restrict__ mean_out,
+                                                        float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[24], h[24], w[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) h[i] = 0.f;
+  ld24(relu_out + static_cast<size_t>(row) * kH, lane, v);
+  float mean, rstd;
+  ln_accum(v, gamma, beta, lane, 1e-12f, h, mean, rstd);
+  ld24(w4, lane, w);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s += h[i] * w[i];
+  s = warp_sum(s) + b4[0];
+  if (lane == 0) {
+    const bool dead = (visited && visited[row]) || (valid && !valid[row]);
+    logits[row] = dead ? -INFINITY : s;
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+int sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, const float* w4, const float* b4,
+                 const uint8_t* visited, const uint8_t* valid, int rows, int H, float* logits, float* mean,
+                 float* rstd, cudaStream_t stream) {
+  ETP_REQUIRE(H == kH, "sap_tail: hidden size must be 768");
+  if (rows <= 0) return ETP_OK;
+  sap_tail_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(relu_out, gamma, beta, w4, b4, visited, valid, rows, logits, mean,
+                                                      rstd);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+
+}  // namespace etp
