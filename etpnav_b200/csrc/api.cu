@@ -6,6 +6,8 @@
 
 namespace etp {
 const char* last_error_cstr();
+int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream);
+int attention_dispatch(const AttnArgs& a, cudaStream_t stream);
 }
 
 using namespace etp;
@@ -53,8 +55,11 @@ ETP_API int etp_attention_fwd(const etp_attn_args* g, void* stream) {
   a.v = static_cast<const bf16*>(g->v); a.ldv = g->ldv;
   a.scale = g->scale; a.key_valid = g->key_valid; a.mask_value = g->mask_value;
   a.pair = g->pair; a.pair_w = g->pair_w; a.pair_b = g->pair_b;
+  a.pair_w_dev = g->pair_w_dev; a.pair_b_dev = g->pair_b_dev;
   a.out = static_cast<bf16*>(g->out); a.ldo = g->ldo; a.lse = g->lse;
-  return attention_fwd(a, S(stream));
+  if (g->impl == 1) return attention_fwd(a, S(stream));
+  if (g->impl == 2) return attention_tc_fwd(a, S(stream));
+  return attention_dispatch(a, S(stream));
 }
 
 ETP_API int etp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t H,

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnArgs a, in
   }
   __syncthreads();
 
+  const float pair_w = a.pair_w_dev ? __ldg(a.pair_w_dev) : a.pair_w;
+  const float pair_b = a.pair_b_dev ? __ldg(a.pair_b_dev) : a.pair_b;
   float* myq = qs + warp * kD;
   float* myp = ps + warp * sk_pad;
   const int nk = sk_pad / 32;
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnArgs a, in
           acc += myq[2 * d] * f.x + myq[2 * d + 1] * f.y;
         }
         s = acc + kb[j];
-        if (pair) s += a.pair_w * pair[j] + a.pair_b;
+        if (pair) s += pair_w * pair[j] + pair_b;
       }
       myp[j] = s;
       mx = fmaxf(mx, s);
@@ -121,6 +123,15 @@ int attention_fwd(const AttnArgs& a, cudaStream_t stream) {
   attention_fwd_kernel<<<grid, 256, smem, stream>>>(a, sk_pad);
   ETP_CHECK_CUDA(cudaGetLastError());
   return ETP_OK;
+}
+
+int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream);  // attention_tc.cu
+bool attention_tc_supported(const AttnArgs& a);
+
+int attention_dispatch(const AttnArgs& a, cudaStream_t stream) {
+  const bool tiny = a.Sk < 32 && a.Sq < 32;  // e.g. panorama views: not worth a 128-row tensor-core tile
+  if (!tiny && attention_tc_supported(a)) return attention_tc_fwd(a, stream);
+  return attention_fwd(a, stream);
 }
 
 }  // namespace etp

@@ -89,6 +89,12 @@ int node_pack_fwd(const NodePackArgs& a, cudaStream_t stream);
 
 // SAP head tail: h = LN_1e-12(relu_out) ; logit = h . w4 + b4 ; -inf where visited or padded.
 // (vilmodel_cmt.py:654-658 net.2..net.4, :742-744)
+// word + position + token-type-0 embedding gather and LayerNorm (BertEmbeddings.forward, vilmodel_cmt.py:62-77)
+int embed_txt_fwd(const int64_t* ids, const float* word_emb, const float* pos_emb, const float* type_emb0,
+                  const float* gamma, const float* beta, float eps, int B, int L, float* x_f32, bf16* x_bf16,
+                  float* sum_pre, float* stats, cudaStream_t stream);
+int seq_mask(const int64_t* lens, int B, int V, uint8_t* mask, cudaStream_t stream);  // mask[b,v] = v < lens[b]
+
 int sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, const float* w4, const float* b4,
                  const uint8_t* visited, const uint8_t* valid, int rows, int H, float* logits, float* mean,
                  float* rstd, cudaStream_t stream);
@@ -107,6 +113,8 @@ struct AttnArgs {
   float mask_value = -10000.0f;        // added where key_valid == 0 (use -inf for nn.MultiheadAttention semantics)
   const float* pair = nullptr;         // [B, Sq, Sk] or null: bias += pair_w * pair + pair_b
   float pair_w = 0.0f, pair_b = 0.0f;
+  const float* pair_w_dev = nullptr;  // optional device scalars overriding pair_w / pair_b
+  const float* pair_b_dev = nullptr;
   bf16* out = nullptr;  // [B, Sq, ldo]
   int ldo = 0;
   float* lse = nullptr;  // [B, heads, Sq] log-sum-exp of the biased scores (saved for backward), may be null

@@ -189,3 +189,55 @@ int sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, c
 }
 
 }  // namespace etp
+
+namespace etp {
+
+__global__ void __launch_bounds__(256) embed_txt_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word_emb,
+                                                         const float* __restrict__ pos_emb, const float* __restrict__ type_emb0,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float eps, int rows, int L, float* __restrict__ x_f32,
+                                                         bf16* __restrict__ x_bf16, float* __restrict__ sum_pre,
+                                                         float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float w[24], p[24], t[24], v[24];
+  ld24(word_emb + static_cast<size_t>(ids[row]) * kH, lane, w);
+  ld24(pos_emb + static_cast<size_t>(row % L) * kH, lane, p);
+  ld24(type_emb0, lane, t);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { w[i] += p[i] + t[i]; v[i] = 0.f; }
+  if (sum_pre) st24(sum_pre + static_cast<size_t>(row) * kH, lane, w);
+  float mean, rstd;
+  ln_accum(w, gamma, beta, lane, eps, v, mean, rstd);
+  st24(x_f32 + static_cast<size_t>(row) * kH, lane, v);
+  if (x_bf16) st24_bf16(x_bf16 + static_cast<size_t>(row) * kH, lane, v);
+  if (stats && lane == 0) {
+    stats[static_cast<size_t>(row) * 2] = mean;
+    stats[static_cast<size_t>(row) * 2 + 1] = rstd;
+  }
+}
+
+int embed_txt_fwd(const int64_t* ids, const float* word_emb, const float* pos_emb, const float* type_emb0,
+                  const float* gamma, const float* beta, float eps, int B, int L, float* x_f32, bf16* x_bf16,
+                  float* sum_pre, float* stats, cudaStream_t stream) {
+  const int rows = B * L;
+  if (rows <= 0) return ETP_OK;
+  embed_txt_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, word_emb, pos_emb, type_emb0, gamma, beta, eps, rows, L,
+                                                       x_f32, x_bf16, sum_pre, stats);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+
+__global__ void seq_mask_kernel(const int64_t* __restrict__ lens, int B, int V, uint8_t* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * V) mask[i] = (i % V) < lens[i / V] ? 1 : 0;
+}
+int seq_mask(const int64_t* lens, int B, int V, uint8_t* mask, cudaStream_t stream) {
+  if (B * V <= 0) return ETP_OK;
+  seq_mask_kernel<<<(B * V + 255) / 256, 256, 0, stream>>>(lens, B, V, mask);
+  ETP_CHECK_CUDA(cudaGetLastError());
+  return ETP_OK;
+}
+
+}  // namespace etp

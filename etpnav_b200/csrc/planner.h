@@ -1,0 +1,89 @@
+// Saved-activation records and helpers shared by the step-level forward (planner.cu) and backward
+// (planner_bwd.cu) sequencing code.
+#pragma once
+#include <vector>
+
+#include "host.h"
+#include "ops.h"
+
+namespace etp {
+
+constexpr int kH = 768;      // hidden size
+constexpr int kI = 3072;     // FFN intermediate size
+constexpr int kHeads = 12;   // heads of 64
+
+// Bump allocator over a caller-owned device buffer (256-byte aligned slices).  With base == nullptr it
+// only measures.
+struct Arena {
+  uint8_t* base;
+  size_t cap;
+  size_t off = 0;
+  Arena(void* b, size_t c) : base(static_cast<uint8_t*>(b)), cap(c) {}
+  template <typename T>
+  T* take(size_t n) {
+    const size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+// One post-LN block (cross-attention part only when `cross`): everything backward needs.
+struct LayerRecord {
+  bf16 *q = nullptr, *kv = nullptr, *ctx1 = nullptr;  // cross-attn: q [rows,768], k|v [kv_rows,1536], context
+  float* lse1 = nullptr;
+  float* t1 = nullptr;   // pre-LayerNorm sum (fp32)
+  float* st1 = nullptr;  // mean[rows], rstd[rows]
+  bf16* ab = nullptr;    // LN output (bf16) = input of the self-attention block
+  bf16 *qkv = nullptr, *ctx2 = nullptr;
+  float* lse2 = nullptr;
+  float* t2 = nullptr;
+  float* st2 = nullptr;
+  bf16* cb = nullptr;
+  bf16 *pre = nullptr, *h = nullptr;  // FFN pre-activation / GELU output [rows,3072]
+  float* t3 = nullptr;
+  float* st3 = nullptr;
+  bf16* xb = nullptr;  // block output (bf16)
+  void carve(Arena& ar, int rows, int kv_rows, int B, int Sq, bool cross);
+};
+
+struct NavRecord {
+  bf16* txtb = nullptr;
+  bf16* x0b = nullptr;
+  float *pos_lin = nullptr, *pos_stats = nullptr;
+  float *xa = nullptr, *xc = nullptr, *xf = nullptr;  // fp32 residual-stream scratch
+  float *relu = nullptr, *sap_stats = nullptr;
+  std::vector<LayerRecord> layers;
+  void carve(Arena& ar, int B, int N, int L, int X, bool training);
+};
+
+struct PanoLayerRecord {
+  bf16* y1b = nullptr;
+  float* st1 = nullptr;
+  bf16 *qkv = nullptr, *ctx = nullptr;
+  float* lse = nullptr;
+  bf16* y2b = nullptr;
+  float* st2 = nullptr;
+  bf16 *pre = nullptr, *h = nullptr;
+};
+struct PanoRecord {
+  bf16 *rgbb = nullptr, *depb = nullptr;
+  float *rgb_lin = nullptr, *dep_lin = nullptr, *loc_lin = nullptr, *sum_pre = nullptr, *stats = nullptr;
+  std::vector<float*> xs;  // fp32 residual stream after packing / after each half-layer
+  float* fin_stats = nullptr;
+  std::vector<PanoLayerRecord> layers;
+  void carve(Arena& ar, int B, int V, int P, bool training);
+};
+
+struct TxtRecord {
+  float *sum_pre = nullptr, *emb_stats = nullptr;
+  bf16* x0b = nullptr;
+  float *xa = nullptr, *xc = nullptr;
+  std::vector<LayerRecord> layers;
+  void carve(Arena& ar, int B, int L, int NL, bool training);
+};
+
+// tcgen05 kernel when the shape allows it, CUDA-core kernel otherwise
+int attention_dispatch(const AttnArgs& a, cudaStream_t stream);
+
+}  // namespace etp

@@ -68,7 +68,7 @@ class AttnArgs(C.Structure):
     _fields_ = [("B", i32), ("heads", i32), ("Sq", i32), ("Sk", i32),
                 ("q", p_void), ("ldq", i32), ("k", p_void), ("ldk", i32), ("v", p_void), ("ldv", i32),
                 ("scale", f32), ("key_valid", p_void), ("mask_value", f32),
-                ("pair", p_f32), ("pair_w", f32), ("pair_b", f32),
+                ("pair", p_f32), ("pair_w", f32), ("pair_b", f32), ("pair_w_dev", p_f32), ("pair_b_dev", p_f32),
                 ("out", p_void), ("ldo", i32), ("lse", p_f32), ("impl", i32)]
 
 

@@ -1,0 +1,389 @@
+"""Drop-in host module for the ETPNav cross-modal planner on B200.
+
+``B200Planner`` exposes the three methods ``ETP.forward`` calls on ``self.vln_bert``
+(vlnce_baselines/models/Policy_ViewSelection_ETP.py:167,346,352-357) with the reference's positional
+signatures and return structures, and a ``state_dict()`` with the reference's 307 keys
+(vlnce_baselines/models/etp/vilmodel_cmt.py:663-750), so reference checkpoints load
+unchanged.  All arithmetic runs in the sm_100a kernels of ``libetpnav_b200.so`` through the step-level C
+ABI (include/etpnav_b200.h); PyTorch only owns memory, streams and the autograd graph.  There is no
+PyTorch/CPU fallback: without the library or a B200 the methods raise.
+
+Numerics: GEMM operands are bf16 (fp32 accumulation in TMEM); the residual stream, LayerNorm, softmax,
+biases and all reductions are fp32.  fp32 master parameters live in one flat buffer (``layout.py``) whose
+bf16 image is refreshed whenever a parameter changes.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import lib as _L
+from .config import PlannerConfig
+from .layout import FlatLayout
+
+p_void, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+
+
+# ----------------------------------------------------------------------------------------------------
+# ctypes mirrors of the step-level structs in include/etpnav_b200.h
+# ----------------------------------------------------------------------------------------------------
+class LayerWeights(C.Structure):
+    _fields_ = [(n, p_void) for n in (
+        "xq_w", "xq_b", "xkv_w", "xkv_b", "xo_w", "xo_b", "xln_g", "xln_b",
+        "sqkv_w", "sqkv_b", "so_w", "so_b", "sln_g", "sln_b",
+        "f1_w", "f1_b", "f2_w", "f2_b", "fln_g", "fln_b")]
+
+
+class NavWeights(C.Structure):
+    _fields_ = [("num_x_layers", i32), ("ln_eps", f32), ("layers", C.POINTER(LayerWeights))] + [
+        (n, p_void) for n in ("pos_w", "pos_b", "pos_g", "pos_bb", "step_emb", "sprel_w", "sprel_b",
+                              "sap0_w", "sap0_b", "sap_g", "sap_bb", "sap4_w", "sap4_b")]
+
+
+class NavInputs(C.Structure):
+    _fields_ = [("B", i32), ("N", i32), ("L", i32)] + [
+        (n, p_void) for n in ("txt_embeds", "txt_masks", "gmap_step_ids", "gmap_img_fts", "gmap_pos_fts",
+                              "gmap_masks", "gmap_visited_masks", "gmap_pair_dists")]
+
+
+class PanoLayerWeights(C.Structure):
+    _fields_ = [(n, p_void) for n in ("in_w", "in_b", "out_w", "out_b", "l1_w", "l1_b", "l2_w", "l2_b",
+                                      "n1_g", "n1_b", "n2_g", "n2_b")]
+
+
+class PanoWeights(C.Structure):
+    _fields_ = [("num_pano_layers", i32), ("layer_eps", f32), ("layers", C.POINTER(PanoLayerWeights))] + [
+        (n, p_void) for n in ("img_w", "img_b", "dep_w", "dep_b", "loc_w", "loc_b", "img_g", "img_bb", "dep_g",
+                              "dep_bb", "loc_g", "loc_bb", "out_g", "out_bb", "nav_emb", "tok_emb1", "fin_g", "fin_b")]
+
+
+class PanoInputs(C.Structure):
+    _fields_ = [("B", i32), ("V", i32)] + [(n, p_void) for n in ("rgb_fts", "dep_fts", "loc_fts", "nav_types", "view_lens")]
+
+
+class TxtWeights(C.Structure):
+    _fields_ = [("num_l_layers", i32), ("ln_eps", f32), ("layers", C.POINTER(LayerWeights))] + [
+        (n, p_void) for n in ("word_emb", "pos_emb", "type_emb0", "emb_g", "emb_b")]
+
+
+_declared = False
+
+
+def _declare():
+    global _declared
+    if _declared:
+        return
+    L = _L.lib()
+    L.etp_nav_saved_bytes.restype = C.c_size_t
+    L.etp_nav_saved_bytes.argtypes = [i32] * 5
+    L.etp_pano_saved_bytes.restype = C.c_size_t
+    L.etp_pano_saved_bytes.argtypes = [i32] * 4
+    L.etp_txt_saved_bytes.restype = C.c_size_t
+    L.etp_txt_saved_bytes.argtypes = [i32] * 4
+    L.etp_forward_navigation.argtypes = [C.POINTER(NavWeights), C.POINTER(NavInputs), p_void, p_void, p_void,
+                                         C.c_size_t, i32, p_void]
+    L.etp_forward_panorama.argtypes = [C.POINTER(PanoWeights), C.POINTER(PanoInputs), p_void, p_void, p_void,
+                                       C.c_size_t, i32, p_void]
+    L.etp_forward_txt.argtypes = [C.POINTER(TxtWeights), p_void, p_void, i32, i32, p_void, p_void, C.c_size_t, i32,
+                                  p_void]
+    _declared = True
+
+
+class _Holder(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter names."""
+
+
+def _f32c(t):
+    return t.detach().float().contiguous()
+
+
+class B200Planner(nn.Module):
+    """Replacement for ``GlocalTextPathNavCMT`` (vilmodel_cmt.py:663)."""
+
+    def __init__(self, config: PlannerConfig, device="cuda"):
+        super().__init__()
+        self.config = config
+        self.layout = FlatLayout(config)
+        dev = torch.device(device)
+        flat = torch.zeros(self.layout.total, dtype=torch.float32, device=dev)
+        self._build_tree(flat)
+        self._reset_parameters()
+        self._cache_key = None
+        self._structs = None
+        if config.fix_lang_embedding:  # vilmodel_cmt.py:675-679
+            for n, p in self.named_parameters():
+                if n.startswith("embeddings.") or n.startswith("lang_encoder."):
+                    p.requires_grad = False
+        if config.fix_pano_embedding:  # vilmodel_cmt.py:680-682
+            for n, p in self.named_parameters():
+                if n.startswith("img_embeddings."):
+                    p.requires_grad = False
+
+    # ------------------------------------------------------------------ parameters / flat storage
+    def _build_tree(self, flat):
+        self._flat = flat
+        self._flat_bf16 = torch.empty(self.layout.total, dtype=torch.bfloat16, device=flat.device)
+        self._pmap = {}
+        for name, (off, numel, shape) in self.layout.entries.items():
+            parts = name.split(".")
+            mod = self
+            for part in parts[:-1]:
+                if not hasattr(mod, part):
+                    mod.add_module(part, _Holder())
+                mod = getattr(mod, part)
+            p = nn.Parameter(flat[off:off + numel].view(shape))
+            mod.register_parameter(parts[-1], p)
+            self._pmap[name] = p
+
+    def _reset_parameters(self):
+        """HF ``_init_weights`` semantics: N(0, 0.02) weights, zero biases, LayerNorm (1, 0)."""
+        with torch.no_grad():
+            for name, p in self._pmap.items():
+                is_ln = ("LayerNorm" in name or "layer_norm" in name or ".norm" in name
+                         or name.startswith("global_encoder.gmap_pos_embeddings.1")
+                         or name.startswith("global_sap_head.net.2"))
+                if is_ln:
+                    p.fill_(1.0 if name.endswith("weight") else 0.0)
+                elif name.endswith("bias"):
+                    p.zero_()
+                else:
+                    p.normal_(0.0, 0.02)
+            self._pmap["embeddings.word_embeddings.weight"][0].zero_()
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        # .to()/.cuda()/.float() re-materialise every parameter separately: re-pack them into one flat buffer
+        first = next(iter(self._pmap.values()))
+        if first.data_ptr() != self._flat.data_ptr() + 4 * self.layout.offset(next(iter(self._pmap))):
+            flat = torch.zeros(self.layout.total, dtype=torch.float32, device=first.device)
+            for name, (off, numel, shape) in self.layout.entries.items():
+                p = self._pmap[name]
+                flat[off:off + numel].copy_(p.data.reshape(-1).float())
+                p.data = flat[off:off + numel].view(shape)
+            self._flat = flat
+            self._flat_bf16 = torch.empty(self.layout.total, dtype=torch.bfloat16, device=flat.device)
+            self._cache_key = None
+            self._structs = None
+        return out
+
+    def _flat_is_intact(self):
+        base = self._flat.data_ptr()
+        for name, (off, _, _) in self.layout.entries.items():
+            if self._pmap[name].data_ptr() != base + 4 * off:
+                return False
+        return True
+
+    def _refresh_cache(self):
+        """Re-cast the flat fp32 parameters to bf16 when any parameter changed (optimizer step, load)."""
+        key = tuple(p._version for p in self._pmap.values())
+        if key == self._cache_key and self._structs is not None:
+            return
+        if not self._flat.is_cuda:
+            raise _L.EtpError("B200Planner parameters must live on a CUDA device (no CPU path exists)")
+        if not self._flat_is_intact():
+            raise _L.EtpError("a parameter was re-allocated outside the flat buffer; call module._apply/.to() again")
+        _L.require_device()
+        _declare()
+        _L.cast_bf16(self._flat, self._flat_bf16)
+        self._cache_key = key
+        if self._structs is None:
+            self._structs = self._build_structs()
+
+    # ------------------------------------------------------------------ ctypes weight structs
+    def _w32(self, name):
+        return C.c_void_p(self._flat.data_ptr() + 4 * self.layout.offset(name))
+
+    def _w16(self, name):
+        return C.c_void_p(self._flat_bf16.data_ptr() + 2 * self.layout.offset(name))
+
+    def _layer_struct(self, att, out, inter, outp, cross=None):
+        lw = LayerWeights()
+        if cross is not None:
+            lw.xq_w, lw.xq_b = self._w16(cross + "att.query.weight"), self._w32(cross + "att.query.bias")
+            lw.xkv_w, lw.xkv_b = self._w16(cross + "att.key.weight"), self._w32(cross + "att.key.bias")
+            assert (self.layout.offset(cross + "att.value.weight")
+                    == self.layout.offset(cross + "att.key.weight") + 768 * 768)
+            lw.xo_w, lw.xo_b = self._w16(cross + "output.dense.weight"), self._w32(cross + "output.dense.bias")
+            lw.xln_g, lw.xln_b = self._w32(cross + "output.LayerNorm.weight"), self._w32(cross + "output.LayerNorm.bias")
+        lw.sqkv_w, lw.sqkv_b = self._w16(att + "query.weight"), self._w32(att + "query.bias")
+        assert self.layout.offset(att + "value.weight") == self.layout.offset(att + "query.weight") + 2 * 768 * 768
+        assert self.layout.offset(att + "value.bias") == self.layout.offset(att + "query.bias") + 2 * 768
+        lw.so_w, lw.so_b = self._w16(out + "dense.weight"), self._w32(out + "dense.bias")
+        lw.sln_g, lw.sln_b = self._w32(out + "LayerNorm.weight"), self._w32(out + "LayerNorm.bias")
+        lw.f1_w, lw.f1_b = self._w16(inter + "dense.weight"), self._w32(inter + "dense.bias")
+        lw.f2_w, lw.f2_b = self._w16(outp + "dense.weight"), self._w32(outp + "dense.bias")
+        lw.fln_g, lw.fln_b = self._w32(outp + "LayerNorm.weight"), self._w32(outp + "LayerNorm.bias")
+        return lw
+
+    def _build_structs(self):
+        cfg = self.config
+        s = {}
+        X = cfg.num_x_layers
+        xl = (LayerWeights * max(X, 1))()
+        for i in range(X):
+            p = f"global_encoder.encoder.x_layers.{i}."
+            xl[i] = self._layer_struct(p + "visn_self_att.self.", p + "visn_self_att.output.", p + "visn_inter.",
+                                       p + "visn_output.", cross=p + "visual_attention.")
+        nw = NavWeights()
+        nw.num_x_layers, nw.ln_eps, nw.layers = X, cfg.layer_norm_eps, xl
+        nw.pos_w = self._w32("global_encoder.gmap_pos_embeddings.0.weight")
+        nw.pos_b = self._w32("global_encoder.gmap_pos_embeddings.0.bias")
+        nw.pos_g = self._w32("global_encoder.gmap_pos_embeddings.1.weight")
+        nw.pos_bb = self._w32("global_encoder.gmap_pos_embeddings.1.bias")
+        nw.step_emb = self._w32("global_encoder.gmap_step_embeddings.weight")
+        if cfg.graph_sprels:
+            nw.sprel_w = self._w32("global_encoder.sprel_linear.weight")
+            nw.sprel_b = self._w32("global_encoder.sprel_linear.bias")
+        nw.sap0_w, nw.sap0_b = self._w16("global_sap_head.net.0.weight"), self._w32("global_sap_head.net.0.bias")
+        nw.sap_g, nw.sap_bb = self._w32("global_sap_head.net.2.weight"), self._w32("global_sap_head.net.2.bias")
+        nw.sap4_w, nw.sap4_b = self._w32("global_sap_head.net.4.weight"), self._w32("global_sap_head.net.4.bias")
+        s["nav"], s["nav_layers"] = nw, xl
+
+        P = cfg.num_pano_layers
+        pl = (PanoLayerWeights * max(P, 1))()
+        for i in range(P):
+            p = f"img_embeddings.pano_encoder.layers.{i}."
+            w = PanoLayerWeights()
+            w.in_w, w.in_b = self._w16(p + "self_attn.in_proj_weight"), self._w32(p + "self_attn.in_proj_bias")
+            w.out_w, w.out_b = self._w16(p + "self_attn.out_proj.weight"), self._w32(p + "self_attn.out_proj.bias")
+            w.l1_w, w.l1_b = self._w16(p + "linear1.weight"), self._w32(p + "linear1.bias")
+            w.l2_w, w.l2_b = self._w16(p + "linear2.weight"), self._w32(p + "linear2.bias")
+            w.n1_g, w.n1_b = self._w32(p + "norm1.weight"), self._w32(p + "norm1.bias")
+            w.n2_g, w.n2_b = self._w32(p + "norm2.weight"), self._w32(p + "norm2.bias")
+            pl[i] = w
+        pw = PanoWeights()
+        pw.num_pano_layers, pw.layer_eps, pw.layers = P, cfg.pano_layer_norm_eps, pl
+        e = "img_embeddings."
+        pw.img_w, pw.img_b = self._w16(e + "img_linear.weight"), self._w32(e + "img_linear.bias")
+        if cfg.use_depth_embedding:
+            pw.dep_w, pw.dep_b = self._w16(e + "dep_linear.weight"), self._w32(e + "dep_linear.bias")
+            pw.dep_g, pw.dep_bb = self._w32(e + "dep_layer_norm.weight"), self._w32(e + "dep_layer_norm.bias")
+        pw.loc_w, pw.loc_b = self._w32(e + "loc_linear.weight"), self._w32(e + "loc_linear.bias")
+        pw.img_g, pw.img_bb = self._w32(e + "img_layer_norm.weight"), self._w32(e + "img_layer_norm.bias")
+        pw.loc_g, pw.loc_bb = self._w32(e + "loc_layer_norm.weight"), self._w32(e + "loc_layer_norm.bias")
+        pw.out_g, pw.out_bb = self._w32(e + "layer_norm.weight"), self._w32(e + "layer_norm.bias")
+        pw.nav_emb = self._w32(e + "nav_type_embedding.weight")
+        pw.tok_emb1 = C.c_void_p(self._w32("embeddings.token_type_embeddings.weight").value + 4 * 768)
+        if P > 0:
+            pw.fin_g, pw.fin_b = self._w32(e + "pano_encoder.norm.weight"), self._w32(e + "pano_encoder.norm.bias")
+        s["pano"], s["pano_layers"] = pw, pl
+
+        NL = cfg.num_l_layers
+        tl = (LayerWeights * max(NL, 1))()
+        for i in range(NL):
+            p = f"lang_encoder.layer.{i}."
+            tl[i] = self._layer_struct(p + "attention.self.", p + "attention.output.", p + "intermediate.", p + "output.")
+        tw = TxtWeights()
+        tw.num_l_layers, tw.ln_eps, tw.layers = NL, cfg.layer_norm_eps, tl
+        tw.word_emb = self._w32("embeddings.word_embeddings.weight")
+        tw.pos_emb = self._w32("embeddings.position_embeddings.weight")
+        tw.type_emb0 = self._w32("embeddings.token_type_embeddings.weight")
+        tw.emb_g, tw.emb_b = self._w32("embeddings.LayerNorm.weight"), self._w32("embeddings.LayerNorm.bias")
+        s["txt"], s["txt_layers"] = tw, tl
+        return s
+
+    # ------------------------------------------------------------------ the three reference methods
+    @staticmethod
+    def _mask_u8(m):
+        m = m.contiguous()
+        return m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+
+    def _needs_grad(self, *tensors):
+        if not torch.is_grad_enabled():
+            return False
+        return any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters())
+
+    def forward_txt(self, txt_ids, txt_masks):
+        """vilmodel_cmt.py:684-688.  txt_ids int64 [B,L], txt_masks bool [B,L] -> txt_embeds fp32 [B,L,768]."""
+        self._refresh_cache()
+        B, Lt = txt_ids.shape
+        if Lt > self.config.max_position_embeddings:
+            raise ValueError("sequence longer than max_position_embeddings")
+        ids = txt_ids.contiguous().long()
+        mk = self._mask_u8(txt_masks)
+        out = torch.empty(B, Lt, 768, device=ids.device, dtype=torch.float32)
+        L = _L.lib()
+        nbytes = L.etp_txt_saved_bytes(B, Lt, self.config.num_l_layers, 0)
+        saved = torch.empty(nbytes, dtype=torch.uint8, device=ids.device)
+        _L._check(L.etp_forward_txt(C.byref(self._structs["txt"]), _L.ptr(ids), _L.ptr(mk), B, Lt, _L.ptr(out),
+                                    _L.ptr(saved), nbytes, 0, _L.stream_ptr()), "etp_forward_txt")
+        return out
+
+    def forward_panorama(self, rgb_fts, dep_fts, loc_fts, nav_types, view_lens):
+        """vilmodel_cmt.py:690-719 -> (pano_embeds fp32 [B,V,768], pano_masks bool [B,V])."""
+        self._refresh_cache()
+        B, V = rgb_fts.shape[:2]
+        rgb, dep, loc = _f32c(rgb_fts), _f32c(dep_fts), _f32c(loc_fts)
+        nt, vl = nav_types.contiguous().long(), view_lens.contiguous().long()
+        out = torch.empty(B, V, 768, device=rgb.device, dtype=torch.float32)
+        masks = torch.empty(B, V, device=rgb.device, dtype=torch.uint8)
+        pi = PanoInputs()
+        pi.B, pi.V = B, V
+        pi.rgb_fts, pi.dep_fts, pi.loc_fts = _L.ptr(rgb), _L.ptr(dep), _L.ptr(loc)
+        pi.nav_types, pi.view_lens = _L.ptr(nt), _L.ptr(vl)
+        L = _L.lib()
+        nbytes = L.etp_pano_saved_bytes(B, V, self.config.num_pano_layers, 0)
+        saved = torch.empty(nbytes, dtype=torch.uint8, device=rgb.device)
+        _L._check(L.etp_forward_panorama(C.byref(self._structs["pano"]), C.byref(pi), _L.ptr(out), _L.ptr(masks),
+                                         _L.ptr(saved), nbytes, 0, _L.stream_ptr()), "etp_forward_panorama")
+        return out, masks.view(torch.bool)
+
+    def forward_navigation(self, txt_embeds, txt_masks, gmap_vpids, gmap_step_ids, gmap_img_fts, gmap_pos_fts,
+                           gmap_masks, gmap_visited_masks, gmap_pair_dists):
+        """vilmodel_cmt.py:721-750 -> {'gmap_embeds': fp32 [B,N,768], 'global_logits': fp32 [B,N]}.
+        ``gmap_vpids`` is accepted and ignored, as in the reference."""
+        self._refresh_cache()
+        B, N = gmap_img_fts.shape[:2]
+        Lt = txt_embeds.shape[1]
+        txt, img, pos, pd = _f32c(txt_embeds), _f32c(gmap_img_fts), _f32c(gmap_pos_fts), _f32c(gmap_pair_dists)
+        ni = NavInputs()
+        ni.B, ni.N, ni.L = B, N, Lt
+        tm, gm, vm = self._mask_u8(txt_masks), self._mask_u8(gmap_masks), self._mask_u8(gmap_visited_masks)
+        ids = gmap_step_ids.contiguous().long()
+        ni.txt_embeds, ni.txt_masks, ni.gmap_step_ids = _L.ptr(txt), _L.ptr(tm), _L.ptr(ids)
+        ni.gmap_img_fts, ni.gmap_pos_fts, ni.gmap_masks = _L.ptr(img), _L.ptr(pos), _L.ptr(gm)
+        ni.gmap_visited_masks, ni.gmap_pair_dists = _L.ptr(vm), _L.ptr(pd)
+        embeds = torch.empty(B, N, 768, device=img.device, dtype=torch.float32)
+        logits = torch.empty(B, N, device=img.device, dtype=torch.float32)
+        L = _L.lib()
+        nbytes = L.etp_nav_saved_bytes(B, N, Lt, self.config.num_x_layers, 0)
+        saved = torch.empty(nbytes, dtype=torch.uint8, device=img.device)
+        _L._check(L.etp_forward_navigation(C.byref(self._structs["nav"]), C.byref(ni), _L.ptr(embeds), _L.ptr(logits),
+                                           _L.ptr(saved), nbytes, 0, _L.stream_ptr()), "etp_forward_navigation")
+        return {"gmap_embeds": embeds, "global_logits": logits}
+
+
+def get_vlnbert_models(config=None):
+    """Replacement for ``vlnbert_init.get_vlnbert_models`` (vlnce_baselines/models/etp/vlnbert_init.py:13-66).
+
+    ``config`` carries ``pretrained_path, task_type, use_depth_embedding, use_sprels, fix_lang_embedding,
+    fix_pano_embedding`` like the reference's model config.  Checkpoint keys are remapped the same way:
+    ``module.`` stripped (:24-25), then HF's ``bert.`` base-model prefix stripped (what
+    ``from_pretrained(state_dict=...)`` does for the ``bert.``-prefixed pre-training keys)."""
+    cfg = PlannerConfig.for_task(getattr(config, "task_type", "r2r"),
+                                 use_depth_embedding=getattr(config, "use_depth_embedding", True),
+                                 graph_sprels=getattr(config, "use_sprels", True),
+                                 fix_lang_embedding=getattr(config, "fix_lang_embedding", False),
+                                 fix_pano_embedding=getattr(config, "fix_pano_embedding", False))
+    cfg.update_lang_bert = not cfg.fix_lang_embedding
+    model = B200Planner(cfg)
+    path = getattr(config, "pretrained_path", None)
+    if path is not None:
+        ckpt = torch.load(path, map_location="cpu")
+        model.load_state_dict(remap_checkpoint_keys(ckpt, model.state_dict().keys()), strict=False)
+    return model
+
+
+def remap_checkpoint_keys(ckpt, own_keys):
+    own = set(own_keys)
+    out = {}
+    for k, v in ckpt.items():
+        if k.startswith("module."):
+            k = k[7:]
+        for pre in ("", "bert.", "net.vln_bert.", "net.module.vln_bert.", "vln_bert."):
+            if pre and k.startswith(pre) and k[len(pre):] in own:
+                k = k[len(pre):]
+                break
+        if k in own:
+            out[k] = v
+    return out

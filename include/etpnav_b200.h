@@ -83,6 +83,8 @@ typedef struct {
   float mask_value;
   const float* pair;         /* [B,Sq,Sk] or NULL */
   float pair_w, pair_b;
+  const float* pair_w_dev;   /* optional DEVICE scalars overriding pair_w / pair_b (sprel_linear params) */
+  const float* pair_b_dev;
   void* out; int32_t ldo;
   float* lse;                /* [B,heads,Sq] or NULL */
   int32_t impl;
@@ -126,6 +128,115 @@ int etp_node_pack_fwd(const etp_node_pack_args* args, void* stream);
 int etp_sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, const float* w4, const float* b4,
                      const uint8_t* visited, const uint8_t* valid, int32_t rows, int32_t H, float* logits,
                      float* mean, float* rstd, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * step level: one call = one reference method
+ * ------------------------------------------------------------------------------------------- */
+
+/* One post-LN BERT-style block.  Used three ways:
+ *   - GraphLXRTXLayer (vilmodel_cmt.py:365-398): cross-attention (x*) + self-attention (s*) + FFN (f*)
+ *   - BertLayer of the language encoder (vilmodel_cmt.py:195-208): x* pointers NULL
+ * GEMM weights are bf16 [out,in] row-major; q|k|v (and key|value) are concatenated along `out`
+ * by the host at weight-cache time (the fp32 master parameters keep the reference's separate names).
+ * biases / LayerNorm affine are fp32. */
+typedef struct {
+  const void* xq_w;   const float* xq_b;    /* visual_attention.att.query            [768,768]  */
+  const void* xkv_w;  const float* xkv_b;   /* visual_attention.att.key|value        [1536,768] */
+  const void* xo_w;   const float* xo_b;    /* visual_attention.output.dense         [768,768]  */
+  const float* xln_g; const float* xln_b;   /* visual_attention.output.LayerNorm                */
+  const void* sqkv_w; const float* sqkv_b;  /* (visn_self_att.self|attention.self).query|key|value [2304,768] */
+  const void* so_w;   const float* so_b;    /* (visn_self_att|attention).output.dense           */
+  const float* sln_g; const float* sln_b;
+  const void* f1_w;   const float* f1_b;    /* (visn_inter|intermediate).dense       [3072,768] */
+  const void* f2_w;   const float* f2_b;    /* (visn_output|output).dense            [768,3072] */
+  const float* fln_g; const float* fln_b;
+} etp_layer_weights;
+
+/* GlobalMapEncoder + CrossmodalEncoder + NextActionPrediction (vilmodel_cmt.py:566-579,435-452,651-661) */
+typedef struct {
+  int32_t num_x_layers;
+  float ln_eps;                       /* config.layer_norm_eps: 1e-12 BERT, 1e-5 XLM-R */
+  const etp_layer_weights* layers;    /* HOST array [num_x_layers] */
+  const float* pos_w; const float* pos_b; const float* pos_g; const float* pos_bb;  /* gmap_pos_embeddings.{0,1} */
+  const float* step_emb;              /* gmap_step_embeddings.weight [100,768] */
+  const float* sprel_w; const float* sprel_b;  /* sprel_linear scalars (device) or NULL when !use_sprels */
+  const void* sap0_w; const float* sap0_b;     /* global_sap_head.net.0 [768,768] bf16 */
+  const float* sap_g; const float* sap_bb;     /* global_sap_head.net.2 LayerNorm */
+  const float* sap4_w; const float* sap4_b;    /* global_sap_head.net.4 [1,768], [1] */
+} etp_nav_weights;
+
+typedef struct {
+  int32_t B, N, L;
+  const float* txt_embeds;            /* [B,L,768] */
+  const uint8_t* txt_masks;           /* [B,L] 1 = token */
+  const int64_t* gmap_step_ids;       /* [B,N] */
+  const float* gmap_img_fts;          /* [B,N,768] */
+  const float* gmap_pos_fts;          /* [B,N,7] */
+  const uint8_t* gmap_masks;          /* [B,N] */
+  const uint8_t* gmap_visited_masks;  /* [B,N] */
+  const float* gmap_pair_dists;       /* [B,N,N] */
+} etp_nav_inputs;
+
+/* Bytes of the activation record forward_navigation writes (and backward reads) when training != 0;
+ * with training == 0 the size of the scratch the forward needs. */
+size_t etp_nav_saved_bytes(int32_t B, int32_t N, int32_t L, int32_t num_x_layers, int32_t training);
+/* GlocalTextPathNavCMT.forward_navigation (vilmodel_cmt.py:721-750).
+ * outputs: gmap_embeds fp32 [B,N,768], global_logits fp32 [B,N] (-inf at visited / padded nodes). */
+int etp_forward_navigation(const etp_nav_weights* w, const etp_nav_inputs* in, float* gmap_embeds,
+                           float* global_logits, void* saved, size_t saved_bytes, int32_t training, void* stream);
+
+/* ImageEmbeddings + pano encoder (vilmodel_cmt.py:454-486; common/transformer.py:127-182) */
+typedef struct {
+  const void* in_w;  const float* in_b;    /* self_attn.in_proj_weight [2304,768] bf16, in_proj_bias */
+  const void* out_w; const float* out_b;   /* self_attn.out_proj */
+  const void* l1_w;  const float* l1_b;    /* linear1 [3072,768] */
+  const void* l2_w;  const float* l2_b;    /* linear2 [768,3072] */
+  const float* n1_g; const float* n1_b; const float* n2_g; const float* n2_b;  /* norm1, norm2 (eps 1e-5) */
+} etp_pano_layer_weights;
+
+typedef struct {
+  int32_t num_pano_layers;
+  float layer_eps;                          /* 1e-5: nn.LayerNorm default inside the pano layers */
+  const etp_pano_layer_weights* layers;     /* HOST array */
+  const void* img_w; const float* img_b;    /* img_linear [768,512] bf16 */
+  const void* dep_w; const float* dep_b;    /* dep_linear [768,128] bf16 or NULL (use_depth_embedding false) */
+  const float* loc_w; const float* loc_b;   /* loc_linear [768,4] fp32 */
+  const float* img_g; const float* img_bb; const float* dep_g; const float* dep_bb;
+  const float* loc_g; const float* loc_bb; const float* out_g; const float* out_bb;  /* 4 LayerNorms, eps 1e-12 */
+  const float* nav_emb;                     /* nav_type_embedding.weight [2,768] */
+  const float* tok_emb1;                    /* embeddings.token_type_embeddings.weight row 1 */
+  const float* fin_g; const float* fin_b;   /* pano_encoder.norm (eps 1e-12) */
+} etp_pano_weights;
+
+typedef struct {
+  int32_t B, V;
+  const float* rgb_fts;       /* [B,V,512] */
+  const float* dep_fts;       /* [B,V,128] */
+  const float* loc_fts;       /* [B,V,4]   */
+  const int64_t* nav_types;   /* [B,V]     */
+  const int64_t* view_lens;   /* [B]       */
+} etp_pano_inputs;
+
+size_t etp_pano_saved_bytes(int32_t B, int32_t V, int32_t num_pano_layers, int32_t training);
+/* GlocalTextPathNavCMT.forward_panorama (vilmodel_cmt.py:690-719).
+ * outputs: pano_embeds fp32 [B,V,768], pano_masks uint8 [B,V] (= arange(V) < view_lens, common/ops.py:36-44). */
+int etp_forward_panorama(const etp_pano_weights* w, const etp_pano_inputs* in, float* pano_embeds,
+                         uint8_t* pano_masks, void* saved, size_t saved_bytes, int32_t training, void* stream);
+
+/* BertEmbeddings + LanguageEncoder (vilmodel_cmt.py:48-77,413-433) */
+typedef struct {
+  int32_t num_l_layers;
+  float ln_eps;
+  const etp_layer_weights* layers;  /* HOST array; x* members NULL */
+  const float* word_emb; const float* pos_emb; const float* type_emb0;  /* fp32 tables; type row 0 */
+  const float* emb_g; const float* emb_b;
+} etp_txt_weights;
+
+size_t etp_txt_saved_bytes(int32_t B, int32_t L, int32_t num_l_layers, int32_t training);
+/* GlocalTextPathNavCMT.forward_txt (vilmodel_cmt.py:684-688): txt_ids int64 [B,L], txt_masks uint8 [B,L]
+ * -> txt_embeds fp32 [B,L,768]. */
+int etp_forward_txt(const etp_txt_weights* w, const int64_t* txt_ids, const uint8_t* txt_masks, int32_t B, int32_t L,
+                    float* txt_embeds, void* saved, size_t saved_bytes, int32_t training, void* stream);
 
 #ifdef __cplusplus
 }
