@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Planner-step benchmark (contract: one JSON line on rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode train|fwd]
+
+Metric (BASELINE.json): planner steps/s at B=64 episodes per GPU, 12 views, 80-node graph, 200-token
+instruction, 6 cross-modal layers (BASELINE.json configs[2]; the reference checkpoints use 4 — pass
+``--x-layers 4``).  One *planner step* = forward_panorama + forward_navigation (+ backward of both and one
+AdamW update in ``train`` mode) on a batch of B episodes.  Synthetic seeded tensors
+(etpnav_b200/synth.py), random-init weights of the reference architecture.
+
+* ``value``  — steps/s with the step's inputs already resident in HBM (CUDA-event time over exactly K
+  steps, max over ranks, barrier + synchronize on both sides).
+* ``e2e``    — the same metric through the public module API with HOST inputs: pinned-host -> device copies
+  of every input tensor and a device -> host read of the node logits inside the timed region.
+* ``roofline`` — tcgen05 GEMM kernel: algorithmic FLOPs of its launches / their CUDA-event time (measured
+  in a separate profiled pass of the same step) against the measured bf16 peak of MEASURED_PEAKS.json.
+* ``cpu_baseline`` — the oracle port of the reference (oracle/planner_port.py, fp32, all host cores) on a
+  bounded sample of the same workload.  ``--impl reference`` runs ONLY that CPU arm.
+Data-parallel (N > 1): every rank runs its own batch of B episodes (weak scaling); in ``train`` mode the
+flat gradient buffer of the step's parameters is all-reduced once over NCCL before AdamW.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from etpnav_b200.config import PlannerConfig            # noqa: E402
+from etpnav_b200.synth import make_inputs, make_weights, step_flops  # noqa: E402
+
+METRIC = "planner steps/sec (B=64,12v,80n,200t)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default=None, choices=["train", "fwd"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--views", type=int, default=12)
+    ap.add_argument("--nodes", type=int, default=80)
+    ap.add_argument("--tokens", type=int, default=200)
+    ap.add_argument("--x-layers", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_cfg(a):
+    # text-side tensors are not part of the per-step path: keep the vocab small so set-up is fast
+    return PlannerConfig(vocab_size=2048, num_l_layers=0, num_x_layers=a.x_layers)
+
+
+def workload_name(a, mode):
+    what = "fwd+bwd+AdamW" if mode == "train" else "fwd"
+    return (f"planner step {what}: forward_panorama+forward_navigation, B={a.batch}/GPU, V={a.views}, N={a.nodes}, "
+            f"L={a.tokens}, {a.x_layers} cross layers")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if len(s) >= 6 and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) >= 6 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].startswith("Active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_time(a, mode, steps, warmup, max_seconds=25.0):
+    from oracle import planner_port as P  # test infrastructure, used here only as the timed CPU baseline
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    cfg = workload_cfg(a)
+    sd = make_weights(cfg, seed=0, skip_text=False)
+    inp = make_inputs(cfg, a.batch, a.views, a.nodes, a.tokens, seed=1, ragged=False)
+    if mode == "train":
+        sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        opt = torch.optim.AdamW([v for v in sd.values()], lr=1e-5)
+
+    def step():
+        if mode == "train":
+            opt.zero_grad(set_to_none=True)
+            pano, pm = P.forward_panorama(sd, cfg, inp["rgb_fts"], inp["dep_fts"], inp["loc_fts"], inp["nav_types"], inp["view_lens"])
+            nav = P.forward_navigation(sd, cfg, inp["txt_embeds"], inp["txt_masks"], None, inp["gmap_step_ids"],
+                                       inp["gmap_img_fts"], inp["gmap_pos_fts"], inp["gmap_masks"],
+                                       inp["gmap_visited_masks"], inp["gmap_pair_dists"])
+            loss = P.step_loss(nav["global_logits"], inp["labels"]) + (pano * pm[..., None]).sum() * 1e-3
+            loss.backward()
+            opt.step()
+        else:
+            with torch.no_grad():
+                P.forward_panorama(sd, cfg, inp["rgb_fts"], inp["dep_fts"], inp["loc_fts"], inp["nav_types"], inp["view_lens"])
+                P.forward_navigation(sd, cfg, inp["txt_embeds"], inp["txt_masks"], None, inp["gmap_step_ids"],
+                                     inp["gmap_img_fts"], inp["gmap_pos_fts"], inp["gmap_masks"],
+                                     inp["gmap_visited_masks"], inp["gmap_pair_dists"])
+
+    for _ in range(warmup):
+        step()
+    times = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > max_seconds:
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    return med, cores, len(times)
+
+
+def run_reference_arm(a, mode, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, 3))
+    med, cores, n = cpu_step_time(a, mode, steps, warmup=1, max_seconds=120.0)
+    val = 1.0 / med
+    sample = f"{n} timed step(s) after 1 warm-up of the full workload, median; oracle port of the reference, fp32, torch CPU"
+    line = {"metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": a.gpus, "steps": n, "warmup": 1,
+            "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(a, mode), "mode": mode},
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from etpnav_b200 import planner as PL
+    mode = a.mode or ("train" if hasattr(PL.B200Planner, "train_step") else "fwd")
+    if a.impl == "reference":
+        run_reference_arm(a, mode, rank)
+        return
+
+    from etpnav_b200 import lib as L
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    L.require_device()
+
+    cfg = workload_cfg(a)
+    model = PL.B200Planner(cfg, device=dev)
+    model.load_state_dict(make_weights(cfg, seed=0), strict=True)
+    B, V, N, Lt = a.batch, a.views, a.nodes, a.tokens
+    host = make_inputs(cfg, B, V, N, Lt, seed=100 + rank, ragged=False)
+    keys_pano = ["rgb_fts", "dep_fts", "loc_fts", "nav_types", "view_lens"]
+    keys_nav = ["txt_embeds", "txt_masks", "gmap_step_ids", "gmap_img_fts", "gmap_pos_fts", "gmap_masks",
+                "gmap_visited_masks", "gmap_pair_dists"]
+    pinned = {k: host[k].pin_memory() for k in keys_pano + keys_nav + ["labels"]}
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    logits_host = torch.empty(B, N, dtype=torch.float32).pin_memory()
+    d2h_bytes = logits_host.numel() * 4
+
+    if mode == "train":
+        model.train()
+        trainer = model.make_trainer(lr=1e-5, world_size=world)
+
+        def step(d):
+            return trainer.step(d)
+    else:
+        model.eval()
+
+        def step(d):
+            with torch.no_grad():
+                model.forward_panorama(*[d[k] for k in keys_pano])
+                out = model.forward_navigation(d["txt_embeds"], d["txt_masks"], None, d["gmap_step_ids"], d["gmap_img_fts"],
+                                               d["gmap_pos_fts"], d["gmap_masks"], d["gmap_visited_masks"], d["gmap_pair_dists"])
+            return out["global_logits"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(3, a.warmup)):
+        step(resident)
+    lib = L.lib()
+    lib.etp_launch_count.restype = __import__("ctypes").c_longlong
+    n0 = lib.etp_launch_count()
+    with Clocks(local) as clk:
+        total_ms = timed(lambda: step(resident), a.steps)
+    launches = lib.etp_launch_count() - n0
+    ms_per_step = total_ms / a.steps
+    value = world / (ms_per_step * 1e-3)
+
+    # end-to-end: host inputs -> H2D -> step -> D2H logits
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        lg = step(d)
+        logits_host.copy_(lg, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    e2e_ms = timed(e2e_step, a.steps) / a.steps
+    e2e_val = world / (e2e_ms * 1e-3)
+
+    # roofline of the dominant kernel (tcgen05 GEMM): profiled pass with per-launch CUDA events
+    import ctypes as C
+    lib.etp_prof_gemm_enable(1)
+    torch.cuda.synchronize()
+    prof_steps = min(a.steps, 5)
+    for _ in range(prof_steps):
+        step(resident)
+    torch.cuda.synchronize()
+    g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_longlong()
+    L._check(lib.etp_prof_gemm_collect(C.byref(g_ms), C.byref(g_fl), C.byref(g_n)), "etp_prof_gemm_collect")
+    lib.etp_prof_gemm_enable(0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
+    achieved = (g_fl.value / (g_ms.value * 1e-3)) / 1e12 if g_ms.value > 0 else 0.0
+    fl = step_flops(cfg, B, V, N, Lt)
+    roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "gemm_launches_per_step": g_n.value / prof_steps, "gemm_ms_per_step": g_ms.value / prof_steps,
+            "gemm_share_of_step": (g_ms.value / prof_steps) / ms_per_step,
+            "step_model_tflops": (fl["step_fwd"] * (3 if mode == "train" else 1)) / (ms_per_step * 1e-3) / 1e12}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            med, cores, n = cpu_step_time(a, mode, steps=3, warmup=1, max_seconds=25.0)
+            cpu = {"value": 1.0 / med, "unit": "steps/s", "cores": cores, "kind": "port",
+                   "sample": f"median of {n} full-size step(s) after 1 warm-up; oracle/planner_port.py fp32 on torch CPU"}
+        line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps,
+                "warmup": max(3, a.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": workload_name(a, mode), "mode": mode, "global_batch": B * world,
+                           "parallelism": f"dp{world}", "x_layers": a.x_layers,
+                           "l2": "no flush: per-step working set (activation record + bf16/fp32 weights) exceeds the 126 MB L2"},
+                "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": e2e_ms},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,8 @@
 
 namespace etp {
 const char* last_error_cstr();
+void prof_enable(bool on);
+int prof_collect(double* ms, double* flops, long long* count);
 int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream);
 int attention_dispatch(const AttnArgs& a, cudaStream_t stream);
 }
@@ -19,6 +21,13 @@ extern "C" {
 
 ETP_API int etp_version(void) { return 100; }
 ETP_API const char* etp_last_error(void) { return last_error_cstr(); }
+
+ETP_API long long etp_launch_count(void) { return g_launches.load(); }
+ETP_API void etp_prof_gemm_enable(int on) { prof_enable(on != 0); }
+ETP_API int etp_prof_gemm_collect(double* total_ms, double* total_flops, long long* launches) {
+  ETP_REQUIRE(total_ms && total_flops && launches, "etp_prof_gemm_collect: null argument");
+  return prof_collect(total_ms, total_flops, launches);
+}
 
 ETP_API int etp_check_device(void) {
   int dev = 0;

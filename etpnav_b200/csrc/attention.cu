@@ -121,7 +121,7 @@ int attention_fwd(const AttnArgs& a, cudaStream_t stream) {
   ETP_REQUIRE(smem <= 220 * 1024, "attention: K/V do not fit shared memory");
   dim3 grid((a.Sq + kQTile - 1) / kQTile, a.heads, a.B);
   attention_fwd_kernel<<<grid, 256, smem, stream>>>(a, sk_pad);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 

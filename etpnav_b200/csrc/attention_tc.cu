@@ -265,7 +265,7 @@ int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream) {
   d.pair_w_dev = a.pair_w_dev; d.pair_b_dev = a.pair_b_dev; d.out = a.out; d.ldo = a.ldo; d.lse = a.lse;
   dim3 grid((a.Sq + kBQ - 1) / kBQ, a.heads, a.B);
   attention_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, d);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 

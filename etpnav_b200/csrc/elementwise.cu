@@ -69,7 +69,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
   ETP_REQUIRE(H == kH, "layernorm: hidden size must be 768");
   if (rows <= 0) return ETP_OK;
   layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, eps, rows, y_f32, y_bf16, mean, rstd);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 
@@ -152,7 +152,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* gamma, const flo
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
   layernorm_bwd_kernel<<<grid, 256, 0, stream>>>(dy, x, gamma, mean, rstd, rows, dx_f32, accumulate_dx, dx_bf16, dgamma,
                                                  dbeta);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 
@@ -201,7 +201,7 @@ static int colsum_impl(const T* x, int rows, int cols, int ld, float* out, cudaS
   if (rpc < 64) rpc = 64;
   gy = (rows + rpc - 1) / rpc;
   colsum_kernel<T><<<dim3(gx, gy), 256, 0, stream>>>(x, rows, cols, ld, rpc, out);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 int colsum_bf16(const bf16* x, int rows, int cols, int ld, float* out, cudaStream_t stream) {
@@ -232,7 +232,7 @@ int cast_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream) {
     cast_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, n4);
   }
   if (n4 * 4 < n) cast_tail_kernel<<<1, 32, 0, stream>>>(x, y, n4 * 4, n);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 
@@ -246,7 +246,7 @@ int add_f32(float* dst, const float* src, int64_t n, cudaStream_t stream) {
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   add_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dst, src, n);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 

@@ -325,8 +325,10 @@ static int launch_gemm(const GemmArgs& a, const GemmDev& dev, cudaStream_t strea
   }
   const int tiles = dev.tiles_m * dev.tiles_n * dev.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  prof_gemm_begin(stream);
   kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, dev);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  prof_gemm_end(stream, 2.0 * a.M * a.N * a.K);
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 

@@ -112,6 +112,46 @@ int get_tmap_3d(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t
   return ETP_OK;
 }
 
+std::atomic<long long> g_launches{0};
+
+// ---- GEMM launch profiling (off by default) ----
+static bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; double flops; };
+static std::vector<ProfRec> g_prof;
+static cudaEvent_t g_prof_cur = nullptr;
+
+void prof_gemm_begin(cudaStream_t s) {
+  if (!g_prof_on) return;
+  cudaEventCreate(&g_prof_cur);
+  cudaEventRecord(g_prof_cur, s);
+}
+void prof_gemm_end(cudaStream_t s, double flops) {
+  if (!g_prof_on || !g_prof_cur) return;
+  ProfRec r;
+  r.a = g_prof_cur;
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.b, s);
+  r.flops = flops;
+  g_prof.push_back(r);
+  g_prof_cur = nullptr;
+}
+void prof_enable(bool on) { g_prof_on = on; }
+int prof_collect(double* ms, double* flops, long long* count) {
+  double t = 0, f = 0;
+  for (auto& r : g_prof) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return fail(ETP_ERR_CUDA, "prof_collect: event sync failed");
+    float e = 0;
+    cudaEventElapsedTime(&e, r.a, r.b);
+    t += e;
+    f += r.flops;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  *ms = t; *flops = f; *count = static_cast<long long>(g_prof.size());
+  g_prof.clear();
+  return ETP_OK;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 namespace etp {
@@ -26,6 +27,18 @@ int fail(int code, const std::string& msg);
     if (_e != cudaSuccess)                                                                         \
       return ::etp::fail(ETP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
+
+// every kernel launch site ends with this: counts the launch (bench.py reports gpu_launches) and checks it
+extern std::atomic<long long> g_launches;
+#define ETP_LAUNCHED()                                            \
+  do {                                                            \
+    ::etp::g_launches.fetch_add(1, std::memory_order_relaxed);    \
+    ETP_CHECK_CUDA(cudaGetLastError());                           \
+  } while (0)
+
+// optional per-launch CUDA-event timing of the tcgen05 GEMM (bench.py roofline leg)
+void prof_gemm_begin(cudaStream_t s);
+void prof_gemm_end(cudaStream_t s, double flops);
 
 #define ETP_REQUIRE(cond, msg)                                                     \
   do {                                                                             \

@@ -103,7 +103,7 @@ int pano_pack_fwd(const PanoPackArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return ETP_OK;
   ETP_REQUIRE(a.rgb_lin && a.loc_fts && a.nav_types && a.x_f32, "pano_pack: null argument");
   pano_pack_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 
@@ -145,7 +145,7 @@ int node_pack_fwd(const NodePackArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return ETP_OK;
   ETP_REQUIRE(a.img_fts && a.step_ids && a.pos_fts && a.x_f32, "node_pack: null argument");
   node_pack_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 
@@ -184,7 +184,7 @@ int sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, c
   if (rows <= 0) return ETP_OK;
   sap_tail_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(relu_out, gamma, beta, w4, b4, visited, valid, rows, logits, mean,
                                                       rstd);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 
@@ -225,7 +225,7 @@ int embed_txt_fwd(const int64_t* ids, const float* word_emb, const float* pos_em
   if (rows <= 0) return ETP_OK;
   embed_txt_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, word_emb, pos_emb, type_emb0, gamma, beta, eps, rows, L,
                                                        x_f32, x_bf16, sum_pre, stats);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 
@@ -236,7 +236,7 @@ __global__ void seq_mask_kernel(const int64_t* __restrict__ lens, int B, int V, 
 int seq_mask(const int64_t* lens, int B, int V, uint8_t* mask, cudaStream_t stream) {
   if (B * V <= 0) return ETP_OK;
   seq_mask_kernel<<<(B * V + 255) / 256, 256, 0, stream>>>(lens, B, V, mask);
-  ETP_CHECK_CUDA(cudaGetLastError());
+  ETP_LAUNCHED();
   return ETP_OK;
 }
 

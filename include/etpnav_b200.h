@@ -41,6 +41,12 @@ int etp_version(void);                /* 100 * major + minor */
 const char* etp_last_error(void);     /* text of the last error on this thread */
 /* 0 if the current CUDA device is sm_100 (B200); ETP_ERR_NO_DEVICE otherwise. */
 int etp_check_device(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long etp_launch_count(void);
+/* CUDA-event timing of every tcgen05 GEMM launch (for the roofline line of bench.py): enable, run steps,
+ * collect = synchronise and return total milliseconds / algorithmic flops / launch count, then reset. */
+void etp_prof_gemm_enable(int on);
+int etp_prof_gemm_collect(double* total_ms, double* total_flops, long long* launches);
 
 /* ---------------------------------------------------------------------------------------------
  * operator level
