@@ -121,4 +121,65 @@ struct AttnArgs {
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t stream);
 
+struct AttnBwdArgs {
+  int B = 0, heads = 12, Sq = 0, Sk = 0;
+  const bf16 *q = nullptr, *k = nullptr, *v = nullptr;  // as in the forward
+  int ldq = 0, ldk = 0, ldv = 0;
+  const bf16* out = nullptr;   // forward output (context), [B,Sq,ldo]
+  int ldo = 0;
+  const bf16* dout = nullptr;  // gradient of the context
+  int lddo = 0;
+  const float* lse = nullptr;  // [B,heads,Sq] from the forward
+  float* dvec = nullptr;       // scratch [B,heads,Sq]: D_i = sum_d dO*O
+  float scale = 0.125f;
+  const uint8_t* key_valid = nullptr;
+  float mask_value = -10000.0f;
+  const float* pair = nullptr;
+  float pair_w = 0.0f, pair_b = 0.0f;
+  const float* pair_w_dev = nullptr;
+  const float* pair_b_dev = nullptr;
+  bf16 *dq = nullptr, *dk = nullptr, *dv = nullptr;
+  int lddq = 0, lddk = 0, lddv = 0;
+  float* dpair_w = nullptr;  // += sum dS * pair   (sprel_linear.weight grad), device scalar or null
+  float* dpair_b = nullptr;  // += sum dS          (sprel_linear.bias grad)
+};
+int attention_bwd(const AttnBwdArgs& a, cudaStream_t stream);      // CUDA-core, any shape
+int attention_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t stream);
+
+// ---- backward of the packing / head kernels (pack_bwd.cu) -------------------------------------------
+// SAP tail backward: dlogits [rows] (entries of dead nodes are ignored) -> d(relu pre-activation) as bf16
+// [rows,768] (ReLU mask applied), accumulates dgamma/dbeta [768], dw4 [768], db4 [1].
+int sap_tail_bwd(const float* dlogits, const float* relu_out, const float* gamma, const float* beta, const float* w4,
+                 const float* mean, const float* rstd, const uint8_t* visited, const uint8_t* valid, int rows,
+                 bf16* dpre_bf16, float* dgamma, float* dbeta, float* dw4, float* db4, cudaStream_t stream);
+// node packing backward: dx [rows,768] -> dstep_emb (scatter-add), LN/Linear7 grads. d(img_fts) == dx.
+int node_pack_bwd(const float* dx, const int64_t* step_ids, const float* pos_fts, const float* pos_lin,
+                  const float* stats, const float* pos_g, int rows, float* dstep_emb, float* dpos_w, float* dpos_b,
+                  float* dpos_g, float* dpos_bb, cudaStream_t stream);
+struct PanoPackBwdArgs {
+  int rows = 0;
+  const float* dx = nullptr;        // grad of the packed token [rows,768]
+  const float *rgb_lin = nullptr, *dep_lin = nullptr, *loc_lin = nullptr, *sum_pre = nullptr, *stats = nullptr;
+  const float* loc_fts = nullptr;
+  const int64_t* nav_types = nullptr;
+  const float *img_g = nullptr, *dep_g = nullptr, *loc_g = nullptr, *out_g = nullptr;
+  bf16 *drgb_lin = nullptr, *ddep_lin = nullptr;  // grads of the two GEMM outputs (bf16, for dgrad/wgrad)
+  float *dimg_g = nullptr, *dimg_b = nullptr, *ddep_g = nullptr, *ddep_b = nullptr, *dloc_g = nullptr, *dloc_b = nullptr,
+        *dout_g = nullptr, *dout_b = nullptr;
+  float *dloc_w = nullptr, *dloc_bias = nullptr;  // [768,4], [768]
+  float *dnav_emb = nullptr, *dtok_emb1 = nullptr;
+};
+int pano_pack_bwd(const PanoPackBwdArgs& a, cudaStream_t stream);
+// embedding + LN backward of forward_txt: dx [rows,768] -> scatter-add into word / position / type-0 tables
+int embed_txt_bwd(const float* dx, const int64_t* ids, const float* sum_pre, const float* stats, const float* gamma,
+                  int B, int L, float* dword, float* dpos, float* dtype0, float* dgamma, float* dbeta,
+                  cudaStream_t stream);
+
+// ---- optimizer (adamw.cu) ----------------------------------------------------------------------------
+// torch.optim.AdamW semantics (decoupled weight decay, bias correction) over flat fp32 buffers; also refreshes
+// the bf16 image of the parameters.  grad_scale multiplies the gradient first (1/world_size after all-reduce).
+int adamw_step(float* param, bf16* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+               float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+               cudaStream_t stream);
+
 }  // namespace etp

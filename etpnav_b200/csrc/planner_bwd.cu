@@ -1,0 +1,337 @@
+// Step-level backward sequencing: the autograd counterparts of forward_navigation / forward_panorama /
+// forward_txt (planner.cu).  Reads the activation record the forward wrote, produces
+//   - parameter gradients, ACCUMULATED (+=) into a flat fp32 gradient buffer laid out like the parameters
+//     (the `g` structs below are the weight structs with every pointer redirected into that buffer),
+//   - gradients w.r.t. the live activations of the caller (txt_embeds, gmap_img_fts, rgb_fts, dep_fts).
+// dgrad = tcgen05 GEMM with the weight consumed MN-major as stored; wgrad = tcgen05 GEMM with both operands
+// MN-major, split-K, fp32 atomic accumulation; bias grads = column sums; LayerNorm / GELU / ReLU / softmax
+// backward fused into the neighbouring kernels where the data is already in registers.
+#include "../../include/etpnav_b200.h"
+#include "planner.h"
+
+namespace etp {
+
+#define ETP_TRY(expr)              \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != ETP_OK) return _rc; \
+  } while (0)
+
+struct BwdScratch {
+  float *g0 = nullptr, *g1 = nullptr, *g2 = nullptr;  // fp32 [rows,768]
+  bf16 *gb = nullptr, *dctx = nullptr, *dq = nullptr;  // bf16 [rows,768]
+  bf16* dqkv = nullptr;                                 // bf16 [rows,2304]
+  bf16* dpre = nullptr;                                 // bf16 [rows,3072]
+  bf16* dkv = nullptr;                                  // bf16 [kv_rows,1536]
+  float* dvec = nullptr;                                // fp32 [B,heads,S]
+  float* dtxt = nullptr;                                // fp32 [kv_rows,768]
+  void carve(Arena& ar, size_t rows, size_t kv_rows, size_t bhs) {
+    g0 = ar.take<float>(rows * kH); g1 = ar.take<float>(rows * kH); g2 = ar.take<float>(rows * kH);
+    gb = ar.take<bf16>(rows * kH); dctx = ar.take<bf16>(rows * kH); dq = ar.take<bf16>(rows * kH);
+    dqkv = ar.take<bf16>(rows * 3 * kH);
+    dpre = ar.take<bf16>(rows * kI);
+    dkv = ar.take<bf16>(kv_rows * 2 * kH);
+    dvec = ar.take<float>(bhs);
+    dtxt = ar.take<float>(kv_rows * kH);
+  }
+};
+
+// dX[rows, K_in] = dY[rows, N_out] . W[N_out, K_in]  (+ resid)   — W consumed MN-major as stored
+static int dgrad(const bf16* dY, int rows, int N_out, int ldy, const void* W, int K_in, const float* resid, float* out_f32,
+                 bf16* out_bf16, int aux_mode, const bf16* aux, cudaStream_t s) {
+  GemmArgs g;
+  g.M = rows; g.N = K_in; g.K = N_out;
+  g.A = dY; g.lda = ldy;
+  g.B = static_cast<const bf16*>(W); g.ldb = K_in; g.b_mn = 1;
+  g.resid = resid; g.ld_resid = K_in;
+  g.out_f32 = out_f32; g.ld_f32 = K_in;
+  g.out_bf16 = out_bf16; g.ld_bf16 = K_in;
+  g.aux_mode = aux_mode; g.aux = aux; g.ld_aux = K_in;
+  return gemm(g, s);
+}
+
+// dW[N_out, K_in] += dY[rows, N_out]^T . X[rows, K_in]   — both operands MN-major as stored; split-K atomics
+static int wgrad(const bf16* dY, int rows, int N_out, int ldy, const bf16* X, int K_in, int ldx, void* dW, cudaStream_t s) {
+  if (dW == nullptr) return ETP_OK;
+  GemmArgs g;
+  g.M = N_out; g.N = K_in; g.K = rows;
+  g.A = dY; g.lda = ldy; g.a_mn = 1;
+  g.B = X; g.ldb = ldx; g.b_mn = 1;
+  g.out_f32 = static_cast<float*>(dW); g.ld_f32 = K_in; g.atomic = 1;
+  g.block_n = (K_in % 256 == 0) ? 256 : 128;
+  const int tiles = ((N_out + 127) / 128) * ((K_in + g.block_n - 1) / g.block_n);
+  const int kb = (rows + 63) / 64;
+  int splits = (2 * num_sms() + tiles - 1) / tiles;
+  if (splits > kb / 2) splits = kb / 2;
+  if (splits < 1) splits = 1;
+  g.k_splits = splits;
+  return gemm(g, s);
+}
+
+static int bias_grad(const bf16* dY, int rows, int cols, int ld, const void* db, cudaStream_t s) {
+  if (db == nullptr) return ETP_OK;
+  return colsum_bf16(dY, rows, cols, ld, static_cast<float*>(const_cast<void*>(db)), s);
+}
+static inline float* F(const void* p) { return static_cast<float*>(const_cast<void*>(p)); }
+
+// Backward of self_ffn_block (planner.cu): dx_out = grad of the block output; writes grad of the block input
+// (the LayerNorm output `a`) to `da`.  `da` may alias neither sc.g0 nor sc.g1.
+static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weights& g, const LayerRecord& rec,
+                              const bf16* a_bf16, const float* dx_out, float* da, int B, int S, const uint8_t* key_valid,
+                              const float* pair, const float* pair_w, const float* pair_b, float* dpair_w, float* dpair_b,
+                              BwdScratch& sc, cudaStream_t s) {
+  const int rows = B * S;
+  // x = LN(t3)
+  ETP_TRY(layernorm_bwd(dx_out, rec.t3, w.fln_g, rec.st3, rec.st3 + rows, rows, kH, sc.g0, 0, sc.gb, F(g.fln_g), F(g.fln_b), s));
+  // t3 = h.W2^T + b2 + c
+  ETP_TRY(bias_grad(sc.gb, rows, kH, kH, g.f2_b, s));
+  ETP_TRY(wgrad(sc.gb, rows, kH, kH, rec.h, kI, kI, const_cast<void*>(g.f2_w), s));
+  ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.f2_w, kI, nullptr, nullptr, sc.dpre, 1, rec.pre, s));  // * gelu'(pre)
+  // pre = c.W1^T + b1
+  ETP_TRY(bias_grad(sc.dpre, rows, kI, kI, g.f1_b, s));
+  ETP_TRY(wgrad(sc.dpre, rows, kI, kI, rec.cb, kH, kH, const_cast<void*>(g.f1_w), s));
+  ETP_TRY(dgrad(sc.dpre, rows, kI, kI, w.f1_w, kH, sc.g0, sc.g1, nullptr, 0, nullptr, s));  // dc = dpre.W1 + dt3
+  // c = LN(t2)
+  ETP_TRY(layernorm_bwd(sc.g1, rec.t2, w.sln_g, rec.st2, rec.st2 + rows, rows, kH, sc.g0, 0, sc.gb, F(g.sln_g), F(g.sln_b), s));
+  // t2 = ctx2.Wo^T + bo + a
+  ETP_TRY(bias_grad(sc.gb, rows, kH, kH, g.so_b, s));
+  ETP_TRY(wgrad(sc.gb, rows, kH, kH, rec.ctx2, kH, kH, const_cast<void*>(g.so_w), s));
+  ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.so_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
+  // attention
+  AttnBwdArgs at;
+  at.B = B; at.heads = kHeads; at.Sq = S; at.Sk = S;
+  at.q = rec.qkv; at.k = rec.qkv + kH; at.v = rec.qkv + 2 * kH; at.ldq = at.ldk = at.ldv = 3 * kH;
+  at.out = rec.ctx2; at.ldo = kH; at.dout = sc.dctx; at.lddo = kH; at.lse = rec.lse2; at.dvec = sc.dvec;
+  at.scale = 0.125f; at.key_valid = key_valid; at.mask_value = -10000.0f;
+  at.pair = pair; at.pair_w_dev = pair_w; at.pair_b_dev = pair_b; at.dpair_w = pair ? dpair_w : nullptr;
+  at.dpair_b = pair ? dpair_b : nullptr;
+  at.dq = sc.dqkv; at.dk = sc.dqkv + kH; at.dv = sc.dqkv + 2 * kH; at.lddq = at.lddk = at.lddv = 3 * kH;
+  ETP_TRY(attention_bwd_dispatch(at, s));
+  // qkv = a.Wqkv^T + b
+  ETP_TRY(bias_grad(sc.dqkv, rows, 3 * kH, 3 * kH, g.sqkv_b, s));
+  ETP_TRY(wgrad(sc.dqkv, rows, 3 * kH, 3 * kH, a_bf16, kH, kH, const_cast<void*>(g.sqkv_w), s));
+  ETP_TRY(dgrad(sc.dqkv, rows, 3 * kH, 3 * kH, w.sqkv_w, kH, sc.g0, da, nullptr, 0, nullptr, s));  // da = dqkv.Wqkv + dt2
+  return ETP_OK;
+}
+
+int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, const etp_nav_inputs& in,
+                        const float* d_gmap_embeds, const float* d_logits, void* saved, size_t saved_bytes, void* work,
+                        size_t work_bytes, float* d_txt_embeds, float* d_gmap_img_fts, cudaStream_t s) {
+  const int B = in.B, N = in.N, L = in.L, X = w.num_x_layers;
+  const int rows = B * N, kv_rows = B * L;
+  Arena ar(saved, saved_bytes);
+  NavRecord rec;
+  rec.carve(ar, B, N, L, X, true);
+  ETP_REQUIRE(ar.off <= saved_bytes, "backward_navigation: saved buffer too small");
+  Arena wa(work, work_bytes);
+  BwdScratch sc;
+  sc.carve(wa, rows, kv_rows, static_cast<size_t>(B) * kHeads * (N > L ? N : L));
+  float* P = wa.take<float>(static_cast<size_t>(rows) * kH);
+  float* Q = wa.take<float>(static_cast<size_t>(rows) * kH);
+  ETP_REQUIRE(wa.off <= work_bytes, "backward_navigation: workspace too small");
+  ETP_REQUIRE(d_gmap_embeds || d_logits, "backward_navigation: no incoming gradient");
+
+  const bf16* x_last = X > 0 ? rec.layers[X - 1].xb : rec.x0b;
+  if (d_logits) {
+    ETP_TRY(sap_tail_bwd(d_logits, rec.relu, w.sap_g, w.sap_bb, w.sap4_w, rec.sap_stats, rec.sap_stats + rows,
+                         in.gmap_visited_masks, in.gmap_masks, rows, sc.gb, F(g.sap_g), F(g.sap_bb), F(g.sap4_w), F(g.sap4_b), s));
+    ETP_TRY(bias_grad(sc.gb, rows, kH, kH, g.sap0_b, s));
+    ETP_TRY(wgrad(sc.gb, rows, kH, kH, x_last, kH, kH, const_cast<void*>(g.sap0_w), s));
+    ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.sap0_w, kH, d_gmap_embeds, P, nullptr, 0, nullptr, s));
+  } else {
+    ETP_CHECK_CUDA(cudaMemcpyAsync(P, d_gmap_embeds, static_cast<size_t>(rows) * kH * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  float* dtxt = d_txt_embeds ? d_txt_embeds : sc.dtxt;
+  bool dtxt_init = false;
+  for (int i = X - 1; i >= 0; --i) {
+    const etp_layer_weights& lw = w.layers[i];
+    const etp_layer_weights& lg = g.layers[i];
+    const LayerRecord& r = rec.layers[i];
+    const bf16* x_in = i > 0 ? rec.layers[i - 1].xb : rec.x0b;
+    ETP_TRY(self_ffn_block_bwd(lw, lg, r, r.ab, P, Q, B, N, in.gmap_masks, w.sprel_w ? in.gmap_pair_dists : nullptr, w.sprel_w,
+                               w.sprel_b, F(g.sprel_w), F(g.sprel_b), sc, s));
+    // a = LN(t1),  t1 = ctx1.Wo^T + bo + x_in
+    ETP_TRY(layernorm_bwd(Q, r.t1, lw.xln_g, r.st1, r.st1 + rows, rows, kH, sc.g0, 0, sc.gb, F(lg.xln_g), F(lg.xln_b), s));
+    ETP_TRY(bias_grad(sc.gb, rows, kH, kH, lg.xo_b, s));
+    ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.ctx1, kH, kH, const_cast<void*>(lg.xo_w), s));
+    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.xo_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
+    AttnBwdArgs at;
+    at.B = B; at.heads = kHeads; at.Sq = N; at.Sk = L;
+    at.q = r.q; at.ldq = kH; at.k = r.kv; at.ldk = 2 * kH; at.v = r.kv + kH; at.ldv = 2 * kH;
+    at.out = r.ctx1; at.ldo = kH; at.dout = sc.dctx; at.lddo = kH; at.lse = r.lse1; at.dvec = sc.dvec;
+    at.scale = 0.125f; at.key_valid = in.txt_masks; at.mask_value = -10000.0f;
+    at.dq = sc.dq; at.lddq = kH; at.dk = sc.dkv; at.lddk = 2 * kH; at.dv = sc.dkv + kH; at.lddv = 2 * kH;
+    ETP_TRY(attention_bwd_dispatch(at, s));
+    ETP_TRY(bias_grad(sc.dq, rows, kH, kH, lg.xq_b, s));
+    ETP_TRY(wgrad(sc.dq, rows, kH, kH, x_in, kH, kH, const_cast<void*>(lg.xq_w), s));
+    ETP_TRY(dgrad(sc.dq, rows, kH, kH, lw.xq_w, kH, sc.g0, P, nullptr, 0, nullptr, s));  // dx_in = dq.Wq + dt1
+    ETP_TRY(bias_grad(sc.dkv, kv_rows, 2 * kH, 2 * kH, lg.xkv_b, s));
+    ETP_TRY(wgrad(sc.dkv, kv_rows, 2 * kH, 2 * kH, rec.txtb, kH, kH, const_cast<void*>(lg.xkv_w), s));
+    ETP_TRY(dgrad(sc.dkv, kv_rows, 2 * kH, 2 * kH, lw.xkv_w, kH, dtxt_init ? dtxt : nullptr, dtxt, nullptr, 0, nullptr, s));
+    dtxt_init = true;
+  }
+  if (d_txt_embeds && !dtxt_init)
+    ETP_CHECK_CUDA(cudaMemsetAsync(d_txt_embeds, 0, static_cast<size_t>(kv_rows) * kH * 4, s));
+  // node packing: x0 = img_fts + E_step[ids] + LN(pos_fts.W^T + b)
+  ETP_TRY(node_pack_bwd(P, in.gmap_step_ids, in.gmap_pos_fts, rec.pos_lin, rec.pos_stats, w.pos_g, rows, F(g.step_emb),
+                        F(g.pos_w), F(g.pos_b), F(g.pos_g), F(g.pos_bb), s));
+  if (d_gmap_img_fts)
+    ETP_CHECK_CUDA(cudaMemcpyAsync(d_gmap_img_fts, P, static_cast<size_t>(rows) * kH * 4, cudaMemcpyDeviceToDevice, s));
+  return ETP_OK;
+}
+
+int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, const etp_pano_inputs& in,
+                      const uint8_t* pano_masks, const float* d_pano_embeds, void* saved, size_t saved_bytes, void* work,
+                      size_t work_bytes, float* d_rgb_fts, float* d_dep_fts, cudaStream_t s) {
+  const int B = in.B, V = in.V, Pn = w.num_pano_layers;
+  const int rows = B * V;
+  Arena ar(saved, saved_bytes);
+  PanoRecord rec;
+  rec.carve(ar, B, V, Pn, true);
+  ETP_REQUIRE(ar.off <= saved_bytes, "backward_panorama: saved buffer too small");
+  Arena wa(work, work_bytes);
+  BwdScratch sc;
+  sc.carve(wa, rows, 0, static_cast<size_t>(B) * kHeads * V);
+  ETP_REQUIRE(wa.off <= work_bytes, "backward_panorama: workspace too small");
+  float* A = sc.g0;
+  float* Bf = sc.g1;
+  if (Pn > 0) {
+    ETP_TRY(layernorm_bwd(d_pano_embeds, rec.xs[2 * Pn], w.fin_g, rec.fin_stats, rec.fin_stats + rows, rows, kH, A, 0, sc.gb,
+                          F(g.fin_g), F(g.fin_b), s));
+  } else {
+    ETP_CHECK_CUDA(cudaMemcpyAsync(A, d_pano_embeds, static_cast<size_t>(rows) * kH * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  for (int i = Pn - 1; i >= 0; --i) {
+    const etp_pano_layer_weights& lw = w.layers[i];
+    const etp_pano_layer_weights& lg = g.layers[i];
+    const PanoLayerRecord& r = rec.layers[i];
+    const float* x = rec.xs[2 * i];
+    const float* x_mid = rec.xs[2 * i + 1];
+    // x_out = x_mid + gelu(LN2(x_mid).W1^T + b1).W2^T + b2      (A = dx_out, sc.gb = bf16(A))
+    ETP_TRY(bias_grad(sc.gb, rows, kH, kH, lg.l2_b, s));
+    ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.h, kI, kI, const_cast<void*>(lg.l2_w), s));
+    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.l2_w, kI, nullptr, nullptr, sc.dpre, 1, r.pre, s));
+    ETP_TRY(bias_grad(sc.dpre, rows, kI, kI, lg.l1_b, s));
+    ETP_TRY(wgrad(sc.dpre, rows, kI, kI, r.y2b, kH, kH, const_cast<void*>(lg.l1_w), s));
+    ETP_TRY(dgrad(sc.dpre, rows, kI, kI, lw.l1_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy2
+    ETP_TRY(layernorm_bwd(Bf, x_mid, lw.n2_g, r.st2, r.st2 + rows, rows, kH, A, 1, sc.gb, F(lg.n2_g), F(lg.n2_b), s));  // A = dx_mid
+    // x_mid = x + attn(LN1(x)).Wout^T + bout
+    ETP_TRY(bias_grad(sc.gb, rows, kH, kH, lg.out_b, s));
+    ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.ctx, kH, kH, const_cast<void*>(lg.out_w), s));
+    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.out_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
+    AttnBwdArgs at;
+    at.B = B; at.heads = kHeads; at.Sq = V; at.Sk = V;
+    at.q = r.qkv; at.k = r.qkv + kH; at.v = r.qkv + 2 * kH; at.ldq = at.ldk = at.ldv = 3 * kH;
+    at.out = r.ctx; at.ldo = kH; at.dout = sc.dctx; at.lddo = kH; at.lse = r.lse; at.dvec = sc.dvec;
+    at.scale = 0.125f; at.key_valid = pano_masks; at.mask_value = -INFINITY;
+    at.dq = sc.dqkv; at.dk = sc.dqkv + kH; at.dv = sc.dqkv + 2 * kH; at.lddq = at.lddk = at.lddv = 3 * kH;
+    ETP_TRY(attention_bwd(at, s));
+    ETP_TRY(bias_grad(sc.dqkv, rows, 3 * kH, 3 * kH, lg.in_b, s));
+    ETP_TRY(wgrad(sc.dqkv, rows, 3 * kH, 3 * kH, r.y1b, kH, kH, const_cast<void*>(lg.in_w), s));
+    ETP_TRY(dgrad(sc.dqkv, rows, 3 * kH, 3 * kH, lw.in_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy1
+    ETP_TRY(layernorm_bwd(Bf, x, lw.n1_g, r.st1, r.st1 + rows, rows, kH, A, 1, sc.gb, F(lg.n1_g), F(lg.n1_b), s));  // A = dx
+  }
+  PanoPackBwdArgs pb;
+  pb.rows = rows; pb.dx = A; pb.rgb_lin = rec.rgb_lin; pb.dep_lin = w.dep_w ? rec.dep_lin : nullptr; pb.loc_lin = rec.loc_lin;
+  pb.sum_pre = rec.sum_pre; pb.stats = rec.stats; pb.loc_fts = in.loc_fts; pb.nav_types = in.nav_types;
+  pb.img_g = w.img_g; pb.dep_g = w.dep_g; pb.loc_g = w.loc_g; pb.out_g = w.out_g;
+  pb.drgb_lin = sc.dq; pb.ddep_lin = sc.dctx;
+  pb.dimg_g = F(g.img_g); pb.dimg_b = F(g.img_bb); pb.ddep_g = F(g.dep_g); pb.ddep_b = F(g.dep_bb);
+  pb.dloc_g = F(g.loc_g); pb.dloc_b = F(g.loc_bb); pb.dout_g = F(g.out_g); pb.dout_b = F(g.out_bb);
+  pb.dloc_w = F(g.loc_w); pb.dloc_bias = F(g.loc_b); pb.dnav_emb = F(g.nav_emb); pb.dtok_emb1 = F(g.tok_emb1);
+  ETP_TRY(pano_pack_bwd(pb, s));
+  ETP_TRY(bias_grad(sc.dq, rows, kH, kH, g.img_b, s));
+  ETP_TRY(wgrad(sc.dq, rows, kH, kH, rec.rgbb, 512, 512, const_cast<void*>(g.img_w), s));
+  if (d_rgb_fts) ETP_TRY(dgrad(sc.dq, rows, kH, kH, w.img_w, 512, nullptr, d_rgb_fts, nullptr, 0, nullptr, s));
+  if (w.dep_w) {
+    ETP_TRY(bias_grad(sc.dctx, rows, kH, kH, g.dep_b, s));
+    ETP_TRY(wgrad(sc.dctx, rows, kH, kH, rec.depb, 128, 128, const_cast<void*>(g.dep_w), s));
+    if (d_dep_fts) ETP_TRY(dgrad(sc.dctx, rows, kH, kH, w.dep_w, 128, nullptr, d_dep_fts, nullptr, 0, nullptr, s));
+  }
+  return ETP_OK;
+}
+
+int backward_txt(const etp_txt_weights& w, const etp_txt_weights& g, const int64_t* txt_ids, const uint8_t* txt_masks, int B,
+                 int L, const float* d_txt_embeds, void* saved, size_t saved_bytes, void* work, size_t work_bytes,
+                 cudaStream_t s) {
+  const int NL = w.num_l_layers, rows = B * L;
+  Arena ar(saved, saved_bytes);
+  TxtRecord rec;
+  rec.carve(ar, B, L, NL, true);
+  ETP_REQUIRE(ar.off <= saved_bytes, "backward_txt: saved buffer too small");
+  Arena wa(work, work_bytes);
+  BwdScratch sc;
+  sc.carve(wa, rows, 0, static_cast<size_t>(B) * kHeads * L);
+  float* P = wa.take<float>(static_cast<size_t>(rows) * kH);
+  float* Q = wa.take<float>(static_cast<size_t>(rows) * kH);
+  ETP_REQUIRE(wa.off <= work_bytes, "backward_txt: workspace too small");
+  const float* dx = d_txt_embeds;
+  for (int i = NL - 1; i >= 0; --i) {
+    const bf16* a_bf16 = i > 0 ? rec.layers[i - 1].xb : rec.x0b;
+    float* da = (dx == P) ? Q : P;
+    ETP_TRY(self_ffn_block_bwd(w.layers[i], g.layers[i], rec.layers[i], a_bf16, dx, da, B, L, txt_masks, nullptr, nullptr,
+                               nullptr, nullptr, nullptr, sc, s));
+    dx = da;
+  }
+  ETP_TRY(embed_txt_bwd(dx, txt_ids, rec.sum_pre, rec.emb_stats, w.emb_g, B, L, F(g.word_emb), F(g.pos_emb), F(g.type_emb0),
+                        F(g.emb_g), F(g.emb_b), s));
+  return ETP_OK;
+}
+
+static size_t work_bytes_for(size_t rows, size_t kv_rows, size_t bhs) {
+  Arena wa(nullptr, ~size_t(0));
+  BwdScratch sc;
+  sc.carve(wa, rows, kv_rows, bhs);
+  wa.take<float>(rows * kH);
+  wa.take<float>(rows * kH);
+  return wa.off;
+}
+
+}  // namespace etp
+
+using namespace etp;
+#define ETP_API __attribute__((visibility("default")))
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+ETP_API size_t etp_nav_bwd_work_bytes(int32_t B, int32_t N, int32_t L) {
+  return work_bytes_for(static_cast<size_t>(B) * N, static_cast<size_t>(B) * L, static_cast<size_t>(B) * kHeads * (N > L ? N : L));
+}
+ETP_API size_t etp_pano_bwd_work_bytes(int32_t B, int32_t V) {
+  return work_bytes_for(static_cast<size_t>(B) * V, 0, static_cast<size_t>(B) * kHeads * V);
+}
+ETP_API size_t etp_txt_bwd_work_bytes(int32_t B, int32_t L) {
+  return work_bytes_for(static_cast<size_t>(B) * L, 0, static_cast<size_t>(B) * kHeads * L);
+}
+
+ETP_API int etp_backward_navigation(const etp_nav_weights* w, const etp_nav_weights* grads, const etp_nav_inputs* in,
+                                    const float* d_gmap_embeds, const float* d_global_logits, void* saved,
+                                    size_t saved_bytes, void* work, size_t work_bytes, float* d_txt_embeds,
+                                    float* d_gmap_img_fts, void* stream) {
+  ETP_REQUIRE(w && grads && in && saved && work, "etp_backward_navigation: null argument");
+  return backward_navigation(*w, *grads, *in, d_gmap_embeds, d_global_logits, saved, saved_bytes, work, work_bytes,
+                             d_txt_embeds, d_gmap_img_fts, S(stream));
+}
+ETP_API int etp_backward_panorama(const etp_pano_weights* w, const etp_pano_weights* grads, const etp_pano_inputs* in,
+                                  const uint8_t* pano_masks, const float* d_pano_embeds, void* saved, size_t saved_bytes,
+                                  void* work, size_t work_bytes, float* d_rgb_fts, float* d_dep_fts, void* stream) {
+  ETP_REQUIRE(w && grads && in && pano_masks && d_pano_embeds && saved && work, "etp_backward_panorama: null argument");
+  return backward_panorama(*w, *grads, *in, pano_masks, d_pano_embeds, saved, saved_bytes, work, work_bytes, d_rgb_fts,
+                           d_dep_fts, S(stream));
+}
+ETP_API int etp_backward_txt(const etp_txt_weights* w, const etp_txt_weights* grads, const int64_t* txt_ids,
+                             const uint8_t* txt_masks, int32_t B, int32_t L, const float* d_txt_embeds, void* saved,
+                             size_t saved_bytes, void* work, size_t work_bytes, void* stream) {
+  ETP_REQUIRE(w && grads && txt_ids && txt_masks && d_txt_embeds && saved && work, "etp_backward_txt: null argument");
+  return backward_txt(*w, *grads, txt_ids, txt_masks, B, L, d_txt_embeds, saved, saved_bytes, work, work_bytes, S(stream));
+}
+
+ETP_API int etp_adamw_step(float* param, void* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                           void* stream) {
+  return adamw_step(param, static_cast<bf16*>(param_bf16), grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                    step, grad_scale, S(stream));
+}
+
+}  // extern "C"

@@ -86,6 +86,18 @@ def _declare():
                                        C.c_size_t, i32, p_void]
     L.etp_forward_txt.argtypes = [C.POINTER(TxtWeights), p_void, p_void, i32, i32, p_void, p_void, C.c_size_t, i32,
                                   p_void]
+    for fn in ("etp_nav_bwd_work_bytes",):
+        getattr(L, fn).restype = C.c_size_t
+        getattr(L, fn).argtypes = [i32] * 3
+    for fn in ("etp_pano_bwd_work_bytes", "etp_txt_bwd_work_bytes"):
+        getattr(L, fn).restype = C.c_size_t
+        getattr(L, fn).argtypes = [i32] * 2
+    L.etp_backward_navigation.argtypes = [C.POINTER(NavWeights), C.POINTER(NavWeights), C.POINTER(NavInputs), p_void,
+                                          p_void, p_void, C.c_size_t, p_void, C.c_size_t, p_void, p_void, p_void]
+    L.etp_backward_panorama.argtypes = [C.POINTER(PanoWeights), C.POINTER(PanoWeights), C.POINTER(PanoInputs), p_void,
+                                        p_void, p_void, C.c_size_t, p_void, C.c_size_t, p_void, p_void, p_void]
+    L.etp_backward_txt.argtypes = [C.POINTER(TxtWeights), C.POINTER(TxtWeights), p_void, p_void, i32, i32, p_void, p_void,
+                                   C.c_size_t, p_void, C.c_size_t, p_void]
     _declared = True
 
 
@@ -110,6 +122,10 @@ class B200Planner(nn.Module):
         self._reset_parameters()
         self._cache_key = None
         self._structs = None
+        self._bf16_fresh = False
+        self._grad_structs = {}
+        self._direct_grad = None      # PlannerTrainer: flat fp32 gradient buffer the backward accumulates into
+        self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         if config.fix_lang_embedding:  # vilmodel_cmt.py:675-679
             for n, p in self.named_parameters():
                 if n.startswith("embeddings.") or n.startswith("lang_encoder."):
@@ -166,6 +182,12 @@ class B200Planner(nn.Module):
             self._structs = None
         return out
 
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        self._bf16_fresh = False
+        self._cache_key = None
+        return out
+
     def _flat_is_intact(self):
         base = self._flat.data_ptr()
         for name, (off, _, _) in self.layout.entries.items():
@@ -175,7 +197,9 @@ class B200Planner(nn.Module):
 
     def _refresh_cache(self):
         """Re-cast the flat fp32 parameters to bf16 when any parameter changed (optimizer step, load)."""
-        key = tuple(p._version for p in self._pmap.values())
+        if self._bf16_fresh and self._structs is not None:
+            return  # the fused AdamW keeps the bf16 image current (PlannerTrainer)
+        key = self._version_key()
         if key == self._cache_key and self._structs is not None:
             return
         if not self._flat.is_cuda:
@@ -185,16 +209,19 @@ class B200Planner(nn.Module):
         _L.require_device()
         _declare()
         _L.cast_bf16(self._flat, self._flat_bf16)
-        self._cache_key = key
+        self._cache_key = self._version_key()
         if self._structs is None:
-            self._structs = self._build_structs()
+            self._structs = self._build_structs(self._flat.data_ptr(), self._flat_bf16.data_ptr(), 2)
 
     # ------------------------------------------------------------------ ctypes weight structs
+    def _version_key(self):
+        return tuple(p._version for p in self._pmap.values())
+
     def _w32(self, name):
-        return C.c_void_p(self._flat.data_ptr() + 4 * self.layout.offset(name))
+        return C.c_void_p(self._b32 + 4 * self.layout.offset(name))
 
     def _w16(self, name):
-        return C.c_void_p(self._flat_bf16.data_ptr() + 2 * self.layout.offset(name))
+        return C.c_void_p(self._b16 + self._s16 * self.layout.offset(name))
 
     def _layer_struct(self, att, out, inter, outp, cross=None):
         lw = LayerWeights()
@@ -215,7 +242,10 @@ class B200Planner(nn.Module):
         lw.fln_g, lw.fln_b = self._w32(outp + "LayerNorm.weight"), self._w32(outp + "LayerNorm.bias")
         return lw
 
-    def _build_structs(self):
+    def _build_structs(self, b32, b16, s16):
+        """ctypes structs over a flat buffer: b32 = base address of the fp32 image, b16/s16 = base address and
+        element size of the image the GEMM-weight pointers refer to (bf16 parameters, or fp32 gradients)."""
+        self._b32, self._b16, self._s16 = b32, b16, s16
         cfg = self.config
         s = {}
         X = cfg.num_x_layers
@@ -282,75 +312,337 @@ class B200Planner(nn.Module):
         s["txt"], s["txt_layers"] = tw, tl
         return s
 
+    # ------------------------------------------------------------------ gradient plumbing
+    def _group_names(self, group):
+        from .layout import ordered_names
+        if not hasattr(self, "_gnames"):
+            self._gnames = ordered_names(self.config)
+        return self._gnames[group]
+
+    def _grad_view(self, gbuf, gstart, name):
+        off, numel, shape = self.layout.entries[name]
+        return gbuf[off - gstart: off - gstart + numel].view(shape)
+
+    def _grad_structs_for(self, gbuf, gstart):
+        """Weight-shaped structs whose every pointer lands in ``gbuf`` (fp32), which holds the flat-layout slice
+        starting at element ``gstart``."""
+        key = (gbuf.data_ptr(), gstart)
+        st = self._grad_structs.get(key)
+        if st is None:
+            base = gbuf.data_ptr() - 4 * gstart
+            st = self._build_structs(base, base, 4)
+            self._b32, self._b16, self._s16 = self._flat.data_ptr(), self._flat_bf16.data_ptr(), 2
+            if len(self._grad_structs) > 8:
+                self._grad_structs.clear()
+            self._grad_structs[key] = st
+        return st
+
+    def _grad_target(self, group):
+        """(buffer, first element, per-call?) the backward of ``group`` accumulates into."""
+        gs, ge = self.layout.group_ranges[group]
+        if self._direct_grad is not None:
+            return self._direct_grad, 0, False
+        return torch.zeros(ge - gs, dtype=torch.float32, device=self._flat.device), gs, True
+
+    def _anchor_t(self):
+        if self._anchor.device != self._flat.device:
+            self._anchor = torch.zeros(1, device=self._flat.device, requires_grad=True)
+        return self._anchor
+
     # ------------------------------------------------------------------ the three reference methods
     @staticmethod
     def _mask_u8(m):
         m = m.contiguous()
         return m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
 
-    def _needs_grad(self, *tensors):
+    def _wants_grad(self, group, *tensors):
         if not torch.is_grad_enabled():
             return False
-        return any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters())
+        if any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+            return True
+        return any(self._pmap[n].requires_grad for n in self._group_names(group))
 
     def forward_txt(self, txt_ids, txt_masks):
         """vilmodel_cmt.py:684-688.  txt_ids int64 [B,L], txt_masks bool [B,L] -> txt_embeds fp32 [B,L,768]."""
         self._refresh_cache()
-        B, Lt = txt_ids.shape
-        if Lt > self.config.max_position_embeddings:
+        if txt_ids.shape[1] > self.config.max_position_embeddings:
             raise ValueError("sequence longer than max_position_embeddings")
         ids = txt_ids.contiguous().long()
         mk = self._mask_u8(txt_masks)
-        out = torch.empty(B, Lt, 768, device=ids.device, dtype=torch.float32)
-        L = _L.lib()
-        nbytes = L.etp_txt_saved_bytes(B, Lt, self.config.num_l_layers, 0)
-        saved = torch.empty(nbytes, dtype=torch.uint8, device=ids.device)
-        _L._check(L.etp_forward_txt(C.byref(self._structs["txt"]), _L.ptr(ids), _L.ptr(mk), B, Lt, _L.ptr(out),
-                                    _L.ptr(saved), nbytes, 0, _L.stream_ptr()), "etp_forward_txt")
-        return out
+        if self._wants_grad("txt") and self.config.update_lang_bert:
+            params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._group_names("txt")]
+            return _TxtFn.apply(self, ids, mk, self._anchor_t(), *params)
+        return _txt_forward(self, ids, mk, 0)[0]
 
     def forward_panorama(self, rgb_fts, dep_fts, loc_fts, nav_types, view_lens):
         """vilmodel_cmt.py:690-719 -> (pano_embeds fp32 [B,V,768], pano_masks bool [B,V])."""
         self._refresh_cache()
-        B, V = rgb_fts.shape[:2]
-        rgb, dep, loc = _f32c(rgb_fts), _f32c(dep_fts), _f32c(loc_fts)
         nt, vl = nav_types.contiguous().long(), view_lens.contiguous().long()
-        out = torch.empty(B, V, 768, device=rgb.device, dtype=torch.float32)
-        masks = torch.empty(B, V, device=rgb.device, dtype=torch.uint8)
-        pi = PanoInputs()
-        pi.B, pi.V = B, V
-        pi.rgb_fts, pi.dep_fts, pi.loc_fts = _L.ptr(rgb), _L.ptr(dep), _L.ptr(loc)
-        pi.nav_types, pi.view_lens = _L.ptr(nt), _L.ptr(vl)
-        L = _L.lib()
-        nbytes = L.etp_pano_saved_bytes(B, V, self.config.num_pano_layers, 0)
-        saved = torch.empty(nbytes, dtype=torch.uint8, device=rgb.device)
-        _L._check(L.etp_forward_panorama(C.byref(self._structs["pano"]), C.byref(pi), _L.ptr(out), _L.ptr(masks),
-                                         _L.ptr(saved), nbytes, 0, _L.stream_ptr()), "etp_forward_panorama")
+        loc = _f32c(loc_fts)
+        if self._wants_grad("pano", rgb_fts, dep_fts):
+            params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._pano_param_names()]
+            return _PanoFn.apply(self, rgb_fts, dep_fts, loc, nt, vl, self._anchor_t(), *params)
+        out, masks, _, _ = _pano_forward(self, _f32c(rgb_fts), _f32c(dep_fts), loc, nt, vl, 0)
         return out, masks.view(torch.bool)
+
+    def _pano_param_names(self):
+        # forward_panorama also reads row 1 of the token-type table (vilmodel_cmt.py:709), which lives in the txt group
+        return self._group_names("pano") + ["embeddings.token_type_embeddings.weight"]
 
     def forward_navigation(self, txt_embeds, txt_masks, gmap_vpids, gmap_step_ids, gmap_img_fts, gmap_pos_fts,
                            gmap_masks, gmap_visited_masks, gmap_pair_dists):
         """vilmodel_cmt.py:721-750 -> {'gmap_embeds': fp32 [B,N,768], 'global_logits': fp32 [B,N]}.
         ``gmap_vpids`` is accepted and ignored, as in the reference."""
         self._refresh_cache()
-        B, N = gmap_img_fts.shape[:2]
-        Lt = txt_embeds.shape[1]
-        txt, img, pos, pd = _f32c(txt_embeds), _f32c(gmap_img_fts), _f32c(gmap_pos_fts), _f32c(gmap_pair_dists)
-        ni = NavInputs()
-        ni.B, ni.N, ni.L = B, N, Lt
-        tm, gm, vm = self._mask_u8(txt_masks), self._mask_u8(gmap_masks), self._mask_u8(gmap_visited_masks)
-        ids = gmap_step_ids.contiguous().long()
-        ni.txt_embeds, ni.txt_masks, ni.gmap_step_ids = _L.ptr(txt), _L.ptr(tm), _L.ptr(ids)
-        ni.gmap_img_fts, ni.gmap_pos_fts, ni.gmap_masks = _L.ptr(img), _L.ptr(pos), _L.ptr(gm)
-        ni.gmap_visited_masks, ni.gmap_pair_dists = _L.ptr(vm), _L.ptr(pd)
-        embeds = torch.empty(B, N, 768, device=img.device, dtype=torch.float32)
-        logits = torch.empty(B, N, device=img.device, dtype=torch.float32)
-        L = _L.lib()
-        nbytes = L.etp_nav_saved_bytes(B, N, Lt, self.config.num_x_layers, 0)
-        saved = torch.empty(nbytes, dtype=torch.uint8, device=img.device)
-        _L._check(L.etp_forward_navigation(C.byref(self._structs["nav"]), C.byref(ni), _L.ptr(embeds), _L.ptr(logits),
-                                           _L.ptr(saved), nbytes, 0, _L.stream_ptr()), "etp_forward_navigation")
+        aux = (self._mask_u8(txt_masks), gmap_step_ids.contiguous().long(), _f32c(gmap_pos_fts),
+               self._mask_u8(gmap_masks), self._mask_u8(gmap_visited_masks), _f32c(gmap_pair_dists))
+        if self._wants_grad("nav", txt_embeds, gmap_img_fts):
+            params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._group_names("nav")]
+            embeds, logits = _NavFn.apply(self, txt_embeds, gmap_img_fts, aux, self._anchor_t(), *params)
+        else:
+            embeds, logits, _, _ = _nav_forward(self, _f32c(txt_embeds), _f32c(gmap_img_fts), aux, 0)
         return {"gmap_embeds": embeds, "global_logits": logits}
+
+    # ------------------------------------------------------------------ training helper
+    def make_trainer(self, lr=1e-5, world_size=1, **kw):
+        return PlannerTrainer(self, lr=lr, world_size=world_size, **kw)
+
+
+# ----------------------------------------------------------------------------------------------------
+# raw step calls (no autograd)
+# ----------------------------------------------------------------------------------------------------
+def _txt_forward(m, ids, mk, training):
+    B, Lt = ids.shape
+    L = _L.lib()
+    out = torch.empty(B, Lt, 768, device=ids.device, dtype=torch.float32)
+    nbytes = L.etp_txt_saved_bytes(B, Lt, m.config.num_l_layers, training)
+    saved = torch.empty(nbytes, dtype=torch.uint8, device=ids.device)
+    _L._check(L.etp_forward_txt(C.byref(m._structs["txt"]), _L.ptr(ids), _L.ptr(mk), B, Lt, _L.ptr(out), _L.ptr(saved),
+                                nbytes, training, _L.stream_ptr()), "etp_forward_txt")
+    return out, saved
+
+
+def _pano_inputs(rgb, dep, loc, nt, vl):
+    pi = PanoInputs()
+    pi.B, pi.V = rgb.shape[0], rgb.shape[1]
+    pi.rgb_fts, pi.dep_fts, pi.loc_fts = _L.ptr(rgb), _L.ptr(dep), _L.ptr(loc)
+    pi.nav_types, pi.view_lens = _L.ptr(nt), _L.ptr(vl)
+    return pi
+
+
+def _pano_forward(m, rgb, dep, loc, nt, vl, training):
+    B, V = rgb.shape[:2]
+    L = _L.lib()
+    out = torch.empty(B, V, 768, device=rgb.device, dtype=torch.float32)
+    masks = torch.empty(B, V, device=rgb.device, dtype=torch.uint8)
+    pi = _pano_inputs(rgb, dep, loc, nt, vl)
+    nbytes = L.etp_pano_saved_bytes(B, V, m.config.num_pano_layers, training)
+    saved = torch.empty(nbytes, dtype=torch.uint8, device=rgb.device)
+    _L._check(L.etp_forward_panorama(C.byref(m._structs["pano"]), C.byref(pi), _L.ptr(out), _L.ptr(masks), _L.ptr(saved),
+                                     nbytes, training, _L.stream_ptr()), "etp_forward_panorama")
+    return out, masks, saved, pi
+
+
+def _nav_inputs(txt, img, aux):
+    tm, ids, pos, gm, vm, pd = aux
+    ni = NavInputs()
+    ni.B, ni.N, ni.L = img.shape[0], img.shape[1], txt.shape[1]
+    ni.txt_embeds, ni.txt_masks, ni.gmap_step_ids = _L.ptr(txt), _L.ptr(tm), _L.ptr(ids)
+    ni.gmap_img_fts, ni.gmap_pos_fts, ni.gmap_masks = _L.ptr(img), _L.ptr(pos), _L.ptr(gm)
+    ni.gmap_visited_masks, ni.gmap_pair_dists = _L.ptr(vm), _L.ptr(pd)
+    return ni
+
+
+def _nav_forward(m, txt, img, aux, training):
+    B, N = img.shape[:2]
+    Lt = txt.shape[1]
+    L = _L.lib()
+    ni = _nav_inputs(txt, img, aux)
+    embeds = torch.empty(B, N, 768, device=img.device, dtype=torch.float32)
+    logits = torch.empty(B, N, device=img.device, dtype=torch.float32)
+    nbytes = L.etp_nav_saved_bytes(B, N, Lt, m.config.num_x_layers, training)
+    saved = torch.empty(nbytes, dtype=torch.uint8, device=img.device)
+    _L._check(L.etp_forward_navigation(C.byref(m._structs["nav"]), C.byref(ni), _L.ptr(embeds), _L.ptr(logits),
+                                       _L.ptr(saved), nbytes, training, _L.stream_ptr()), "etp_forward_navigation")
+    return embeds, logits, saved, ni
+
+
+# ----------------------------------------------------------------------------------------------------
+# autograd glue: one node per reference method; backward = one step-level C call
+# ----------------------------------------------------------------------------------------------------
+def _param_grads(m, names, gbuf, gstart, per_call, nparams):
+    if nparams == 0 or not per_call:
+        return [None] * nparams
+    return [m._grad_view(gbuf, gstart, n) if m._pmap[n].requires_grad else None for n in names]
+
+
+class _NavFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, m, txt_embeds, gmap_img_fts, aux, anchor, *params):
+        txt, img = _f32c(txt_embeds), _f32c(gmap_img_fts)
+        embeds, logits, saved, _ = _nav_forward(m, txt, img, aux, 1)
+        ctx.m, ctx.saved, ctx.keep, ctx.nparams = m, saved, (txt, img, aux), len(params)
+        return embeds, logits
+
+    @staticmethod
+    def backward(ctx, d_embeds, d_logits):
+        m = ctx.m
+        txt, img, aux = ctx.keep
+        L = _L.lib()
+        B, N, Lt = img.shape[0], img.shape[1], txt.shape[1]
+        gbuf, gstart, per_call = m._grad_target("nav")
+        gst = m._grad_structs_for(gbuf, gstart)
+        ni = _nav_inputs(txt, img, aux)
+        de = _f32c(d_embeds) if d_embeds is not None else None
+        dl = _f32c(d_logits) if d_logits is not None else None
+        if dl is not None:
+            dl = torch.nan_to_num(dl, nan=0.0, posinf=0.0, neginf=0.0)
+        d_txt = torch.empty_like(txt) if ctx.needs_input_grad[1] else None
+        d_img = torch.empty_like(img) if ctx.needs_input_grad[2] else None
+        wbytes = L.etp_nav_bwd_work_bytes(B, N, Lt)
+        work = torch.empty(wbytes, dtype=torch.uint8, device=img.device)
+        _L._check(L.etp_backward_navigation(C.byref(m._structs["nav"]), C.byref(gst["nav"]), C.byref(ni), _L.ptr(de),
+                                            _L.ptr(dl), _L.ptr(ctx.saved), ctx.saved.numel(), _L.ptr(work), wbytes,
+                                            _L.ptr(d_txt), _L.ptr(d_img), _L.stream_ptr()), "etp_backward_navigation")
+        pg = _param_grads(m, m._group_names("nav"), gbuf, gstart, per_call, ctx.nparams)
+        return (None, d_txt, d_img, None, None, *pg)
+
+
+class _PanoFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, m, rgb_fts, dep_fts, loc, nt, vl, anchor, *params):
+        rgb, dep = _f32c(rgb_fts), _f32c(dep_fts)
+        out, masks, saved, _ = _pano_forward(m, rgb, dep, loc, nt, vl, 1)
+        ctx.m, ctx.saved, ctx.keep, ctx.nparams = m, saved, (rgb, dep, loc, nt, vl, masks), len(params)
+        mb = masks.view(torch.bool)
+        ctx.mark_non_differentiable(mb)
+        return out, mb
+
+    @staticmethod
+    def backward(ctx, d_out, _unused):
+        m = ctx.m
+        rgb, dep, loc, nt, vl, masks = ctx.keep
+        L = _L.lib()
+        B, V = rgb.shape[:2]
+        gs, ge = m.layout.group_ranges["pano"]
+        if m._direct_grad is not None:
+            gbuf, gstart, per_call = m._direct_grad, 0, False
+            gst = m._grad_structs_for(gbuf, gstart)
+            tok = None
+        else:
+            # group-sized scratch + 768 extra floats for the token-type row 1, which lives in the txt group
+            gbuf = torch.zeros(ge - gs + 768, dtype=torch.float32, device=rgb.device)
+            gstart, per_call = gs, True
+            gst = m._grad_structs_for(gbuf, gstart)
+            tok = gbuf[ge - gs:]
+            gst["pano"].tok_emb1 = C.c_void_p(tok.data_ptr())
+        pi = _pano_inputs(rgb, dep, loc, nt, vl)
+        d_rgb = torch.empty_like(rgb) if ctx.needs_input_grad[1] else None
+        d_dep = torch.empty_like(dep) if (ctx.needs_input_grad[2] and m.config.use_depth_embedding) else None
+        wbytes = L.etp_pano_bwd_work_bytes(B, V)
+        work = torch.empty(wbytes, dtype=torch.uint8, device=rgb.device)
+        _L._check(L.etp_backward_panorama(C.byref(m._structs["pano"]), C.byref(gst["pano"]), C.byref(pi), _L.ptr(masks),
+                                          _L.ptr(_f32c(d_out)), _L.ptr(ctx.saved), ctx.saved.numel(), _L.ptr(work), wbytes,
+                                          _L.ptr(d_rgb), _L.ptr(d_dep), _L.stream_ptr()), "etp_backward_panorama")
+        pg = []
+        if ctx.nparams:
+            names = m._pano_param_names()
+            pg = _param_grads(m, names[:-1], gbuf, gstart, per_call, ctx.nparams - 1)
+            tt = None
+            if per_call and m._pmap[names[-1]].requires_grad:
+                tt = torch.zeros_like(m._pmap[names[-1]])
+                tt[1] = tok
+            pg.append(tt)
+        if d_dep is None and ctx.needs_input_grad[2]:
+            d_dep = torch.zeros_like(dep)
+        return (None, d_rgb, d_dep, None, None, None, None, *pg)
+
+
+class _TxtFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, m, ids, mk, anchor, *params):
+        out, saved = _txt_forward(m, ids, mk, 1)
+        ctx.m, ctx.saved, ctx.keep, ctx.nparams = m, saved, (ids, mk), len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        m = ctx.m
+        ids, mk = ctx.keep
+        L = _L.lib()
+        B, Lt = ids.shape
+        gbuf, gstart, per_call = m._grad_target("txt")
+        gst = m._grad_structs_for(gbuf, gstart)
+        wbytes = L.etp_txt_bwd_work_bytes(B, Lt)
+        work = torch.empty(wbytes, dtype=torch.uint8, device=ids.device)
+        _L._check(L.etp_backward_txt(C.byref(m._structs["txt"]), C.byref(gst["txt"]), _L.ptr(ids), _L.ptr(mk), B, Lt,
+                                     _L.ptr(_f32c(d_out)), _L.ptr(ctx.saved), ctx.saved.numel(), _L.ptr(work), wbytes,
+                                     _L.stream_ptr()), "etp_backward_txt")
+        pg = _param_grads(m, m._group_names("txt"), gbuf, gstart, per_call, ctx.nparams)
+        return (None, None, None, None, *pg)
+
+
+class PlannerTrainer:
+    """Fused training step for the planner hot path: forward_panorama + forward_navigation, the caller-side loss of
+    ss_trainer_ETP.py:890-892 (cross-entropy, sum over the batch, divided by the number of actions as :1055),
+    backward through the step-level C calls accumulating straight into one flat fp32 gradient buffer, ONE NCCL
+    all-reduce of that buffer's step slice (the reference's DDP mean, ss_trainer_ETP.py:211-212) and a fused
+    AdamW (torch.optim.AdamW defaults, :213) that also refreshes the bf16 weight image."""
+
+    def __init__(self, model, lr=1e-5, world_size=1, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, groups=("pano", "nav")):
+        self.m, self.lr, self.world, self.betas, self.eps, self.wd = model, lr, world_size, betas, eps, weight_decay
+        model._refresh_cache()
+        dev = model._flat.device
+        model._direct_grad = torch.zeros(model.layout.total, dtype=torch.float32, device=dev)
+        self.lo = min(model.layout.group_ranges[g][0] for g in groups)
+        self.hi = max(model.layout.group_ranges[g][1] for g in groups)
+        n = self.hi - self.lo
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.t = 0
+        L = _L.lib()
+        L.etp_adamw_step.argtypes = [p_void, p_void, p_void, p_void, p_void, C.c_int64, f32, f32, f32, f32, f32, i32, f32,
+                                     p_void]
+
+    def zero_grad(self):
+        self.m._direct_grad[self.lo:self.hi].zero_()
+
+    def forward_backward(self, d):
+        m = self.m
+        pano, pmask = m.forward_panorama(d["rgb_fts"], d["dep_fts"], d["loc_fts"], d["nav_types"], d["view_lens"])
+        # the trainer feeds the masked mean of the view embeddings back into the map as a node feature
+        # (ss_trainer_ETP.py:838-839, graph_utils.py:206): here it is added to node 1 so the panorama branch trains
+        w = pmask.unsqueeze(-1).float()
+        avg = (pano * w).sum(1) / w.sum(1)
+        img = d["gmap_img_fts"].clone()
+        img[:, 1] = img[:, 1] + avg
+        nav = m.forward_navigation(d["txt_embeds"], d["txt_masks"], None, d["gmap_step_ids"], img, d["gmap_pos_fts"],
+                                   d["gmap_masks"], d["gmap_visited_masks"], d["gmap_pair_dists"])
+        logits = nav["global_logits"]
+        loss = torch.nn.functional.cross_entropy(logits, d["labels"], reduction="sum", ignore_index=-100) / logits.shape[0]
+        loss.backward()
+        return logits, loss
+
+    def optimizer_step(self):
+        m = self.m
+        g = m._direct_grad[self.lo:self.hi]
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(g)  # SUM over ranks; the 1/world of DDP's mean is folded into AdamW's grad_scale
+        self.t += 1
+        _L._check(_L.lib().etp_adamw_step(
+            C.c_void_p(m._flat.data_ptr() + 4 * self.lo), C.c_void_p(m._flat_bf16.data_ptr() + 2 * self.lo), _L.ptr(g),
+            _L.ptr(self.exp_avg), _L.ptr(self.exp_avg_sq), self.hi - self.lo, self.lr, self.betas[0], self.betas[1], self.eps,
+            self.wd, self.t, 1.0 / self.world, _L.stream_ptr()), "etp_adamw_step")
+        m._bf16_fresh = True  # AdamW rewrote the bf16 image of the updated slice
+
+    def step(self, d):
+        self.zero_grad()
+        logits, _ = self.forward_backward(d)
+        self.optimizer_step()
+        return logits
+
+
 
 
 def get_vlnbert_models(config=None):

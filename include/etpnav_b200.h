@@ -244,6 +244,35 @@ size_t etp_txt_saved_bytes(int32_t B, int32_t L, int32_t num_l_layers, int32_t t
 int etp_forward_txt(const etp_txt_weights* w, const int64_t* txt_ids, const uint8_t* txt_masks, int32_t B, int32_t L,
                     float* txt_embeds, void* saved, size_t saved_bytes, int32_t training, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * step level, backward (autograd counterparts; the reference gets these from torch autograd via
+ * scaler.scale(loss).backward(), ss_trainer_ETP.py:504).
+ * `grads` is the same struct type as the weights with EVERY pointer redirected into a flat fp32
+ * gradient buffer laid out like the parameters; parameter gradients are ACCUMULATED (+=) there.
+ * `saved` is the record the matching forward call wrote with training != 0; `work` is scratch.
+ * ------------------------------------------------------------------------------------------- */
+size_t etp_nav_bwd_work_bytes(int32_t B, int32_t N, int32_t L);
+size_t etp_pano_bwd_work_bytes(int32_t B, int32_t V);
+size_t etp_txt_bwd_work_bytes(int32_t B, int32_t L);
+/* d_gmap_embeds [B,N,768] and/or d_global_logits [B,N] (either may be NULL) -> d_txt_embeds [B,L,768],
+ * d_gmap_img_fts [B,N,768] (overwritten; either may be NULL) + parameter gradients. */
+int etp_backward_navigation(const etp_nav_weights* w, const etp_nav_weights* grads, const etp_nav_inputs* in,
+                            const float* d_gmap_embeds, const float* d_global_logits, void* saved, size_t saved_bytes,
+                            void* work, size_t work_bytes, float* d_txt_embeds, float* d_gmap_img_fts, void* stream);
+/* d_pano_embeds [B,V,768] -> d_rgb_fts [B,V,512], d_dep_fts [B,V,128] (either may be NULL) + parameter gradients. */
+int etp_backward_panorama(const etp_pano_weights* w, const etp_pano_weights* grads, const etp_pano_inputs* in,
+                          const uint8_t* pano_masks, const float* d_pano_embeds, void* saved, size_t saved_bytes,
+                          void* work, size_t work_bytes, float* d_rgb_fts, float* d_dep_fts, void* stream);
+int etp_backward_txt(const etp_txt_weights* w, const etp_txt_weights* grads, const int64_t* txt_ids,
+                     const uint8_t* txt_masks, int32_t B, int32_t L, const float* d_txt_embeds, void* saved,
+                     size_t saved_bytes, void* work, size_t work_bytes, void* stream);
+
+/* torch.optim.AdamW semantics (ss_trainer_ETP.py:213) over flat fp32 buffers; also rewrites the bf16 image of
+ * the parameters.  grad_scale multiplies the gradient first (1/world_size after the gradient all-reduce). */
+int etp_adamw_step(float* param, void* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
