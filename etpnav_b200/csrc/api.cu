@@ -10,6 +10,7 @@ void prof_enable(bool on);
 int prof_collect(double* ms, double* flops, long long* count);
 int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream);
 int attention_dispatch(const AttnArgs& a, cudaStream_t stream);
+int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream);
 }
 
 using namespace etp;
@@ -69,6 +70,23 @@ ETP_API int etp_attention_fwd(const etp_attn_args* g, void* stream) {
   if (g->impl == 1) return attention_fwd(a, S(stream));
   if (g->impl == 2) return attention_tc_fwd(a, S(stream));
   return attention_dispatch(a, S(stream));
+}
+
+ETP_API int etp_attention_bwd(const etp_attn_bwd_args* g, void* stream) {
+  ETP_REQUIRE(g != nullptr, "etp_attention_bwd: null args");
+  AttnBwdArgs a;
+  a.B = g->B; a.heads = g->heads; a.Sq = g->Sq; a.Sk = g->Sk;
+  a.q = static_cast<const bf16*>(g->q); a.k = static_cast<const bf16*>(g->k); a.v = static_cast<const bf16*>(g->v);
+  a.ldq = g->ldq; a.ldk = g->ldk; a.ldv = g->ldv;
+  a.out = static_cast<const bf16*>(g->out); a.ldo = g->ldo;
+  a.dout = static_cast<const bf16*>(g->dout); a.lddo = g->lddo;
+  a.lse = g->lse; a.dvec = g->dvec; a.scale = g->scale; a.key_valid = g->key_valid; a.mask_value = g->mask_value;
+  a.pair = g->pair; a.pair_w = g->pair_w; a.pair_b = g->pair_b;
+  a.dq = static_cast<bf16*>(g->dq); a.dk = static_cast<bf16*>(g->dk); a.dv = static_cast<bf16*>(g->dv);
+  a.lddq = g->lddq; a.lddk = g->lddk; a.lddv = g->lddv; a.dpair_w = g->dpair_w; a.dpair_b = g->dpair_b;
+  if (g->impl == 1) return attention_bwd(a, S(stream));
+  if (g->impl == 2) return attention_bwd_tc(a, S(stream));
+  return attention_bwd_dispatch(a, S(stream));
 }
 
 ETP_API int etp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t H,

@@ -209,6 +209,12 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   return ETP_OK;
 }
 
-int attention_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t stream) { return attention_bwd(a, stream); }
+bool attention_bwd_tc_supported(const AttnBwdArgs& a);          // attention_bwd_tc.cu
+int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream);
+
+int attention_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t stream) {
+  if (attention_bwd_tc_supported(a)) return attention_bwd_tc(a, stream);
+  return attention_bwd(a, stream);
+}
 
 }  // namespace etp

@@ -5,12 +5,14 @@
 // One CTA = one (batch, head, 128-query tile).  Q, and K/V in blocks of 128 keys, are brought in by TMA
 // (3-D tensor maps over [B, S, heads*64], 128-byte swizzle; rows past the sequence end are zero-filled by
 // the TMA unit).  Per key block:   S = Q.K^T  (tcgen05.mma M=128 N=128 K=64, fp32 in TMEM)
-//   -> four softmax warps, one query row per thread: tcgen05.ld, scale + key mask + pair bias, online
-//      max/sum in fp32, P = exp(S - m) written to shared memory as bf16 in the K-major 128B-swizzled
-//      layout the tensor core reads;
+//   -> four softmax warps, one query row per thread.  Pass 1: tcgen05.ld the scores, add the per-key mask
+//      (shared-memory broadcast) and the pair bias (staged coalesced through shared memory, 32 keys at a
+//      time), all in the log2 domain, track the row max and write the biased scores back to TMEM
+//      (tcgen05.st).  Pass 2: tcgen05.ld, P = exp2(s - m) -> bf16 -> shared memory in the K-major
+//      128B-swizzled layout the tensor core reads; online row sum;
 //   -> O_blk = P.V (tcgen05.mma M=128 N=64 K=128; V is consumed MN-major exactly as it lies in memory),
 //      read back and folded into the per-thread fp32 running output with the usual rescale.
-// 80 KB shared memory and 256 TMEM columns per CTA, so two CTAs share an SM and hide each other's
+// ~98 KB shared memory and 256 TMEM columns per CTA, so two CTAs share an SM and hide each other's
 // load / softmax phases.
 #include "common.cuh"
 #include "host.h"
@@ -26,9 +28,13 @@ constexpr int kD = 64;
 constexpr int kQBytes = kBQ * kD * 2;       // 16 KB
 constexpr int kKBytes = kBK * kD * 2;       // 16 KB
 constexpr int kPBytes = kBQ * kBK * 2;      // 32 KB (two 64-key swizzle panels of 16 KB)
-constexpr int kSmemBytes = kQBytes + 2 * kKBytes + kPBytes + 1024 + 256;
+constexpr int kPairStride = 33;
+constexpr int kPairBytes = kBQ * kPairStride * 4;
+constexpr int kSmemBytes = kQBytes + 2 * kKBytes + kPBytes + kPairBytes + kBK * 4 + 1024 + 256;
 constexpr int kThreads = 160;               // 4 softmax warps + 1 control warp
 constexpr uint32_t kTmemCols = 256;         // S: [0,128)  O_blk: [128,192)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 struct AttnDev {
   int B, heads, Sq, Sk;
@@ -53,7 +59,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = sQ + kQBytes;
   uint8_t* sV = sK + kKBytes;
   uint8_t* sP = sV + kKBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  float* sPair = reinterpret_cast<float*>(sP + kPBytes);
+  float* sKb = sPair + kBQ * kPairStride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKb + kBK);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;
   uint64_t* v_full = bars + 2;
@@ -130,10 +138,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int q = q0 + r;
     const bool qv = q < p.Sq;
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    const float pw = p.pair_w_dev ? __ldg(p.pair_w_dev) : p.pair_w;
-    const float pb = p.pair_b_dev ? __ldg(p.pair_b_dev) : p.pair_b;
-    const float* prow = (p.pair && qv) ? p.pair + (static_cast<size_t>(b) * p.Sq + q) * p.Sk : nullptr;
+    const float pw = (p.pair_w_dev ? __ldg(p.pair_w_dev) : p.pair_w) * kLog2e;
+    const float pb = (p.pair_b_dev ? __ldg(p.pair_b_dev) : p.pair_b) * kLog2e;
+    const float sl2 = p.scale * kLog2e;
+    const float mask2 = p.mask_value * kLog2e;
     const uint8_t* kvalid = p.key_valid ? p.key_valid + static_cast<size_t>(b) * p.Sk : nullptr;
+    const float* pair_b0 = p.pair ? p.pair + static_cast<size_t>(b) * p.Sq * p.Sk : nullptr;
     float m = -INFINITY, l = 0.f;
     float o[kD];
 #pragma unroll
@@ -142,31 +152,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < nblk; ++j) {
       const uint32_t ph = j & 1;
       const int k0 = j * kBK;
+      // per-key additive mask of this block (log2 domain); keys past the sequence end get -inf
+      {
+        const int k = k0 + r;
+        float kb = -INFINITY;
+        if (k < p.Sk) kb = (kvalid && !kvalid[k]) ? mask2 : 0.f;
+        sKb[r] = kb;
+      }
+      named_bar_sync(1, 128);
       mbar_wait(s_ready, ph);
       tc_fence_after();
-      // pass 1: block max of the biased scores
+      // pass 1: biased scores (log2 domain) -> TMEM, block max
       float mj = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < kBK; c += 32) {
+        if (pair_b0) {
+          // coalesced staging of pair[b, q0 + row, k0 + c + lane] for the 128 rows of the tile
+          const int key = k0 + c + lane;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int row = warp + 4 * i;
+            float v = 0.f;
+            if (q0 + row < p.Sq && key < p.Sk) v = __ldg(pair_b0 + static_cast<size_t>(q0 + row) * p.Sk + key);
+            sPair[row * kPairStride + lane] = v;
+          }
+          named_bar_sync(1, 128);
+        }
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_sel + c, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int k = k0 + c + i;
-          float s = -INFINITY;
-          if (k < p.Sk) {
-            s = __uint_as_float(v[i]) * p.scale;
-            if (kvalid && !kvalid[k]) s += p.mask_value;
-            if (prow) s += pw * prow[k] + pb;
-          }
+          float s = fmaf(__uint_as_float(v[i]), sl2, sKb[c + i]);
+          if (pair_b0) s += fmaf(pw, sPair[r * kPairStride + i], pb);
           mj = fmaxf(mj, s);
+          v[i] = __float_as_uint(s);
         }
+        tmem_st32(tmem_S + lane_sel + c, v);
+        if (pair_b0) named_bar_sync(1, 128);  // staging buffer is reused by the next chunk
       }
+      tmem_st_wait();
       const float m_new = fmaxf(m, mj);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = __expf(m - m_use);  // m = -inf on the first block -> 0
-      // pass 2: P = exp(s - m) -> bf16 -> swizzled shared memory; row sum
+      const float alpha = exp2f(m - m_use);  // m = -inf on the first block -> 0
+      // pass 2: P = exp2(s - m) -> bf16 -> swizzled shared memory; row sum
       float lsum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < kBK; c += 32) {
@@ -176,14 +205,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float e[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int k = k0 + c + i;
-          float s = -INFINITY;
-          if (k < p.Sk) {
-            s = __uint_as_float(v[i]) * p.scale;
-            if (kvalid && !kvalid[k]) s += p.mask_value;
-            if (prow) s += pw * prow[k] + pb;
-          }
-          e[i] = __expf(s - m_use);
+          e[i] = exp2f(__uint_as_float(v[i]) - m_use);
           lsum += e[i];
         }
         // 32 keys = 4 chunks of 16 B inside the 64-key panel (c >> 6)
@@ -223,7 +245,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                                    pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv), pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv));
         *reinterpret_cast<uint4*>(og + i) = u;
       }
-      if (p.lse) p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Sq + q] = m + __logf(l);
+      if (p.lse) p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Sq + q] = (m + log2f(l)) * kLn2;
     }
   }
 

@@ -72,6 +72,15 @@ class AttnArgs(C.Structure):
                 ("out", p_void), ("ldo", i32), ("lse", p_f32), ("impl", i32)]
 
 
+class AttnBwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("heads", i32), ("Sq", i32), ("Sk", i32),
+                ("q", p_void), ("k", p_void), ("v", p_void), ("ldq", i32), ("ldk", i32), ("ldv", i32),
+                ("out", p_void), ("ldo", i32), ("dout", p_void), ("lddo", i32), ("lse", p_f32), ("dvec", p_f32),
+                ("scale", f32), ("key_valid", p_void), ("mask_value", f32), ("pair", p_f32), ("pair_w", f32),
+                ("pair_b", f32), ("dq", p_void), ("dk", p_void), ("dv", p_void), ("lddq", i32), ("lddk", i32),
+                ("lddv", i32), ("dpair_w", p_f32), ("dpair_b", p_f32), ("impl", i32)]
+
+
 class PanoPackArgs(C.Structure):
     _fields_ = [("rows", i32)] + [(n, p_void) for n in (
         "rgb_lin", "dep_lin", "loc_fts", "nav_types", "loc_w", "loc_b", "img_g", "img_b", "dep_g", "dep_b",
@@ -87,6 +96,7 @@ class NodePackArgs(C.Structure):
 def _declare(L):
     L.etp_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     L.etp_attention_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+    L.etp_attention_bwd.argtypes = [C.POINTER(AttnBwdArgs), C.c_void_p]
     L.etp_layernorm_fwd.argtypes = [p_void, p_void, p_void, f32, i32, i32, p_void, p_void, p_void, p_void, p_void]
     L.etp_layernorm_bwd.argtypes = [p_void, p_void, p_void, p_void, p_void, i32, i32, p_void, i32, p_void, p_void,
                                     p_void, p_void]
@@ -145,6 +155,20 @@ def attention_fwd(q, k, v, out, *, B, heads, Sq, Sk, scale=0.125, key_valid=None
     a.pair, a.pair_w, a.pair_b = ptr(pair), pair_w, pair_b
     a.out, a.ldo, a.lse, a.impl = ptr(out), out.stride(0), ptr(lse), impl
     _check(lib().etp_attention_fwd(C.byref(a), stream_ptr()), "etp_attention_fwd")
+
+
+def attention_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, B, heads, Sq, Sk, scale=0.125, key_valid=None,
+                  mask_value=-10000.0, pair=None, pair_w=0.0, pair_b=0.0, dpair_w=None, dpair_b=None, impl=0):
+    a = AttnBwdArgs()
+    a.B, a.heads, a.Sq, a.Sk = B, heads, Sq, Sk
+    a.q, a.k, a.v, a.ldq, a.ldk, a.ldv = ptr(q), ptr(k), ptr(v), q.stride(0), k.stride(0), v.stride(0)
+    a.out, a.ldo, a.dout, a.lddo, a.lse = ptr(out), out.stride(0), ptr(dout), dout.stride(0), ptr(lse)
+    dvec = torch.empty(B * heads * Sq, device=q.device, dtype=torch.float32)
+    a.dvec, a.scale, a.key_valid, a.mask_value = ptr(dvec), scale, ptr(key_valid), mask_value
+    a.pair, a.pair_w, a.pair_b = ptr(pair), pair_w, pair_b
+    a.dq, a.dk, a.dv, a.lddq, a.lddk, a.lddv = ptr(dq), ptr(dk), ptr(dv), dq.stride(0), dk.stride(0), dv.stride(0)
+    a.dpair_w, a.dpair_b, a.impl = ptr(dpair_w), ptr(dpair_b), impl
+    _check(lib().etp_attention_bwd(C.byref(a), stream_ptr()), "etp_attention_bwd")
 
 
 def layernorm_fwd(x, gamma, beta, eps, y_f32=None, y_bf16=None, mean=None, rstd=None):

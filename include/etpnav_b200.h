@@ -97,6 +97,29 @@ typedef struct {
 } etp_attn_args;
 int etp_attention_fwd(const etp_attn_args* args, void* stream);
 
+/* Backward of etp_attention_fwd (same q/k/v/out/lse): dq, dk, dv (bf16) and, when `pair` is given, the
+ * sprel_linear gradients accumulated into the device scalars dpair_w / dpair_b.  dvec: fp32 scratch
+ * [B,heads,Sq].  impl: 0 auto, 1 CUDA-core, 2 tcgen05 (Sq <= 128). */
+typedef struct {
+  int32_t B, heads, Sq, Sk;
+  const void* q; const void* k; const void* v;
+  int32_t ldq, ldk, ldv;
+  const void* out; int32_t ldo;
+  const void* dout; int32_t lddo;
+  const float* lse;
+  float* dvec;
+  float scale;
+  const uint8_t* key_valid;
+  float mask_value;
+  const float* pair;
+  float pair_w, pair_b;
+  void* dq; void* dk; void* dv;
+  int32_t lddq, lddk, lddv;
+  float* dpair_w; float* dpair_b;
+  int32_t impl;
+} etp_attn_bwd_args;
+int etp_attention_bwd(const etp_attn_bwd_args* args, void* stream);
+
 /* LayerNorm over the last dim (768), biased variance (torch.nn.LayerNorm / BertLayerNorm,
  * vilmodel_cmt.py:24-28). */
 int etp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t H,

