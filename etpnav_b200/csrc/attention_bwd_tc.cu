@@ -178,21 +178,26 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (k < p.Sk) kb = (kvalid && !kvalid[k]) ? mask2 : 0.f;
         sKb[r] = kb;
       }
+      float prg[32];
+      auto load_pair = [&](int c) {
+        const int key = k0 + c + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int row = warp + 4 * i;
+          prg[i] = (row < p.Sq && key < p.Sk) ? __ldg(pair_b0 + static_cast<size_t>(row) * p.Sk + key) : 0.f;
+        }
+      };
+      if (pair_b0) load_pair(0);  // in flight while the S / dP MMAs run
       named_bar_sync(1, 128);
       mbar_wait(sdp_ready, ph);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < kBK; c += 32) {
         if (pair_b0) {
-          const int key = k0 + c + lane;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const int row = warp + 4 * i;
-            float v = 0.f;
-            if (row < p.Sq && key < p.Sk) v = __ldg(pair_b0 + static_cast<size_t>(row) * p.Sk + key);
-            sPair[row * kPairStride + lane] = v;
-          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sPair[(warp + 4 * i) * kPairStride + lane] = prg[i];
           named_bar_sync(1, 128);
+          if (c + 32 < kBK) load_pair(c + 32);
         }
         uint32_t vs[32], vd[32];
         tmem_ld32(tS + lane_sel + c, vs);

@@ -159,6 +159,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (k < p.Sk) kb = (kvalid && !kvalid[k]) ? mask2 : 0.f;
         sKb[r] = kb;
       }
+      // first 32-key chunk of the pair bias: issue the (coalesced) loads now, they land while the MMA runs
+      float pr[32];
+      auto load_pair = [&](int c) {
+        const int key = k0 + c + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int row = warp + 4 * i;
+          pr[i] = (q0 + row < p.Sq && key < p.Sk) ? __ldg(pair_b0 + static_cast<size_t>(q0 + row) * p.Sk + key) : 0.f;
+        }
+      };
+      if (pair_b0) load_pair(0);
       named_bar_sync(1, 128);
       mbar_wait(s_ready, ph);
       tc_fence_after();
@@ -168,15 +179,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int c = 0; c < kBK; c += 32) {
         if (pair_b0) {
           // coalesced staging of pair[b, q0 + row, k0 + c + lane] for the 128 rows of the tile
-          const int key = k0 + c + lane;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const int row = warp + 4 * i;
-            float v = 0.f;
-            if (q0 + row < p.Sq && key < p.Sk) v = __ldg(pair_b0 + static_cast<size_t>(q0 + row) * p.Sk + key);
-            sPair[row * kPairStride + lane] = v;
-          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sPair[(warp + 4 * i) * kPairStride + lane] = pr[i];
           named_bar_sync(1, 128);
+          if (c + 32 < kBK) load_pair(c + 32);  // software prefetch of the next chunk
         }
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_sel + c, v);

@@ -57,14 +57,25 @@ static int wgrad(const bf16* dY, int rows, int N_out, int ldy, const bf16* X, in
   g.M = N_out; g.N = K_in; g.K = rows;
   g.A = dY; g.lda = ldy; g.a_mn = 1;
   g.B = X; g.ldb = ldx; g.b_mn = 1;
-  g.out_f32 = static_cast<float*>(dW); g.ld_f32 = K_in; g.atomic = 1;
-  g.block_n = (K_in % 256 == 0) ? 256 : 128;
-  const int tiles = ((N_out + 127) / 128) * ((K_in + g.block_n - 1) / g.block_n);
+  g.out_f32 = static_cast<float*>(dW); g.ld_f32 = K_in;
+  // Few output tiles, long reduction (rows = tokens).  128x128 tiles; when they alone nearly fill the chip every
+  // tile owns its output and accumulates with a plain read-add-write (resid = out); otherwise split the token
+  // axis just enough to cover the SMs and accumulate with 128-bit vector reductions.
+  g.block_n = 128;
+  const int tiles = ((N_out + 127) / 128) * ((K_in + 127) / 128);
   const int kb = (rows + 63) / 64;
-  int splits = (2 * num_sms() + tiles - 1) / tiles;
-  if (splits > kb / 2) splits = kb / 2;
-  if (splits < 1) splits = 1;
+  int splits = 1;
+  if (tiles < (num_sms() * 2) / 3) {
+    splits = num_sms() / tiles;  // floor: one wave
+    if (splits > kb / 4) splits = kb / 4;
+    if (splits < 1) splits = 1;
+  }
   g.k_splits = splits;
+  if (splits > 1) {
+    g.atomic = 1;
+  } else {
+    g.resid = g.out_f32; g.ld_resid = K_in;  // dW = acc + dW
+  }
   return gemm(g, s);
 }
 
