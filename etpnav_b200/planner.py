@@ -625,15 +625,14 @@ class PlannerTrainer:
 
     def optimizer_step(self):
         m = self.m
+        from .dist import allreduce_flat_
         g = m._direct_grad[self.lo:self.hi]
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(g)  # SUM over ranks; the 1/world of DDP's mean is folded into AdamW's grad_scale
+        scale = allreduce_flat_(g, self.world)  # SUM over ranks; DDP's 1/world is folded into AdamW's grad_scale
         self.t += 1
         _L._check(_L.lib().etp_adamw_step(
             C.c_void_p(m._flat.data_ptr() + 4 * self.lo), C.c_void_p(m._flat_bf16.data_ptr() + 2 * self.lo), _L.ptr(g),
             _L.ptr(self.exp_avg), _L.ptr(self.exp_avg_sq), self.hi - self.lo, self.lr, self.betas[0], self.betas[1], self.eps,
-            self.wd, self.t, 1.0 / self.world, _L.stream_ptr()), "etp_adamw_step")
+            self.wd, self.t, scale, _L.stream_ptr()), "etp_adamw_step")
         m._bf16_fresh = True  # AdamW rewrote the bf16 image of the updated slice
 
     def step(self, d):
