@@ -17,6 +17,8 @@ constexpr int kKStride = 66;  // bf16 elements per K row in smem (33 words: conf
 constexpr int kQTile = 16;
 
 __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnArgs a, int sk_pad) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   extern __shared__ uint8_t smem[];
   bf16* Ks = reinterpret_cast<bf16*>(smem);
   bf16* Vs = Ks + static_cast<size_t>(sk_pad) * kKStride;
@@ -120,7 +122,7 @@ int attention_fwd(const AttnArgs& a, cudaStream_t stream) {
   }
   ETP_REQUIRE(smem <= 220 * 1024, "attention: K/V do not fit shared memory");
   dim3 grid((a.Sq + kQTile - 1) / kQTile, a.heads, a.B);
-  attention_fwd_kernel<<<grid, 256, smem, stream>>>(a, sk_pad);
+  ETP_CHECK_CUDA(launch_pdl(attention_fwd_kernel, dim3(grid), dim3(256), smem, stream, a, sk_pad));
   ETP_LAUNCHED();
   return ETP_OK;
 }

@@ -41,6 +41,8 @@ ETP_DEVICE void stage_rows(bf16* dst, const bf16* src, int rows, int ld) {
 }
 
 __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const AttnBwdArgs a, int sk_pad) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   extern __shared__ uint8_t smem[];
   bf16* Ks = reinterpret_cast<bf16*>(smem);
   bf16* Vs = Ks + static_cast<size_t>(sk_pad) * kStr;
@@ -119,6 +121,8 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const AttnBwdArgs a, i
 }
 
 __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const AttnBwdArgs a, int sq_pad) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   extern __shared__ uint8_t smem[];
   bf16* Qs = reinterpret_cast<bf16*>(smem);
   bf16* dOs = Qs + static_cast<size_t>(sq_pad) * kStr;
@@ -202,9 +206,9 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
     ETP_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
-  attn_bwd_dq_kernel<<<dim3((a.Sq + kTile - 1) / kTile, a.heads, a.B), 256, smem_a, stream>>>(a, sk_pad);
+  ETP_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel, dim3(dim3((a.Sq + kTile - 1) / kTile, a.heads, a.B)), dim3(256), smem_a, stream, a, sk_pad));
   ETP_LAUNCHED();
-  attn_bwd_dkv_kernel<<<dim3((a.Sk + kTile - 1) / kTile, a.heads, a.B), 256, smem_b, stream>>>(a, sq_pad);
+  ETP_CHECK_CUDA(launch_pdl(attn_bwd_dkv_kernel, dim3(dim3((a.Sk + kTile - 1) / kTile, a.heads, a.B)), dim3(256), smem_b, stream, a, sq_pad));
   ETP_LAUNCHED();
   return ETP_OK;
 }

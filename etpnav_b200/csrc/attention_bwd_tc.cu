@@ -82,6 +82,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     fence_barrier_init();
     fence_proxy_async();
   }
+  griddep_launch();  // PDL: the next kernel may start its own prologue
+  griddep_wait();    // previous kernel complete; nothing above touched global memory or TMEM
   if (warp == 4) {
     tmem_alloc(tmem_ptr, kTmemCols);
     tmem_relinquish();
@@ -336,7 +338,7 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream) {
   d.pair_b_dev = a.pair_b_dev; d.out = a.out; d.ldo = a.ldo; d.dout = a.dout; d.lddo = a.lddo; d.lse = a.lse;
   d.dq = a.dq; d.dk = a.dk; d.dv = a.dv; d.lddq = a.lddq; d.lddk = a.lddk; d.lddv = a.lddv;
   d.dpair_w = a.dpair_w; d.dpair_b = a.dpair_b;
-  attention_bwd_tc_kernel<<<dim3(a.heads, a.B), kThreads, kSmemBytes, stream>>>(tq, tdo, tk, tv, d);
+  ETP_CHECK_CUDA(launch_pdl(attention_bwd_tc_kernel, dim3(dim3(a.heads, a.B)), dim3(kThreads), kSmemBytes, stream, tq, tdo, tk, tv, d));
   ETP_LAUNCHED();
   return ETP_OK;
 }

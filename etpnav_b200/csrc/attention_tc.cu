@@ -87,6 +87,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_barrier_init();
     fence_proxy_async();
   }
+  griddep_launch();  // PDL: the next kernel may start its own prologue
+  griddep_wait();    // previous kernel complete; nothing above touched global memory or TMEM
   if (warp == 4) {
     tmem_alloc(tmem_ptr, kTmemCols);
     tmem_relinquish();
@@ -292,7 +294,7 @@ int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream) {
   d.mask_value = a.mask_value; d.pair = a.pair; d.pair_w = a.pair_w; d.pair_b = a.pair_b;
   d.pair_w_dev = a.pair_w_dev; d.pair_b_dev = a.pair_b_dev; d.out = a.out; d.ldo = a.ldo; d.lse = a.lse;
   dim3 grid((a.Sq + kBQ - 1) / kBQ, a.heads, a.B);
-  attention_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tq, tk, tv, d);
+  ETP_CHECK_CUDA(launch_pdl(attention_tc_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, tq, tk, tv, d));
   ETP_LAUNCHED();
   return ETP_OK;
 }

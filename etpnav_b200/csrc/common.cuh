@@ -25,6 +25,16 @@ ETP_DEVICE bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization.  griddep_launch() lets the NEXT kernel in the stream
+// start being scheduled once all CTAs of this grid have issued it; griddep_wait() blocks until the PREVIOUS
+// grid has completed and its memory is visible.  Rule: nothing that touches global memory, and nothing that
+// can spin on a cross-kernel resource (TMEM allocation), may precede griddep_wait().
+// ----------------------------------------------------------------------------------------------
+ETP_DEVICE void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+ETP_DEVICE void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 ETP_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                              const float* __restrict__ beta, float eps, int rows,
                                                              float* __restrict__ y_f32, bf16* __restrict__ y_bf16,
                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -68,7 +70,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
                   bf16* y_bf16, float* mean, float* rstd, cudaStream_t stream) {
   ETP_REQUIRE(H == kH, "layernorm: hidden size must be 768");
   if (rows <= 0) return ETP_OK;
-  layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, eps, rows, y_f32, y_bf16, mean, rstd);
+  ETP_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, gamma, beta, eps, rows, y_f32, y_bf16, mean, rstd));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                              const float* __restrict__ rstd, int rows, float* __restrict__ dx_f32,
                                                              int accumulate_dx, bf16* __restrict__ dx_bf16,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   __shared__ float red[8][kH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g[24], dg[24], db[24];
@@ -150,8 +154,8 @@ int layernorm_bwd(const float* dy, const float* x, const float* gamma, const flo
   if (rows <= 0) return ETP_OK;
   int grid = (rows + 7) / 8;
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
-  layernorm_bwd_kernel<<<grid, 256, 0, stream>>>(dy, x, gamma, mean, rstd, rows, dx_f32, accumulate_dx, dx_bf16, dgamma,
-                                                 dbeta);
+  ETP_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(grid), dim3(256), 0, stream, dy, x, gamma, mean, rstd, rows, dx_f32, accumulate_dx, dx_bf16, dgamma,
+                                                 dbeta));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -161,6 +165,8 @@ int layernorm_bwd(const float* dy, const float* x, const float* gamma, const flo
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int rows, int cols, int ld, int rows_per_cta,
                                                       float* __restrict__ out) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   __shared__ float red[8][64];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + tx * 2;
@@ -200,7 +206,7 @@ static int colsum_impl(const T* x, int rows, int cols, int ld, float* out, cudaS
   int rpc = (rows + gy - 1) / gy;
   if (rpc < 64) rpc = 64;
   gy = (rows + rpc - 1) / rpc;
-  colsum_kernel<T><<<dim3(gx, gy), 256, 0, stream>>>(x, rows, cols, ld, rpc, out);
+  ETP_CHECK_CUDA(launch_pdl(colsum_kernel<T>, dim3(dim3(gx, gy)), dim3(256), 0, stream, x, rows, cols, ld, rpc, out));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -212,6 +218,8 @@ int colsum_f32(const float* x, int rows, int cols, int ld, float* out, cudaStrea
 }
 
 __global__ void cast_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n4) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float4 t = reinterpret_cast<const float4*>(x)[i];
@@ -219,6 +227,8 @@ __global__ void cast_kernel(const float* __restrict__ x, bf16* __restrict__ y, i
   }
 }
 __global__ void cast_tail_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t start, int64_t n) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   const int64_t i = start + threadIdx.x;
   if (i < n) y[i] = __float2bfloat16(x[i]);
 }
@@ -229,14 +239,16 @@ int cast_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream) {
   if (n4 > 0) {
     int64_t blocks = (n4 + 255) / 256;
     if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-    cast_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, y, n4);
+    ETP_CHECK_CUDA(launch_pdl(cast_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, x, y, n4));
   }
-  if (n4 * 4 < n) cast_tail_kernel<<<1, 32, 0, stream>>>(x, y, n4 * 4, n);
+  if (n4 * 4 < n) ETP_CHECK_CUDA(launch_pdl(cast_tail_kernel, dim3(1), dim3(32), 0, stream, x, y, n4 * 4, n));
   ETP_LAUNCHED();
   return ETP_OK;
 }
 
 __global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     dst[i] += src[i];
@@ -245,7 +257,7 @@ int add_f32(float* dst, const float* src, int64_t n, cudaStream_t stream) {
   if (n <= 0) return ETP_OK;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  add_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dst, src, n);
+  ETP_CHECK_CUDA(launch_pdl(add_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, dst, src, n));
   ETP_LAUNCHED();
   return ETP_OK;
 }

@@ -84,6 +84,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_barrier_init();
     fence_proxy_async();
   }
+  griddep_launch();  // PDL: the next kernel may start its own prologue
+  griddep_wait();    // previous kernel complete; nothing above touched global memory or TMEM
   if (warp == 1) {
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     tmem_relinquish();
@@ -334,7 +336,7 @@ static int launch_gemm(const GemmArgs& a, const GemmDev& dev, cudaStream_t strea
   const int tiles = dev.tiles_m * dev.tiles_n * dev.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   prof_gemm_begin(stream);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, dev);
+  ETP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, dev));
   prof_gemm_end(stream, 2.0 * a.M * a.N * a.K);
   ETP_LAUNCHED();
   return ETP_OK;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <utility>
 #include <string>
 
 namespace etp {
@@ -35,6 +36,18 @@ extern std::atomic<long long> g_launches;
     ::etp::g_launches.fetch_add(1, std::memory_order_relaxed);    \
     ETP_CHECK_CUDA(cudaGetLastError());                           \
   } while (0)
+
+// launch with programmatic stream serialization (see griddep_* in common.cuh)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // optional per-launch CUDA-event timing of the tcgen05 GEMM (bench.py roofline leg)
 void prof_gemm_begin(cudaStream_t s);

@@ -52,6 +52,8 @@ ETP_DEVICE void ln_accum(const float (&v)[24], const float* g, const float* b, i
 }
 
 __global__ void __launch_bounds__(256) pano_pack_kernel(const PanoPackArgs a) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= a.rows) return;
@@ -102,12 +104,14 @@ __global__ void __launch_bounds__(256) pano_pack_kernel(const PanoPackArgs a) {
 int pano_pack_fwd(const PanoPackArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return ETP_OK;
   ETP_REQUIRE(a.rgb_lin && a.loc_fts && a.nav_types && a.x_f32, "pano_pack: null argument");
-  pano_pack_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a);
+  ETP_CHECK_CUDA(launch_pdl(pano_pack_kernel, dim3((a.rows + 7) / 8), dim3(256), 0, stream, a));
   ETP_LAUNCHED();
   return ETP_OK;
 }
 
 __global__ void __launch_bounds__(256) node_pack_kernel(const NodePackArgs a) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= a.rows) return;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(256) node_pack_kernel(const NodePackArgs a) {
 int node_pack_fwd(const NodePackArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return ETP_OK;
   ETP_REQUIRE(a.img_fts && a.step_ids && a.pos_fts && a.x_f32, "node_pack: null argument");
-  node_pack_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a);
+  ETP_CHECK_CUDA(launch_pdl(node_pack_kernel, dim3((a.rows + 7) / 8), dim3(256), 0, stream, a));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -155,6 +159,8 @@ __global__ void __launch_bounds__(256) sap_tail_kernel(const float* __restrict__
                                                         const uint8_t* __restrict__ valid, int rows,
                                                         float* __restrict__ logits, float* __restrict__ mean_out,
                                                         float* __restrict__ rstd_out) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -182,8 +188,8 @@ int sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, c
                  float* rstd, cudaStream_t stream) {
   ETP_REQUIRE(H == kH, "sap_tail: hidden size must be 768");
   if (rows <= 0) return ETP_OK;
-  sap_tail_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(relu_out, gamma, beta, w4, b4, visited, valid, rows, logits, mean,
-                                                      rstd);
+  ETP_CHECK_CUDA(launch_pdl(sap_tail_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, relu_out, gamma, beta, w4, b4, visited, valid, rows, logits, mean,
+                                                      rstd));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -198,6 +204,8 @@ __global__ void __launch_bounds__(256) embed_txt_kernel(const int64_t* __restric
                                                          float eps, int rows, int L, float* __restrict__ x_f32,
                                                          bf16* __restrict__ x_bf16, float* __restrict__ sum_pre,
                                                          float* __restrict__ stats) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -223,19 +231,21 @@ int embed_txt_fwd(const int64_t* ids, const float* word_emb, const float* pos_em
                   float* sum_pre, float* stats, cudaStream_t stream) {
   const int rows = B * L;
   if (rows <= 0) return ETP_OK;
-  embed_txt_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, word_emb, pos_emb, type_emb0, gamma, beta, eps, rows, L,
-                                                       x_f32, x_bf16, sum_pre, stats);
+  ETP_CHECK_CUDA(launch_pdl(embed_txt_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, ids, word_emb, pos_emb, type_emb0, gamma, beta, eps, rows, L,
+                                                       x_f32, x_bf16, sum_pre, stats));
   ETP_LAUNCHED();
   return ETP_OK;
 }
 
 __global__ void seq_mask_kernel(const int64_t* __restrict__ lens, int B, int V, uint8_t* __restrict__ mask) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * V) mask[i] = (i % V) < lens[i / V] ? 1 : 0;
 }
 int seq_mask(const int64_t* lens, int B, int V, uint8_t* mask, cudaStream_t stream) {
   if (B * V <= 0) return ETP_OK;
-  seq_mask_kernel<<<(B * V + 255) / 256, 256, 0, stream>>>(lens, B, V, mask);
+  ETP_CHECK_CUDA(launch_pdl(seq_mask_kernel, dim3((B * V + 255) / 256), dim3(256), 0, stream, lens, B, V, mask));
   ETP_LAUNCHED();
   return ETP_OK;
 }

@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(256) sap_tail_bwd_kernel(const float* __restri
                                                             const float* __restrict__ rstd, const uint8_t* __restrict__ visited,
                                                             const uint8_t* __restrict__ valid, int rows, bf16* __restrict__ dpre,
                                                             float* dgamma, float* dbeta, float* dw4, float* db4) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   extern __shared__ float sm[];  // [3][768] + [1]
   float* s_g = sm; float* s_b = sm + kH; float* s_w = sm + 2 * kH; float* s_b4 = sm + 3 * kH;
   zero_smem(sm, 3 * kH + 1);
@@ -117,8 +119,8 @@ int sap_tail_bwd(const float* dlogits, const float* relu_out, const float* gamma
                  const float* mean, const float* rstd, const uint8_t* visited, const uint8_t* valid, int rows,
                  bf16* dpre_bf16, float* dgamma, float* dbeta, float* dw4, float* db4, cudaStream_t stream) {
   if (rows <= 0) return ETP_OK;
-  sap_tail_bwd_kernel<<<grid_for(rows), 256, (3 * kH + 1) * sizeof(float), stream>>>(
-      dlogits, relu_out, gamma, beta, w4, mean, rstd, visited, valid, rows, dpre_bf16, dgamma, dbeta, dw4, db4);
+  ETP_CHECK_CUDA(launch_pdl(sap_tail_bwd_kernel, dim3(grid_for(rows)), dim3(256), (3 * kH + 1) * sizeof(float), stream, 
+      dlogits, relu_out, gamma, beta, w4, mean, rstd, visited, valid, rows, dpre_bf16, dgamma, dbeta, dw4, db4));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(256) node_pack_bwd_kernel(const float* __restr
                                                              const float* __restrict__ stats, const float* __restrict__ pos_g,
                                                              int rows, float* dstep_emb, float* dpos_w, float* dpos_b,
                                                              float* dpos_g, float* dpos_bb) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   extern __shared__ float sm[];
   float* s_w = sm;                       // [768*7]
   float* s_b = s_w + kH * 7;             // [768]
@@ -190,14 +194,16 @@ int node_pack_bwd(const float* dx, const int64_t* step_ids, const float* pos_fts
   }
   int grid = grid_for(rows);
   if (grid > num_sms()) grid = num_sms();
-  node_pack_bwd_kernel<<<grid, 256, smem, stream>>>(dx, step_ids, pos_fts, pos_lin, stats, pos_g, rows, dstep_emb, dpos_w,
-                                                    dpos_b, dpos_g, dpos_bb);
+  ETP_CHECK_CUDA(launch_pdl(node_pack_bwd_kernel, dim3(grid), dim3(256), smem, stream, dx, step_ids, pos_fts, pos_lin, stats, pos_g, rows, dstep_emb, dpos_w,
+                                                    dpos_b, dpos_g, dpos_bb));
   ETP_LAUNCHED();
   return ETP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pano_pack_bwd_kernel(const PanoPackBwdArgs a) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   extern __shared__ float sm[];
   // [0] out_g [1] out_b [2] img_g [3] img_b [4] dep_g [5] dep_b [6] loc_g [7] loc_b [8] loc_bias [9] tok [10,11] nav [12..15] loc_w
   zero_smem(sm, 16 * kH);
@@ -269,7 +275,7 @@ int pano_pack_bwd(const PanoPackBwdArgs& a, cudaStream_t stream) {
   }
   int grid = grid_for(a.rows);
   if (grid > num_sms()) grid = num_sms();
-  pano_pack_bwd_kernel<<<grid, 256, smem, stream>>>(a);
+  ETP_CHECK_CUDA(launch_pdl(pano_pack_bwd_kernel, dim3(grid), dim3(256), smem, stream, a));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -279,6 +285,8 @@ __global__ void __launch_bounds__(256) embed_txt_bwd_kernel(const float* __restr
                                                              const float* __restrict__ sum_pre, const float* __restrict__ stats,
                                                              const float* __restrict__ gamma, int rows, int L, float* dword,
                                                              float* dpos, float* dtype0, float* dgamma, float* dbeta) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   extern __shared__ float sm[];  // [3][768]: gamma, beta, type0
   zero_smem(sm, 3 * kH);
   __syncthreads();
@@ -313,8 +321,8 @@ int embed_txt_bwd(const float* dx, const int64_t* ids, const float* sum_pre, con
                   cudaStream_t stream) {
   const int rows = B * L;
   if (rows <= 0) return ETP_OK;
-  embed_txt_bwd_kernel<<<grid_for(rows), 256, 3 * kH * sizeof(float), stream>>>(dx, ids, sum_pre, stats, gamma, rows, L,
-                                                                                 dword, dpos, dtype0, dgamma, dbeta);
+  ETP_CHECK_CUDA(launch_pdl(embed_txt_bwd_kernel, dim3(grid_for(rows)), dim3(256), 3 * kH * sizeof(float), stream, dx, ids, sum_pre, stats, gamma, rows, L,
+                                                                                 dword, dpos, dtype0, dgamma, dbeta));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -325,6 +333,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, bf16*
                                                      float* __restrict__ m, float* __restrict__ v, int64_t n4, float lr,
                                                      float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
                                                      float gscale) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
@@ -361,8 +371,8 @@ int adamw_step(float* param, bf16* param_bf16, const float* grad, float* exp_avg
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
-  adamw_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(param, param_bf16, grad, exp_avg, exp_avg_sq, n / 4, lr, beta1,
-                                                             beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  ETP_CHECK_CUDA(launch_pdl(adamw_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, param, param_bf16, grad, exp_avg, exp_avg_sq, n / 4, lr, beta1,
+                                                             beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale));
   ETP_LAUNCHED();
   return ETP_OK;
 }

@@ -16,7 +16,7 @@ void LayerRecord::carve(Arena& ar, int rows, int kv_rows, int B, int Sq, bool cr
   const size_t r = rows;
   if (cross) {
     q = ar.take<bf16>(r * kH);
-    kv = ar.take<bf16>(static_cast<size_t>(kv_rows) * 2 * kH);
+    if (kv_rows > 0) { kv = ar.take<bf16>(static_cast<size_t>(kv_rows) * 2 * kH); ldkv = 2 * kH; }
     ctx1 = ar.take<bf16>(r * kH);
     lse1 = ar.take<float>(static_cast<size_t>(B) * kHeads * Sq);
     t1 = ar.take<float>(r * kH);
@@ -39,6 +39,7 @@ void LayerRecord::carve(Arena& ar, int rows, int kv_rows, int B, int Sq, bool cr
 void NavRecord::carve(Arena& ar, int B, int N, int L, int X, bool training) {
   const size_t rows = static_cast<size_t>(B) * N;
   txtb = ar.take<bf16>(static_cast<size_t>(B) * L * kH);
+  kv_all = ar.take<bf16>(static_cast<size_t>(B) * L * 2 * kH * (X > 0 ? X : 1));
   x0b = ar.take<bf16>(rows * kH);
   pos_lin = ar.take<float>(rows * kH);
   pos_stats = ar.take<float>(rows * 2);
@@ -51,7 +52,9 @@ void NavRecord::carve(Arena& ar, int B, int N, int L, int X, bool training) {
   const size_t mark = ar.off;
   for (int i = 0; i < X; ++i) {
     if (!training) ar.off = mark;  // inference: all layers alias one scratch record
-    layers[i].carve(ar, static_cast<int>(rows), B * L, B, N, true);
+    layers[i].carve(ar, static_cast<int>(rows), 0, B, N, true);
+    layers[i].kv = kv_all + static_cast<size_t>(i) * 2 * kH;  // slice of the all-layer K|V buffer
+    layers[i].ldkv = X * 2 * kH;
   }
 }
 
@@ -166,6 +169,9 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
   np.pos_lin = training ? rec.pos_lin : nullptr; np.stats = rec.pos_stats;
   ETP_TRY(node_pack_fwd(np, s));
 
+  // text K|V of every layer in ONE GEMM: [B*L,768] x [X*1536,768]^T (they depend only on txt_embeds)
+  if (X > 0)
+    ETP_TRY(linear(rec.txtb, B * L, kH, w.xkv_all_w, X * 2 * kH, w.xkv_all_b, 0, nullptr, nullptr, rec.kv_all, nullptr, s));
   const float* x_f32 = np.x_f32;
   const bf16* x_bf16 = rec.x0b;
   for (int i = 0; i < X; ++i) {
@@ -173,12 +179,11 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
     LayerRecord& r = rec.layers[i];
     // cross-attention: nodes query the instruction (BertXAttention, vilmodel_cmt.py:354-363,325-352)
     ETP_TRY(linear(x_bf16, rows, kH, lw.xq_w, kH, lw.xq_b, 0, nullptr, nullptr, r.q, nullptr, s));
-    ETP_TRY(linear(rec.txtb, B * L, kH, lw.xkv_w, 2 * kH, lw.xkv_b, 0, nullptr, nullptr, r.kv, nullptr, s));
     AttnArgs at;
     at.B = B; at.heads = kHeads; at.Sq = N; at.Sk = L;
     at.q = r.q; at.ldq = kH;
-    at.k = r.kv; at.ldk = 2 * kH;
-    at.v = r.kv + kH; at.ldv = 2 * kH;
+    at.k = r.kv; at.ldk = r.ldkv;
+    at.v = r.kv + kH; at.ldv = r.ldkv;
     at.scale = 0.125f; at.key_valid = in.txt_masks; at.mask_value = -10000.0f;
     at.out = r.ctx1; at.ldo = kH; at.lse = r.lse1;
     ETP_TRY(attention_dispatch(at, s));

@@ -44,11 +44,13 @@ struct LayerRecord {
   float* t3 = nullptr;
   float* st3 = nullptr;
   bf16* xb = nullptr;  // block output (bf16)
+  int ldkv = 0;        // row pitch of kv (elements): 2*768 when owned, X*1536 when it is a slice of NavRecord::kv_all
   void carve(Arena& ar, int rows, int kv_rows, int B, int Sq, bool cross);
 };
 
 struct NavRecord {
   bf16* txtb = nullptr;
+  bf16* kv_all = nullptr;  // text K|V of all layers, [B*L, X*1536]
   bf16* x0b = nullptr;
   float *pos_lin = nullptr, *pos_stats = nullptr;
   float *xa = nullptr, *xc = nullptr, *xf = nullptr;  // fp32 residual-stream scratch

@@ -25,12 +25,12 @@ struct BwdScratch {
   bf16* dkv = nullptr;                                  // bf16 [kv_rows,1536]
   float* dvec = nullptr;                                // fp32 [B,heads,S]
   float* dtxt = nullptr;                                // fp32 [kv_rows,768]
-  void carve(Arena& ar, size_t rows, size_t kv_rows, size_t bhs) {
+  void carve(Arena& ar, size_t rows, size_t kv_rows, size_t bhs, size_t kv_layers = 1) {
     g0 = ar.take<float>(rows * kH); g1 = ar.take<float>(rows * kH); g2 = ar.take<float>(rows * kH);
     gb = ar.take<bf16>(rows * kH); dctx = ar.take<bf16>(rows * kH); dq = ar.take<bf16>(rows * kH);
     dqkv = ar.take<bf16>(rows * 3 * kH);
     dpre = ar.take<bf16>(rows * kI);
-    dkv = ar.take<bf16>(kv_rows * 2 * kH);
+    dkv = ar.take<bf16>(kv_rows * 2 * kH * kv_layers);  // all layers' dK|dV side by side
     dvec = ar.take<float>(bhs);
     dtxt = ar.take<float>(kv_rows * kH);
   }
@@ -136,7 +136,7 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
   ETP_REQUIRE(ar.off <= saved_bytes, "backward_navigation: saved buffer too small");
   Arena wa(work, work_bytes);
   BwdScratch sc;
-  sc.carve(wa, rows, kv_rows, static_cast<size_t>(B) * kHeads * (N > L ? N : L));
+  sc.carve(wa, rows, kv_rows, static_cast<size_t>(B) * kHeads * (N > L ? N : L), X > 0 ? X : 1);
   float* P = wa.take<float>(static_cast<size_t>(rows) * kH);
   float* Q = wa.take<float>(static_cast<size_t>(rows) * kH);
   ETP_REQUIRE(wa.off <= work_bytes, "backward_navigation: workspace too small");
@@ -153,7 +153,7 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     ETP_CHECK_CUDA(cudaMemcpyAsync(P, d_gmap_embeds, static_cast<size_t>(rows) * kH * 4, cudaMemcpyDeviceToDevice, s));
   }
   float* dtxt = d_txt_embeds ? d_txt_embeds : sc.dtxt;
-  bool dtxt_init = false;
+  const int ldkv = X * 2 * kH;
   for (int i = X - 1; i >= 0; --i) {
     const etp_layer_weights& lw = w.layers[i];
     const etp_layer_weights& lg = g.layers[i];
@@ -168,21 +168,24 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.xo_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
     AttnBwdArgs at;
     at.B = B; at.heads = kHeads; at.Sq = N; at.Sk = L;
-    at.q = r.q; at.ldq = kH; at.k = r.kv; at.ldk = 2 * kH; at.v = r.kv + kH; at.ldv = 2 * kH;
+    at.q = r.q; at.ldq = kH; at.k = r.kv; at.ldk = r.ldkv; at.v = r.kv + kH; at.ldv = r.ldkv;
     at.out = r.ctx1; at.ldo = kH; at.dout = sc.dctx; at.lddo = kH; at.lse = r.lse1; at.dvec = sc.dvec;
     at.scale = 0.125f; at.key_valid = in.txt_masks; at.mask_value = -10000.0f;
-    at.dq = sc.dq; at.lddq = kH; at.dk = sc.dkv; at.lddk = 2 * kH; at.dv = sc.dkv + kH; at.lddv = 2 * kH;
+    bf16* dkv_i = sc.dkv + static_cast<size_t>(i) * 2 * kH;  // this layer's slice of [B*L, X*1536]
+    at.dq = sc.dq; at.lddq = kH; at.dk = dkv_i; at.lddk = ldkv; at.dv = dkv_i + kH; at.lddv = ldkv;
     ETP_TRY(attention_bwd_dispatch(at, s));
     ETP_TRY(bias_grad(sc.dq, rows, kH, kH, lg.xq_b, s));
     ETP_TRY(wgrad(sc.dq, rows, kH, kH, x_in, kH, kH, const_cast<void*>(lg.xq_w), s));
     ETP_TRY(dgrad(sc.dq, rows, kH, kH, lw.xq_w, kH, sc.g0, P, nullptr, 0, nullptr, s));  // dx_in = dq.Wq + dt1
-    ETP_TRY(bias_grad(sc.dkv, kv_rows, 2 * kH, 2 * kH, lg.xkv_b, s));
-    ETP_TRY(wgrad(sc.dkv, kv_rows, 2 * kH, 2 * kH, rec.txtb, kH, kH, const_cast<void*>(lg.xkv_w), s));
-    ETP_TRY(dgrad(sc.dkv, kv_rows, 2 * kH, 2 * kH, lw.xkv_w, kH, dtxt_init ? dtxt : nullptr, dtxt, nullptr, 0, nullptr, s));
-    dtxt_init = true;
   }
-  if (d_txt_embeds && !dtxt_init)
+  // text side, all layers at once: kv_all = txt . Wkv_all^T + b  ->  one bias-grad, one wgrad, one dgrad
+  if (X > 0) {
+    ETP_TRY(bias_grad(sc.dkv, kv_rows, ldkv, ldkv, g.xkv_all_b, s));
+    ETP_TRY(wgrad(sc.dkv, kv_rows, ldkv, ldkv, rec.txtb, kH, kH, const_cast<void*>(g.xkv_all_w), s));
+    if (d_txt_embeds) ETP_TRY(dgrad(sc.dkv, kv_rows, ldkv, ldkv, w.xkv_all_w, kH, nullptr, dtxt, nullptr, 0, nullptr, s));
+  } else if (d_txt_embeds) {
     ETP_CHECK_CUDA(cudaMemsetAsync(d_txt_embeds, 0, static_cast<size_t>(kv_rows) * kH * 4, s));
+  }
   // node packing: x0 = img_fts + E_step[ids] + LN(pos_fts.W^T + b)
   ETP_TRY(node_pack_bwd(P, in.gmap_step_ids, in.gmap_pos_fts, rec.pos_lin, rec.pos_stats, w.pos_g, rows, F(g.step_emb),
                         F(g.pos_w), F(g.pos_b), F(g.pos_g), F(g.pos_bb), s));
@@ -289,10 +292,10 @@ int backward_txt(const etp_txt_weights& w, const etp_txt_weights& g, const int64
   return ETP_OK;
 }
 
-static size_t work_bytes_for(size_t rows, size_t kv_rows, size_t bhs) {
+static size_t work_bytes_for(size_t rows, size_t kv_rows, size_t bhs, size_t kv_layers = 1) {
   Arena wa(nullptr, ~size_t(0));
   BwdScratch sc;
-  sc.carve(wa, rows, kv_rows, bhs);
+  sc.carve(wa, rows, kv_rows, bhs, kv_layers);
   wa.take<float>(rows * kH);
   wa.take<float>(rows * kH);
   return wa.off;
@@ -306,8 +309,9 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 
 extern "C" {
 
-ETP_API size_t etp_nav_bwd_work_bytes(int32_t B, int32_t N, int32_t L) {
-  return work_bytes_for(static_cast<size_t>(B) * N, static_cast<size_t>(B) * L, static_cast<size_t>(B) * kHeads * (N > L ? N : L));
+ETP_API size_t etp_nav_bwd_work_bytes(int32_t B, int32_t N, int32_t L, int32_t num_x_layers) {
+  return work_bytes_for(static_cast<size_t>(B) * N, static_cast<size_t>(B) * L, static_cast<size_t>(B) * kHeads * (N > L ? N : L),
+                        num_x_layers > 0 ? num_x_layers : 1);
 }
 ETP_API size_t etp_pano_bwd_work_bytes(int32_t B, int32_t V) {
   return work_bytes_for(static_cast<size_t>(B) * V, 0, static_cast<size_t>(B) * kHeads * V);

@@ -57,11 +57,17 @@ def ordered_names(cfg: PlannerConfig):
            "global_encoder.gmap_step_embeddings.weight"]
     if cfg.graph_sprels:
         nv += ["global_encoder.sprel_linear.weight", "global_encoder.sprel_linear.bias"]
+    # text-side key|value projections of ALL cross-modal layers are adjacent: K/V of every layer come out of ONE
+    # [B*L,768] x [X*1536,768]^T GEMM (they depend only on txt_embeds), and their dgrad / wgrad are one GEMM each
+    for i in range(cfg.num_x_layers):
+        p = f"global_encoder.encoder.x_layers.{i}."
+        nv += [p + f"visual_attention.att.{n}.weight" for n in ("key", "value")]
+    for i in range(cfg.num_x_layers):
+        p = f"global_encoder.encoder.x_layers.{i}."
+        nv += [p + f"visual_attention.att.{n}.bias" for n in ("key", "value")]
     for i in range(cfg.num_x_layers):
         p = f"global_encoder.encoder.x_layers.{i}."
         nv += [p + "visual_attention.att.query.weight", p + "visual_attention.att.query.bias"]
-        nv += [p + f"visual_attention.att.{n}.weight" for n in ("key", "value")]
-        nv += [p + f"visual_attention.att.{n}.bias" for n in ("key", "value")]
         nv += [p + "visual_attention.output.dense.weight", p + "visual_attention.output.dense.bias",
                p + "visual_attention.output.LayerNorm.weight", p + "visual_attention.output.LayerNorm.bias"]
         nv += [p + f"visn_self_att.self.{n}.weight" for n in ("query", "key", "value")]

@@ -37,7 +37,7 @@ class LayerWeights(C.Structure):
 class NavWeights(C.Structure):
     _fields_ = [("num_x_layers", i32), ("ln_eps", f32), ("layers", C.POINTER(LayerWeights))] + [
         (n, p_void) for n in ("pos_w", "pos_b", "pos_g", "pos_bb", "step_emb", "sprel_w", "sprel_b",
-                              "sap0_w", "sap0_b", "sap_g", "sap_bb", "sap4_w", "sap4_b")]
+                              "sap0_w", "sap0_b", "sap_g", "sap_bb", "sap4_w", "sap4_b", "xkv_all_w", "xkv_all_b")]
 
 
 class NavInputs(C.Structure):
@@ -88,7 +88,7 @@ def _declare():
                                   p_void]
     for fn in ("etp_nav_bwd_work_bytes",):
         getattr(L, fn).restype = C.c_size_t
-        getattr(L, fn).argtypes = [i32] * 3
+        getattr(L, fn).argtypes = [i32] * 4
     for fn in ("etp_pano_bwd_work_bytes", "etp_txt_bwd_work_bytes"):
         getattr(L, fn).restype = C.c_size_t
         getattr(L, fn).argtypes = [i32] * 2
@@ -267,6 +267,13 @@ class B200Planner(nn.Module):
         nw.sap0_w, nw.sap0_b = self._w16("global_sap_head.net.0.weight"), self._w32("global_sap_head.net.0.bias")
         nw.sap_g, nw.sap_bb = self._w32("global_sap_head.net.2.weight"), self._w32("global_sap_head.net.2.bias")
         nw.sap4_w, nw.sap4_b = self._w32("global_sap_head.net.4.weight"), self._w32("global_sap_head.net.4.bias")
+        if X > 0:
+            k0 = "global_encoder.encoder.x_layers.0.visual_attention.att.key."
+            nw.xkv_all_w, nw.xkv_all_b = self._w16(k0 + "weight"), self._w32(k0 + "bias")
+            for i in range(X):  # [X*1536, 768] stacked key|value weights, [X*1536] biases
+                ki = f"global_encoder.encoder.x_layers.{i}.visual_attention.att.key."
+                assert self.layout.offset(ki + "weight") == self.layout.offset(k0 + "weight") + i * 2 * 768 * 768
+                assert self.layout.offset(ki + "bias") == self.layout.offset(k0 + "bias") + i * 2 * 768
         s["nav"], s["nav_layers"] = nw, xl
 
         P = cfg.num_pano_layers
@@ -499,7 +506,7 @@ class _NavFn(torch.autograd.Function):
             dl = torch.nan_to_num(dl, nan=0.0, posinf=0.0, neginf=0.0)
         d_txt = torch.empty_like(txt) if ctx.needs_input_grad[1] else None
         d_img = torch.empty_like(img) if ctx.needs_input_grad[2] else None
-        wbytes = L.etp_nav_bwd_work_bytes(B, N, Lt)
+        wbytes = L.etp_nav_bwd_work_bytes(B, N, Lt, m.config.num_x_layers)
         work = torch.empty(wbytes, dtype=torch.uint8, device=img.device)
         _L._check(L.etp_backward_navigation(C.byref(m._structs["nav"]), C.byref(gst["nav"]), C.byref(ni), _L.ptr(de),
                                             _L.ptr(dl), _L.ptr(ctx.saved), ctx.saved.numel(), _L.ptr(work), wbytes,

@@ -192,6 +192,9 @@ typedef struct {
   const void* sap0_w; const float* sap0_b;     /* global_sap_head.net.0 [768,768] bf16 */
   const float* sap_g; const float* sap_bb;     /* global_sap_head.net.2 LayerNorm */
   const float* sap4_w; const float* sap4_b;    /* global_sap_head.net.4 [1,768], [1] */
+  /* key|value projections of ALL x-layers stacked: bf16 [num_x_layers*1536, 768] and fp32 [num_x_layers*1536]
+   * (layers[i].xkv_w == xkv_all_w + i*1536*768): the text K/V of every layer come out of one GEMM. */
+  const void* xkv_all_w; const float* xkv_all_b;
 } etp_nav_weights;
 
 typedef struct {
@@ -274,7 +277,7 @@ int etp_forward_txt(const etp_txt_weights* w, const int64_t* txt_ids, const uint
  * gradient buffer laid out like the parameters; parameter gradients are ACCUMULATED (+=) there.
  * `saved` is the record the matching forward call wrote with training != 0; `work` is scratch.
  * ------------------------------------------------------------------------------------------- */
-size_t etp_nav_bwd_work_bytes(int32_t B, int32_t N, int32_t L);
+size_t etp_nav_bwd_work_bytes(int32_t B, int32_t N, int32_t L, int32_t num_x_layers);
 size_t etp_pano_bwd_work_bytes(int32_t B, int32_t V);
 size_t etp_txt_bwd_work_bytes(int32_t B, int32_t L);
 /* d_gmap_embeds [B,N,768] and/or d_global_logits [B,N] (either may be NULL) -> d_txt_embeds [B,L,768],
