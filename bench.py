@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--tokens", type=int, default=200)
     ap.add_argument("--x-layers", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-report", default=None, help="write the per-kernel CUDA-event table of the profiled pass here")
     return ap.parse_args()
 
 
@@ -301,9 +302,26 @@ def main():
     for _ in range(prof_steps):
         step(resident)
     torch.cuda.synchronize()
-    g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_longlong()
-    L._check(lib.etp_prof_gemm_collect(C.byref(g_ms), C.byref(g_fl), C.byref(g_n)), "etp_prof_gemm_collect")
+    buf = C.create_string_buffer(1 << 20)
+    lib.etp_prof_report.argtypes = [C.c_char_p, C.c_size_t]
+    L._check(lib.etp_prof_report(buf, len(buf)), "etp_prof_report")
     lib.etp_prof_gemm_enable(0)
+    g_ms, g_fl, g_n = C.c_double(0.0), C.c_double(0.0), C.c_longlong(0)
+    rows = []
+    for ln in buf.value.decode().splitlines():
+        cnt, ms, fl, name, tag = (ln.split("\t") + [""])[:5]
+        rows.append((int(cnt), float(ms), float(fl), name, tag))
+        if float(fl) > 0:
+            g_ms.value += float(ms); g_fl.value += float(fl); g_n.value += int(cnt)
+    if a.kernel_report and rank == 0:
+        tot = sum(r[1] for r in rows) or 1.0
+        with open(a.kernel_report, "w") as f:
+            f.write(f"# per-kernel CUDA-event time over {prof_steps} profiled step(s) of: {workload_name(a, mode)}\n")
+            f.write("# count/step\tus/step\tshare\tavg_us\tTFLOP/s\tkernel\ttag\n")
+            for cnt, ms, fl, name, tag in sorted(rows, key=lambda r: -r[1]):
+                tf = fl / (ms * 1e-3) / 1e12 if fl > 0 and ms > 0 else 0.0
+                f.write(f"{cnt / prof_steps:.1f}\t{ms * 1e3 / prof_steps:.1f}\t{ms / tot * 100:.1f}%\t{ms * 1e3 / cnt:.1f}\t{tf:.0f}\t{name}\t{tag}\n")
+            f.write(f"# total {tot * 1e3 / prof_steps:.1f} us/step (events serialise the launches: PDL overlap is off in this pass)\n")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

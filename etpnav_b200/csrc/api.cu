@@ -7,7 +7,7 @@
 namespace etp {
 const char* last_error_cstr();
 void prof_enable(bool on);
-int prof_collect(double* ms, double* flops, long long* count);
+int prof_collect(double* ms, double* flops, long long* count, char* report, size_t cap);
 int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream);
 int attention_dispatch(const AttnArgs& a, cudaStream_t stream);
 int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream);
@@ -27,7 +27,11 @@ ETP_API long long etp_launch_count(void) { return g_launches.load(); }
 ETP_API void etp_prof_gemm_enable(int on) { prof_enable(on != 0); }
 ETP_API int etp_prof_gemm_collect(double* total_ms, double* total_flops, long long* launches) {
   ETP_REQUIRE(total_ms && total_flops && launches, "etp_prof_gemm_collect: null argument");
-  return prof_collect(total_ms, total_flops, launches);
+  return prof_collect(total_ms, total_flops, launches, nullptr, 0);
+}
+ETP_API int etp_prof_report(char* buf, size_t cap) {
+  ETP_REQUIRE(buf && cap > 0, "etp_prof_report: null argument");
+  return prof_collect(nullptr, nullptr, nullptr, buf, cap);
 }
 
 ETP_API int etp_check_device(void) {

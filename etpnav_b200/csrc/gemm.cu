@@ -14,6 +14,8 @@
 //
 // Replaces the cuBLAS calls behind torch.nn.Linear / torch.matmul on the reference path
 // (vilmodel_cmt.py:108-110,326-328,151,178,190,654; common/transformer.py:174-181).
+#include <cstdio>
+
 #include "common.cuh"
 #include "host.h"
 #include "ops.h"
@@ -335,9 +337,14 @@ static int launch_gemm(const GemmArgs& a, const GemmDev& dev, cudaStream_t strea
   }
   const int tiles = dev.tiles_m * dev.tiles_n * dev.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  prof_gemm_begin(stream);
+  if (g_prof_on) {
+    char tag[160];
+    snprintf(tag, sizeof(tag), "M%d N%d K%d bn%d %s%s ks%d%s%s%s%s%s%s", a.M, a.N, a.K, BN, A_MN ? "T" : "N", B_MN ? "T" : "N",
+             dev.k_splits, a.bias ? " bias" : "", a.act ? (a.act == 1 ? " gelu" : " relu") : "", a.aux_mode ? " aux" : "",
+             a.resid ? " resid" : "", a.out_f32 ? (a.atomic ? " red32" : " f32") : "", (a.out_bf16 ? " bf16" : ""));
+    prof_tag(tag, 2.0 * a.M * a.N * a.K);
+  }
   ETP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, dev));
-  prof_gemm_end(stream, 2.0 * a.M * a.N * a.K);
   ETP_LAUNCHED();
   return ETP_OK;
 }

@@ -2,6 +2,7 @@
 
 #include <cudaTypedefs.h>
 
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -114,40 +115,78 @@ int get_tmap_3d(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t
 
 std::atomic<long long> g_launches{0};
 
-// ---- GEMM launch profiling (off by default) ----
-static bool g_prof_on = false;
-struct ProfRec { cudaEvent_t a, b; double flops; };
+// ---- per-launch profiling (off by default) ----
+bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; const void* func; std::string tag; double flops; };
 static std::vector<ProfRec> g_prof;
 static cudaEvent_t g_prof_cur = nullptr;
+static std::string g_prof_tag;
+static double g_prof_flops = 0.0;
 
-void prof_gemm_begin(cudaStream_t s) {
+void prof_tag(const char* tag, double flops) {
   if (!g_prof_on) return;
+  g_prof_tag = tag ? tag : "";
+  g_prof_flops = flops;
+}
+void prof_begin(cudaStream_t s) {
   cudaEventCreate(&g_prof_cur);
   cudaEventRecord(g_prof_cur, s);
 }
-void prof_gemm_end(cudaStream_t s, double flops) {
-  if (!g_prof_on || !g_prof_cur) return;
+void prof_end(cudaStream_t s, const void* func) {
+  if (!g_prof_cur) return;
   ProfRec r;
   r.a = g_prof_cur;
   cudaEventCreate(&r.b);
   cudaEventRecord(r.b, s);
-  r.flops = flops;
-  g_prof.push_back(r);
+  r.func = func;
+  r.tag.swap(g_prof_tag);
+  r.flops = g_prof_flops;
+  g_prof_flops = 0.0;
+  g_prof.push_back(std::move(r));
   g_prof_cur = nullptr;
 }
 void prof_enable(bool on) { g_prof_on = on; }
-int prof_collect(double* ms, double* flops, long long* count) {
+
+static std::string func_name(const void* f) {
+  const char* n = nullptr;
+  if (cudaFuncGetName(&n, f) != cudaSuccess || !n) return "?";
+  return n;
+}
+
+// Totals over the launches that carried FLOPs (the tcgen05 GEMM); optionally a text report, one line per
+// (kernel, tag): "<count>\t<total_ms>\t<flops>\t<kernel>\t<tag>".  Clears the records.
+int prof_collect(double* ms, double* flops, long long* count, char* report, size_t cap) {
   double t = 0, f = 0;
+  long long n = 0;
+  struct Agg { long long n = 0; double ms = 0, fl = 0; };
+  std::unordered_map<std::string, Agg> agg;
+  std::vector<std::string> order;
   for (auto& r : g_prof) {
     if (cudaEventSynchronize(r.b) != cudaSuccess) return fail(ETP_ERR_CUDA, "prof_collect: event sync failed");
     float e = 0;
     cudaEventElapsedTime(&e, r.a, r.b);
-    t += e;
-    f += r.flops;
+    if (r.flops > 0) { t += e; f += r.flops; ++n; }
+    if (report) {
+      std::string key = func_name(r.func) + "\t" + r.tag;
+      auto it = agg.find(key);
+      if (it == agg.end()) { order.push_back(key); it = agg.emplace(key, Agg()).first; }
+      it->second.n++; it->second.ms += e; it->second.fl += r.flops;
+    }
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
-  *ms = t; *flops = f; *count = static_cast<long long>(g_prof.size());
+  if (ms) *ms = t;
+  if (flops) *flops = f;
+  if (count) *count = n;
+  if (report && cap > 0) {
+    std::string out;
+    for (auto& k : order) {
+      const Agg& a = agg[k];
+      out += std::to_string(a.n) + "\t" + std::to_string(a.ms) + "\t" + std::to_string(a.fl) + "\t" + k + "\n";
+    }
+    if (out.size() >= cap) out.resize(cap - 1);
+    memcpy(report, out.c_str(), out.size() + 1);
+  }
   g_prof.clear();
   return ETP_OK;
 }

@@ -38,6 +38,13 @@ extern std::atomic<long long> g_launches;
   } while (0)
 
 // launch with programmatic stream serialization (see griddep_* in common.cuh)
+// optional per-launch CUDA-event timing of every kernel (bench.py roofline leg, profiles/): when enabled,
+// launch_pdl brackets each launch with a pair of events; prof_tag() labels the next launch (GEMM shape, FLOPs).
+extern bool g_prof_on;
+void prof_tag(const char* tag, double flops);
+void prof_begin(cudaStream_t s);
+void prof_end(cudaStream_t s, const void* func);
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -46,12 +53,11 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (g_prof_on) prof_begin(s);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (g_prof_on) prof_end(s, reinterpret_cast<const void*>(kern));
+  return e;
 }
-
-// optional per-launch CUDA-event timing of the tcgen05 GEMM (bench.py roofline leg)
-void prof_gemm_begin(cudaStream_t s);
-void prof_gemm_end(cudaStream_t s, double flops);
 
 #define ETP_REQUIRE(cond, msg)                                                     \
   do {                                                                             \

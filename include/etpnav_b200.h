@@ -47,6 +47,9 @@ long long etp_launch_count(void);
  * collect = synchronise and return total milliseconds / algorithmic flops / launch count, then reset. */
 void etp_prof_gemm_enable(int on);
 int etp_prof_gemm_collect(double* total_ms, double* total_flops, long long* launches);
+/* same records as a text table, one line per (kernel, shape tag): count \t total_ms \t flops \t kernel \t tag;
+ * every kernel of the library is timed while profiling is enabled.  Resets the records. */
+int etp_prof_report(char* buf, size_t cap);
 
 /* ---------------------------------------------------------------------------------------------
  * operator level
