@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--tokens", type=int, default=200)
     ap.add_argument("--x-layers", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-eager", action="store_true",
+                    help="also time the oracle port in eager PyTorch on this GPU (fp32 and bf16 autocast): the "
+                         "'reference GPU eager' figure the north_star's >=10x target is stated against")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel CUDA-event table of the profiled pass here")
     return ap.parse_args()
 
@@ -172,6 +175,53 @@ def cpu_step_time(a, mode, steps, warmup, max_seconds=25.0):
     times.sort()
     med = times[len(times) // 2]
     return med, cores, len(times)
+
+
+def gpu_eager_time(a, mode, dev, autocast, steps=10, warmup=3):
+    """Eager-PyTorch GPU baseline: the oracle port (the reference's op sequence) with torch's own fused
+    F.linear / F.layer_norm, fp32 or bf16 autocast, same workload, CUDA-event timed.  A reported baseline only."""
+    import torch.nn.functional as F
+    from oracle import planner_port as P  # test infrastructure, used here only as a timed baseline
+    P._lin = lambda sd, name, x: F.linear(x, sd[name + ".weight"], sd[name + ".bias"])
+    P._ln = lambda sd, name, x, eps: F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], eps)
+    cfg = workload_cfg(a)
+    sd = {k: v.to(dev) for k, v in make_weights(cfg, seed=0, skip_text=False).items()}
+    inp = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v)
+           for k, v in make_inputs(cfg, a.batch, a.views, a.nodes, a.tokens, seed=1, ragged=False).items()}
+    if mode == "train":
+        sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        opt = torch.optim.AdamW(list(sd.values()), lr=1e-5)
+
+    def fwd():
+        pano, pm = P.forward_panorama(sd, cfg, inp["rgb_fts"], inp["dep_fts"], inp["loc_fts"], inp["nav_types"], inp["view_lens"])
+        nav = P.forward_navigation(sd, cfg, inp["txt_embeds"], inp["txt_masks"], None, inp["gmap_step_ids"],
+                                   inp["gmap_img_fts"], inp["gmap_pos_fts"], inp["gmap_masks"],
+                                   inp["gmap_visited_masks"], inp["gmap_pair_dists"])
+        return pano, pm, nav
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            if mode == "train":
+                opt.zero_grad(set_to_none=True)
+                pano, pm, nav = fwd()
+                loss = P.step_loss(nav["global_logits"].float(), inp["labels"]) + (pano.float() * pm[..., None]).sum() * 1e-3
+            else:
+                with torch.no_grad():
+                    fwd()
+        if mode == "train":
+            loss.backward()
+            opt.step()
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
 def run_reference_arm(a, mode, rank):
@@ -343,6 +393,12 @@ def main():
             med, cores, n = cpu_step_time(a, mode, steps=3, warmup=1, max_seconds=25.0)
             cpu = {"value": 1.0 / med, "unit": "steps/s", "cores": cores, "kind": "port",
                    "sample": f"median of {n} full-size step(s) after 1 warm-up; oracle/planner_port.py fp32 on torch CPU"}
+        eager = None
+        if a.gpu_eager and world == 1:
+            ms32 = gpu_eager_time(a, mode, dev, autocast=False)
+            ms16 = gpu_eager_time(a, mode, dev, autocast=True)
+            eager = {"fp32_steps_per_s": 1e3 / ms32, "bf16_autocast_steps_per_s": 1e3 / ms16, "unit": "steps/s",
+                     "what": "oracle port of the reference, eager PyTorch on this GPU (F.linear/F.layer_norm, torch AdamW)"}
         line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps,
                 "warmup": max(3, a.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -352,6 +408,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_ms},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu}
+        if eager:
+            line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -159,6 +159,67 @@ ETP_DEVICE void named_bar_sync(int id, int nthreads) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA spans the tensor cores and TMEM of two SMs
+// ----------------------------------------------------------------------------------------------
+ETP_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// execution barrier across the cluster.  Relaxed arrive: a release arrive compiles to MEMBAR.ALL.GPU, and none of the
+// uses needs memory ordering (mbarrier initialisation is published by fence.mbarrier_init.release.cluster).
+ETP_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+ETP_DEVICE uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Default semantics (.release at CTA scope) on purpose: a cluster-scope release compiles to MEMBAR.ALL.GPU in front
+// of every arrive (measured: ~0.9 us per pipeline stage).  The hand-offs that use this need no memory ordering: TMA
+// bytes are tracked by the barrier's transaction count, TMEM reads are ordered by tcgen05.fence::before_thread_sync.
+ETP_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load issued by either CTA of a pair; the transaction bytes are signalled on `bar_cluster_addr`
+// (a shared::cluster address, normally the leader CTA's barrier)
+ETP_DEVICE void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+ETP_DEVICE void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {  // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+ETP_DEVICE void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+ETP_DEVICE void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA), each CTA supplying half of B.  Leader CTA only.
+ETP_DEVICE void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in both CTAs once the pair's MMAs issued so far are done
+ETP_DEVICE void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // UMMA descriptors
 // ----------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit):
@@ -195,6 +256,33 @@ ETP_DEVICE float dgelu_erf(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
+}
+// GELU / GELU' for the GEMM epilogues: Phi(x) from erfc by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 on erf, far
+// below the bf16 rounding of the values these feed), 1 MUFU.RCP + 1 MUFU.EX2 + ~12 FMA-pipe instructions instead of
+// erff's ~28; the exponential is shared with the Gaussian density needed by the derivative.
+ETP_DEVICE void phi_parts(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  // 0.5 * (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5)
+  float q = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  q = fmaf(q, t, 0.5f * 1.421413741f);
+  q = fmaf(q, t, 0.5f * -0.284496736f);
+  q = fmaf(q, t, 0.5f * 0.254829592f);
+  q *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));  // exp(-x^2 / 2)
+  q *= e;                                        // 0.5 * erfc(|x| / sqrt 2)
+  cdf = x >= 0.0f ? 1.0f - q : q;
+}
+ETP_DEVICE float gelu_fast(float x) {
+  float cdf, e;
+  phi_parts(x, cdf, e);
+  return x * cdf;
+}
+ETP_DEVICE float dgelu_fast(float x) {
+  float cdf, e;
+  phi_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 ETP_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -82,15 +82,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                              const float* __restrict__ gamma, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, int rows, float* __restrict__ dx_f32,
                                                              int accumulate_dx, bf16* __restrict__ dx_bf16,
-                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                             float* __restrict__ dxsum) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
   __shared__ float red[8][kH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float g[24], dg[24], db[24];
+  float g[24], dg[24], db[24], ds[24];
   load_row(gamma, lane, g);
 #pragma unroll
-  for (int i = 0; i < 24; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  for (int i = 0; i < 24; ++i) { dg[i] = 0.f; db[i] = 0.f; ds[i] = 0.f; }
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     float d[24], v[24];
     load_row(dy + static_cast<size_t>(row) * kH, lane, d);
@@ -119,6 +120,23 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
     store_row(o, lane, d);
     if (dx_bf16) store_row_bf16(dx_bf16 + static_cast<size_t>(row) * kH, lane, d);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) ds[i] += d[i];
+  }
+  if (dxsum != nullptr) {
+    // column sums of dx: the bias gradient of the Linear whose output (+ residual) this LayerNorm normalised
+#pragma unroll
+    for (int i = 0; i < kVec; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[warp][(i * 32 + lane) * 4 + j] = ds[4 * i + j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < kH; c += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][c];
+      atomicAdd(dxsum + c, s);
+    }
+    __syncthreads();
   }
   if (dgamma == nullptr) return;
   // CTA reduction of the per-warp partials
@@ -149,13 +167,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
 int layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int rows,
                   int H, float* dx_f32, int accumulate_dx, bf16* dx_bf16, float* dgamma, float* dbeta,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, float* dxsum) {
   ETP_REQUIRE(H == kH, "layernorm: hidden size must be 768");
   if (rows <= 0) return ETP_OK;
   int grid = (rows + 7) / 8;
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
   ETP_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(grid), dim3(256), 0, stream, dy, x, gamma, mean, rstd, rows, dx_f32, accumulate_dx, dx_bf16, dgamma,
-                                                 dbeta));
+                                                 dbeta, dxsum));
   ETP_LAUNCHED();
   return ETP_OK;
 }

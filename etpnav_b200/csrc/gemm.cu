@@ -15,8 +15,10 @@
 // Replaces the cuBLAS calls behind torch.nn.Linear / torch.matmul on the reference path
 // (vilmodel_cmt.py:108-110,326-328,151,178,190,654; common/transformer.py:174-181).
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
+#include "gemm_dev.h"
 #include "host.h"
 #include "ops.h"
 
@@ -37,25 +39,6 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-struct GemmDev {
-  int M, N, K;
-  int tiles_m, tiles_n, k_splits, kb_per_split;  // kb = 64-wide k blocks
-  float alpha;
-  const float* bias;
-  int act;       // 0 none, 1 gelu(erf), 2 relu
-  int aux_mode;  // 0 none, 1: *= gelu'(aux), 2: *= (aux > 0)
-  const __nv_bfloat16* aux;
-  int ld_aux;
-  const float* resid;
-  int ld_resid;
-  float* out_f32;
-  int ld_f32;
-  int atomic;
-  __nv_bfloat16* out_bf16;
-  int ld_bf16;
-  __nv_bfloat16* out_pre;  // pre-activation copy (bf16), for the GELU backward
-  int ld_pre;
-};
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -363,6 +346,16 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
               "gemm: epilogue leading dimensions must keep rows 16-byte aligned");
   GemmDev d;
   d.M = a.M; d.N = a.N; d.K = a.K;
+  d.alpha = a.alpha;
+  d.bias = a.bias; d.act = a.act; d.aux_mode = a.aux_mode; d.aux = a.aux; d.ld_aux = a.ld_aux;
+  d.resid = a.resid; d.ld_resid = a.ld_resid; d.out_f32 = a.out_f32; d.ld_f32 = a.ld_f32; d.atomic = a.atomic;
+  d.out_bf16 = a.out_bf16; d.ld_bf16 = a.ld_bf16; d.out_pre = a.out_pre; d.ld_pre = a.ld_pre;
+  d.tiles_m = d.tiles_n = d.kb_per_split = 0; d.k_splits = a.k_splits;
+  d.colsum = a.colsum;
+  ETP_REQUIRE(!a.colsum || (a.k_splits == 1 && !a.atomic), "gemm: colsum needs whole-K tiles");
+  // default: CTA-pair kernel (gemm_pair.cu).  ETP_GEMM_IMPL=1 selects the one-CTA kernel below (A/B measurements).
+  static const bool legacy = [] { const char* e = getenv("ETP_GEMM_IMPL"); return e && e[0] == '1'; }();
+  if (!legacy && a.N % 2 == 0) return gemm_pair(a, d, stream);  // (its epilogue moves column pairs)
   // tile-N choice: 256-wide tiles halve B re-reads from smem per flop; fall back to 128 when N is small
   // or when 256-wide tiles would leave most SMs idle.
   int bn = a.block_n;
@@ -378,15 +371,19 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   const int total_kb = (a.K + BK - 1) / BK;
   d.kb_per_split = (total_kb + a.k_splits - 1) / a.k_splits;
   d.k_splits = (total_kb + d.kb_per_split - 1) / d.kb_per_split;  // drop empty splits
-  d.alpha = a.alpha;
-  d.bias = a.bias; d.act = a.act; d.aux_mode = a.aux_mode; d.aux = a.aux; d.ld_aux = a.ld_aux;
-  d.resid = a.resid; d.ld_resid = a.ld_resid; d.out_f32 = a.out_f32; d.ld_f32 = a.ld_f32; d.atomic = a.atomic;
-  d.out_bf16 = a.out_bf16; d.ld_bf16 = a.ld_bf16; d.out_pre = a.out_pre; d.ld_pre = a.ld_pre;
 #define ETP_GEMM_DISPATCH(BN_)                                                            \
   if (!a.a_mn && !a.b_mn) return launch_gemm<BN_, false, false>(a, d, stream);            \
   if (!a.a_mn && a.b_mn) return launch_gemm<BN_, false, true>(a, d, stream);              \
   if (a.a_mn && a.b_mn) return launch_gemm<BN_, true, true>(a, d, stream);                \
   return launch_gemm<BN_, true, false>(a, d, stream);
+  if (a.colsum) {  // the one-CTA kernel has no fused column sums: separate pass over the bf16 output
+    ETP_REQUIRE(a.out_bf16 != nullptr, "gemm: colsum on the one-CTA kernel needs a bf16 output");
+    GemmArgs b = a;
+    b.colsum = nullptr;
+    int rc = gemm(b, stream);
+    if (rc) return rc;
+    return colsum_bf16(a.out_bf16, a.M, a.N, a.ld_bf16, a.colsum, stream);
+  }
   if (bn == 256) { ETP_GEMM_DISPATCH(256) }
   ETP_GEMM_DISPATCH(128)
 #undef ETP_GEMM_DISPATCH

@@ -33,6 +33,7 @@ struct GemmArgs {
   int ld_pre = 0;
   int k_splits = 1;
   int block_n = 0;  // 0 = auto, else 128 or 256
+  float* colsum = nullptr;  // fp32 [N]: += column sums of the final value (bias gradient of the producing Linear)
 };
 int gemm(const GemmArgs& a, cudaStream_t stream);
 
@@ -43,10 +44,11 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
                   bf16* y_bf16, float* mean, float* rstd, cudaStream_t stream);
 // dx = LN backward (dy fp32 [rows,H], x fp32, mean, rstd); accumulates dgamma/dbeta (fp32 [H], atomicAdd).
 // dx is written to dx_f32 (fp32; if accumulate_dx != 0 it is added to the existing content) and,
-// if non-null, a bf16 copy to dx_bf16.
+// if non-null, a bf16 copy to dx_bf16.  dxsum (fp32 [H], optional) += column sums of the written dx: the bias
+// gradient of the Linear feeding this LayerNorm, fused here instead of a separate column-sum pass.
 int layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int rows,
                   int H, float* dx_f32, int accumulate_dx, bf16* dx_bf16, float* dgamma, float* dbeta,
-                  cudaStream_t stream);
+                  cudaStream_t stream, float* dxsum = nullptr);
 // out[c] += sum_r x[r, c]   (bias gradients)
 int colsum_bf16(const bf16* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
 int colsum_f32(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream);

@@ -38,7 +38,7 @@ struct BwdScratch {
 
 // dX[rows, K_in] = dY[rows, N_out] . W[N_out, K_in]  (+ resid)   — W consumed MN-major as stored
 static int dgrad(const bf16* dY, int rows, int N_out, int ldy, const void* W, int K_in, const float* resid, float* out_f32,
-                 bf16* out_bf16, int aux_mode, const bf16* aux, cudaStream_t s) {
+                 bf16* out_bf16, int aux_mode, const bf16* aux, cudaStream_t s, const void* colsum = nullptr) {
   GemmArgs g;
   g.M = rows; g.N = K_in; g.K = N_out;
   g.A = dY; g.lda = ldy;
@@ -47,6 +47,7 @@ static int dgrad(const bf16* dY, int rows, int N_out, int ldy, const void* W, in
   g.out_f32 = out_f32; g.ld_f32 = K_in;
   g.out_bf16 = out_bf16; g.ld_bf16 = K_in;
   g.aux_mode = aux_mode; g.aux = aux; g.ld_aux = K_in;
+  g.colsum = static_cast<float*>(const_cast<void*>(colsum));  // bias gradient of the layer that produced dX's pre-image
   return gemm(g, s);
 }
 
@@ -58,20 +59,29 @@ static int wgrad(const bf16* dY, int rows, int N_out, int ldy, const bf16* X, in
   g.A = dY; g.lda = ldy; g.a_mn = 1;
   g.B = X; g.ldb = ldx; g.b_mn = 1;
   g.out_f32 = static_cast<float*>(dW); g.ld_f32 = K_in;
-  // Few output tiles, long reduction (rows = tokens).  128x128 tiles; when they alone nearly fill the chip every
-  // tile owns its output and accumulates with a plain read-add-write (resid = out); otherwise split the token
-  // axis just enough to cover the SMs and accumulate with 128-bit vector reductions.
-  g.block_n = 128;
-  const int tiles = ((N_out + 127) / 128) * ((K_in + 127) / 128);
+  // Few output tiles (256 x bn per CTA pair), long reduction (rows = tokens): pick the tile width and the number of
+  // token-axis splits that minimise  waves x (k-blocks per split + epilogue), in units of one 256x256x64 MMA block.
+  // One split: every tile owns its output and accumulates with a plain read-add-write (resid = out); otherwise the
+  // partial tiles are added with fp32 reductions.
+  const int pairs = num_sms() / 2;
   const int kb = (rows + 63) / 64;
-  int splits = 1;
-  if (tiles < (num_sms() * 2) / 3) {
-    splits = num_sms() / tiles;  // floor: one wave
-    if (splits > kb / 4) splits = kb / 4;
-    if (splits < 1) splits = 1;
+  double best = 1e30;
+  int best_bn = 128, best_splits = 1;
+  for (int bn = 128; bn <= 256; bn += 128) {
+    if (bn == 256 && K_in % 256 != 0) continue;
+    const int tiles = ((N_out + 255) / 256) * ((K_in + bn - 1) / bn);
+    const double w = bn / 256.0;
+    for (int splits = 1; splits <= 32 && splits * 4 <= kb; ++splits) {
+      const int total = tiles * splits;
+      const int waves = (total + pairs - 1) / pairs;
+      const int kbs = (kb + splits - 1) / splits;
+      const double cost = waves * (kbs * w + 8.0 * w + 4.0);
+      if (cost < best) { best = cost; best_bn = bn; best_splits = splits; }
+    }
   }
-  g.k_splits = splits;
-  if (splits > 1) {
+  g.block_n = best_bn;
+  g.k_splits = best_splits;
+  if (best_splits > 1) {
     g.atomic = 1;
   } else {
     g.resid = g.out_f32; g.ld_resid = K_in;  // dW = acc + dW
@@ -93,19 +103,19 @@ static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weight
                               BwdScratch& sc, cudaStream_t s) {
   const int rows = B * S;
   // x = LN(t3)
-  ETP_TRY(layernorm_bwd(dx_out, rec.t3, w.fln_g, rec.st3, rec.st3 + rows, rows, kH, sc.g0, 0, sc.gb, F(g.fln_g), F(g.fln_b), s));
+  // (bias gradients ride along: column sums of dt3 inside the LayerNorm backward, of dpre inside the dgrad epilogue)
+  ETP_TRY(layernorm_bwd(dx_out, rec.t3, w.fln_g, rec.st3, rec.st3 + rows, rows, kH, sc.g0, 0, sc.gb, F(g.fln_g), F(g.fln_b), s,
+                        F(g.f2_b)));
   // t3 = h.W2^T + b2 + c
-  ETP_TRY(bias_grad(sc.gb, rows, kH, kH, g.f2_b, s));
   ETP_TRY(wgrad(sc.gb, rows, kH, kH, rec.h, kI, kI, const_cast<void*>(g.f2_w), s));
-  ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.f2_w, kI, nullptr, nullptr, sc.dpre, 1, rec.pre, s));  // * gelu'(pre)
+  ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.f2_w, kI, nullptr, nullptr, sc.dpre, 1, rec.pre, s, g.f1_b));  // * gelu'(pre)
   // pre = c.W1^T + b1
-  ETP_TRY(bias_grad(sc.dpre, rows, kI, kI, g.f1_b, s));
   ETP_TRY(wgrad(sc.dpre, rows, kI, kI, rec.cb, kH, kH, const_cast<void*>(g.f1_w), s));
   ETP_TRY(dgrad(sc.dpre, rows, kI, kI, w.f1_w, kH, sc.g0, sc.g1, nullptr, 0, nullptr, s));  // dc = dpre.W1 + dt3
   // c = LN(t2)
-  ETP_TRY(layernorm_bwd(sc.g1, rec.t2, w.sln_g, rec.st2, rec.st2 + rows, rows, kH, sc.g0, 0, sc.gb, F(g.sln_g), F(g.sln_b), s));
+  ETP_TRY(layernorm_bwd(sc.g1, rec.t2, w.sln_g, rec.st2, rec.st2 + rows, rows, kH, sc.g0, 0, sc.gb, F(g.sln_g), F(g.sln_b), s,
+                        F(g.so_b)));
   // t2 = ctx2.Wo^T + bo + a
-  ETP_TRY(bias_grad(sc.gb, rows, kH, kH, g.so_b, s));
   ETP_TRY(wgrad(sc.gb, rows, kH, kH, rec.ctx2, kH, kH, const_cast<void*>(g.so_w), s));
   ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.so_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
   // attention
@@ -162,8 +172,8 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     ETP_TRY(self_ffn_block_bwd(lw, lg, r, r.ab, P, Q, B, N, in.gmap_masks, w.sprel_w ? in.gmap_pair_dists : nullptr, w.sprel_w,
                                w.sprel_b, F(g.sprel_w), F(g.sprel_b), sc, s));
     // a = LN(t1),  t1 = ctx1.Wo^T + bo + x_in
-    ETP_TRY(layernorm_bwd(Q, r.t1, lw.xln_g, r.st1, r.st1 + rows, rows, kH, sc.g0, 0, sc.gb, F(lg.xln_g), F(lg.xln_b), s));
-    ETP_TRY(bias_grad(sc.gb, rows, kH, kH, lg.xo_b, s));
+    ETP_TRY(layernorm_bwd(Q, r.t1, lw.xln_g, r.st1, r.st1 + rows, rows, kH, sc.g0, 0, sc.gb, F(lg.xln_g), F(lg.xln_b), s,
+                          F(lg.xo_b)));
     ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.ctx1, kH, kH, const_cast<void*>(lg.xo_w), s));
     ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.xo_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
     AttnBwdArgs at;
@@ -211,7 +221,7 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
   float* Bf = sc.g1;
   if (Pn > 0) {
     ETP_TRY(layernorm_bwd(d_pano_embeds, rec.xs[2 * Pn], w.fin_g, rec.fin_stats, rec.fin_stats + rows, rows, kH, A, 0, sc.gb,
-                          F(g.fin_g), F(g.fin_b), s));
+                          F(g.fin_g), F(g.fin_b), s, F(g.layers[Pn - 1].l2_b)));  // dx_out of the last layer: its linear2 bias grad
   } else {
     ETP_CHECK_CUDA(cudaMemcpyAsync(A, d_pano_embeds, static_cast<size_t>(rows) * kH * 4, cudaMemcpyDeviceToDevice, s));
   }
@@ -221,16 +231,15 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
     const PanoLayerRecord& r = rec.layers[i];
     const float* x = rec.xs[2 * i];
     const float* x_mid = rec.xs[2 * i + 1];
-    // x_out = x_mid + gelu(LN2(x_mid).W1^T + b1).W2^T + b2      (A = dx_out, sc.gb = bf16(A))
-    ETP_TRY(bias_grad(sc.gb, rows, kH, kH, lg.l2_b, s));
+    // x_out = x_mid + gelu(LN2(x_mid).W1^T + b1).W2^T + b2      (A = dx_out, sc.gb = bf16(A); the linear2 bias
+    // gradient = column sums of A was accumulated by the LayerNorm backward that produced A)
     ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.h, kI, kI, const_cast<void*>(lg.l2_w), s));
-    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.l2_w, kI, nullptr, nullptr, sc.dpre, 1, r.pre, s));
-    ETP_TRY(bias_grad(sc.dpre, rows, kI, kI, lg.l1_b, s));
+    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.l2_w, kI, nullptr, nullptr, sc.dpre, 1, r.pre, s, lg.l1_b));
     ETP_TRY(wgrad(sc.dpre, rows, kI, kI, r.y2b, kH, kH, const_cast<void*>(lg.l1_w), s));
     ETP_TRY(dgrad(sc.dpre, rows, kI, kI, lw.l1_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy2
-    ETP_TRY(layernorm_bwd(Bf, x_mid, lw.n2_g, r.st2, r.st2 + rows, rows, kH, A, 1, sc.gb, F(lg.n2_g), F(lg.n2_b), s));  // A = dx_mid
+    ETP_TRY(layernorm_bwd(Bf, x_mid, lw.n2_g, r.st2, r.st2 + rows, rows, kH, A, 1, sc.gb, F(lg.n2_g), F(lg.n2_b), s,
+                          F(lg.out_b)));  // A = dx_mid
     // x_mid = x + attn(LN1(x)).Wout^T + bout
-    ETP_TRY(bias_grad(sc.gb, rows, kH, kH, lg.out_b, s));
     ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.ctx, kH, kH, const_cast<void*>(lg.out_w), s));
     ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.out_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
     AttnBwdArgs at;
@@ -243,7 +252,8 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
     ETP_TRY(bias_grad(sc.dqkv, rows, 3 * kH, 3 * kH, lg.in_b, s));
     ETP_TRY(wgrad(sc.dqkv, rows, 3 * kH, 3 * kH, r.y1b, kH, kH, const_cast<void*>(lg.in_w), s));
     ETP_TRY(dgrad(sc.dqkv, rows, 3 * kH, 3 * kH, lw.in_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy1
-    ETP_TRY(layernorm_bwd(Bf, x, lw.n1_g, r.st1, r.st1 + rows, rows, kH, A, 1, sc.gb, F(lg.n1_g), F(lg.n1_b), s));  // A = dx
+    ETP_TRY(layernorm_bwd(Bf, x, lw.n1_g, r.st1, r.st1 + rows, rows, kH, A, 1, sc.gb, F(lg.n1_g), F(lg.n1_b), s,
+                          i > 0 ? F(g.layers[i - 1].l2_b) : nullptr));  // A = dx (= dx_out of layer i-1)
   }
   PanoPackBwdArgs pb;
   pb.rows = rows; pb.dx = A; pb.rgb_lin = rec.rgb_lin; pb.dep_lin = w.dep_w ? rec.dep_lin : nullptr; pb.loc_lin = rec.loc_lin;

@@ -59,7 +59,7 @@ int etp_prof_report(char* buf, size_t cap);
  * reference path (vilmodel_cmt.py:108-110,326-328,151,178,190,654; common/transformer.py:174-181).
  * a_mn/b_mn = 0: operand stored [rows, K] (K contiguous); 1: stored [K, rows] (rows contiguous).
  * epilogue: x = alpha*acc + bias[n]; out_pre = bf16(x); x = act(x); x *= f(aux); x += resid;
- *           out_f32 (=, or += atomically) x; out_bf16 = bf16(x). */
+ *           out_f32 (=, or += atomically) x; out_bf16 = bf16(x); colsum[n] += sum_m x (bias gradients). */
 typedef struct {
   int32_t M, N, K;
   const void* A; int32_t lda; int32_t a_mn;
@@ -75,6 +75,7 @@ typedef struct {
   void* out_pre; int32_t ld_pre;
   int32_t k_splits;   /* >1 requires atomic */
   int32_t block_n;    /* 0 auto, 128, 256 */
+  float* colsum;      /* optional fp32 [N]: += column sums of the final value x */
 } etp_gemm_args;
 int etp_gemm(const etp_gemm_args* args, void* stream);
 
