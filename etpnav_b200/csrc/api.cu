@@ -57,7 +57,7 @@ ETP_API int etp_gemm(const etp_gemm_args* g, void* stream) {
   a.out_bf16 = static_cast<bf16*>(g->out_bf16); a.ld_bf16 = g->ld_bf16;
   a.out_pre = static_cast<bf16*>(g->out_pre); a.ld_pre = g->ld_pre;
   a.k_splits = g->k_splits < 1 ? 1 : g->k_splits; a.block_n = g->block_n;
-  a.colsum = g->colsum;
+  a.colsum = g->colsum; a.pre_mode = g->pre_mode;
   return gemm(a, S(stream));
 }
 

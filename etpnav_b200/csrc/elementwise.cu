@@ -179,7 +179,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* gamma, const flo
 }
 
 // out[c] += sum_r x[r, c].  Each CTA covers 64 columns x a slab of rows; threads (32 x 8): lane-pairs of columns,
-// 8 row lanes; shared-memory reduce over the 8 row lanes; one atomicAdd per column per CTA.
+// 8 row lanes, 4 rows in flight per thread; shared-memory reduce over the 8 row lanes; one atomicAdd per column per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int rows, int cols, int ld, int rows_per_cta,
                                                       float* __restrict__ out) {
@@ -192,15 +192,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
   const int r1 = min(rows, r0 + rows_per_cta);
   float s0 = 0.f, s1 = 0.f;
   if (c < cols) {
-    for (int r = r0 + ty; r < r1; r += 8) {
+    auto ld2 = [&](int r) -> float2 {
       const T* p = x + static_cast<size_t>(r) * ld + c;
-      if constexpr (sizeof(T) == 2) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
-        s0 += f.x; s1 += f.y;
-      } else {
-        const float2 f = *reinterpret_cast<const float2*>(p);
-        s0 += f.x; s1 += f.y;
-      }
+      if constexpr (sizeof(T) == 2) return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+      else return *reinterpret_cast<const float2*>(p);
+    };
+    int r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      const float2 a = ld2(r), b = ld2(r + 8), d = ld2(r + 16), e = ld2(r + 24);
+      s0 += (a.x + b.x) + (d.x + e.x);
+      s1 += (a.y + b.y) + (d.y + e.y);
+    }
+    for (; r < r1; r += 8) {
+      const float2 a = ld2(r);
+      s0 += a.x; s1 += a.y;
     }
   }
   red[ty][tx * 2] = s0;
@@ -220,7 +225,7 @@ static int colsum_impl(const T* x, int rows, int cols, int ld, float* out, cudaS
   ETP_REQUIRE(cols % 2 == 0 && ld % 2 == 0, "colsum: even cols/ld required");
   if (rows <= 0) return ETP_OK;
   const int gx = (cols + 63) / 64;
-  int gy = (2 * num_sms() + gx - 1) / gx;
+  int gy = (4 * num_sms() + gx - 1) / gx;  // ~4 CTAs per SM: the kernel is pure streaming
   int rpc = (rows + gy - 1) / gy;
   if (rpc < 64) rpc = 64;
   gy = (rows + rpc - 1) / rpc;

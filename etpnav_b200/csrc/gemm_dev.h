@@ -1,5 +1,4 @@
-// Device-side parameter block shared by the tcgen05 GEMM kernels (gemm.cu: one CTA per 128-row tile;
-// gemm_pair.cu: CTA pairs, cta_group::2, 256-row tiles).
+// Device-side parameter block of the tcgen05 GEMM kernel (gemm.cu: CTA pairs, cta_group::2, 256-row tiles).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -11,7 +10,7 @@ struct GemmDev {
   float alpha;
   const float* bias;
   int act;       // 0 none, 1 gelu(erf), 2 relu
-  int aux_mode;  // 0 none, 1: *= gelu'(aux), 2: *= (aux > 0)
+  int aux_mode;  // 0 none, 1: *= gelu'(aux), 2: *= (aux > 0), 3: *= aux
   const __nv_bfloat16* aux;
   int ld_aux;
   const float* resid;
@@ -23,11 +22,8 @@ struct GemmDev {
   int ld_bf16;
   __nv_bfloat16* out_pre;  // pre-activation copy (bf16), for the GELU backward
   int ld_pre;
+  int pre_mode;   // 0: out_pre = pre-activation; 1: out_pre = gelu'(pre-activation)
   float* colsum;  // fp32 [N] += column sums of the final value (CTA-pair kernel only)
 };
-
-struct GemmArgs;
-// CTA-pair kernel (gemm_pair.cu).  `d` arrives with the epilogue fields filled; tiling fields are set here.
-int gemm_pair(const GemmArgs& a, GemmDev d, cudaStream_t stream);
 
 }  // namespace etp

@@ -19,7 +19,7 @@ struct GemmArgs {
   float alpha = 1.0f;
   const float* bias = nullptr;  // [N]
   int act = 0;                  // 0 none, 1 gelu(erf), 2 relu
-  int aux_mode = 0;             // 0 none, 1: *= gelu'(aux), 2: *= (aux > 0)
+  int aux_mode = 0;             // 0 none, 1: *= gelu'(aux), 2: *= (aux > 0), 3: *= aux
   const bf16* aux = nullptr;
   int ld_aux = 0;
   const float* resid = nullptr;  // fp32 [M, N] added after activation
@@ -29,8 +29,9 @@ struct GemmArgs {
   int atomic = 0;  // out_f32 += result (atomicAdd); required for k_splits > 1
   bf16* out_bf16 = nullptr;
   int ld_bf16 = 0;
-  bf16* out_pre = nullptr;  // bf16 copy of the pre-activation value (alpha*acc + bias)
+  bf16* out_pre = nullptr;  // bf16 copy of the pre-activation value (alpha*acc + bias) ...
   int ld_pre = 0;
+  int pre_mode = 0;         // ... or, if 1 (with act = gelu), of the activation derivative gelu'(pre) for the backward
   int k_splits = 1;
   int block_n = 0;  // 0 = auto, else 128 or 256
   float* colsum = nullptr;  // fp32 [N]: += column sums of the final value (bias gradient of the producing Linear)

@@ -50,8 +50,19 @@ ETP_DEVICE void ln_bwd_row(float (&dy)[24], float (&x)[24], float mean, float rs
 #pragma unroll
   for (int i = 0; i < 24; ++i) dy[i] = rstd * (dy[i] - s1 - x[i] * s2);
 }
+// CTA partial -> global gradient.  128-bit vector reductions (4x fewer L2 atomic operations) when the destination
+// is 16-byte aligned, which every parameter gradient in the flat buffer is; all-zero quads are skipped.
 ETP_DEVICE void flush(float* dst, const float* s, int n) {
   if (dst == nullptr) return;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (n & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(s + i);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float v = s[i];
     if (v != 0.f) atomicAdd(dst + i, v);
@@ -60,9 +71,10 @@ ETP_DEVICE void flush(float* dst, const float* s, int n) {
 ETP_DEVICE void zero_smem(float* s, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = 0.f;
 }
-int grid_for(int rows) {
+// Every CTA of these kernels ends by adding its shared-memory partials (thousands of floats) to global memory, so
+// the grid is kept small: the row loop is short either way, the flush traffic scales with the CTA count.
+int grid_for(int rows, int cap = 64) {
   int g = (rows + 7) / 8;
-  const int cap = 2 * num_sms();
   return g > cap ? cap : (g < 1 ? 1 : g);
 }
 }  // namespace
@@ -192,8 +204,7 @@ int node_pack_bwd(const float* dx, const int64_t* step_ids, const float* pos_fts
     ETP_CHECK_CUDA(cudaFuncSetAttribute(node_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  int grid = grid_for(rows);
-  if (grid > num_sms()) grid = num_sms();
+  int grid = grid_for(rows, 48);
   ETP_CHECK_CUDA(launch_pdl(node_pack_bwd_kernel, dim3(grid), dim3(256), smem, stream, dx, step_ids, pos_fts, pos_lin, stats, pos_g, rows, dstep_emb, dpos_w,
                                                     dpos_b, dpos_g, dpos_bb));
   ETP_LAUNCHED();
@@ -273,8 +284,7 @@ int pano_pack_bwd(const PanoPackBwdArgs& a, cudaStream_t stream) {
     ETP_CHECK_CUDA(cudaFuncSetAttribute(pano_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  int grid = grid_for(a.rows);
-  if (grid > num_sms()) grid = num_sms();
+  const int grid = grid_for(a.rows, 24);
   ETP_CHECK_CUDA(launch_pdl(pano_pack_bwd_kernel, dim3(grid), dim3(256), smem, stream, a));
   ETP_LAUNCHED();
   return ETP_OK;

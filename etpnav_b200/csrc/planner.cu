@@ -107,7 +107,7 @@ void TxtRecord::carve(Arena& ar, int B, int L, int NL, bool training) {
 // ---------------------------------------------------------------------------------------------------
 // out = A[rows,K] . W[N,K]^T + bias  with the usual epilogue options
 static int linear(const bf16* A, int rows, int K, const void* W, int N, const float* bias, int act, const float* resid,
-                  float* out_f32, bf16* out_bf16, bf16* out_pre, cudaStream_t s) {
+                  float* out_f32, bf16* out_bf16, bf16* out_dact, cudaStream_t s) {
   GemmArgs g;
   g.M = rows; g.N = N; g.K = K;
   g.A = A; g.lda = K;
@@ -116,7 +116,7 @@ static int linear(const bf16* A, int rows, int K, const void* W, int N, const fl
   g.resid = resid; g.ld_resid = N;
   g.out_f32 = out_f32; g.ld_f32 = N;
   g.out_bf16 = out_bf16; g.ld_bf16 = N;
-  g.out_pre = out_pre; g.ld_pre = N;
+  g.out_pre = out_dact; g.ld_pre = N; g.pre_mode = out_dact ? 1 : 0;  // saved for backward: gelu'(pre-activation)
   return gemm(g, s);
 }
 

@@ -40,7 +40,7 @@ struct LayerRecord {
   float* t2 = nullptr;
   float* st2 = nullptr;
   bf16* cb = nullptr;
-  bf16 *pre = nullptr, *h = nullptr;  // FFN pre-activation / GELU output [rows,3072]
+  bf16 *pre = nullptr, *h = nullptr;  // FFN: gelu'(pre-activation) for the backward / GELU output [rows,3072]
   float* t3 = nullptr;
   float* st3 = nullptr;
   bf16* xb = nullptr;  // block output (bf16)

@@ -108,7 +108,7 @@ static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weight
                         F(g.f2_b)));
   // t3 = h.W2^T + b2 + c
   ETP_TRY(wgrad(sc.gb, rows, kH, kH, rec.h, kI, kI, const_cast<void*>(g.f2_w), s));
-  ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.f2_w, kI, nullptr, nullptr, sc.dpre, 1, rec.pre, s, g.f1_b));  // * gelu'(pre)
+  ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.f2_w, kI, nullptr, nullptr, sc.dpre, 3, rec.pre, s, g.f1_b));  // * gelu'(pre), saved by the forward
   // pre = c.W1^T + b1
   ETP_TRY(wgrad(sc.dpre, rows, kI, kI, rec.cb, kH, kH, const_cast<void*>(g.f1_w), s));
   ETP_TRY(dgrad(sc.dpre, rows, kI, kI, w.f1_w, kH, sc.g0, sc.g1, nullptr, 0, nullptr, s));  // dc = dpre.W1 + dt3
@@ -234,7 +234,7 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
     // x_out = x_mid + gelu(LN2(x_mid).W1^T + b1).W2^T + b2      (A = dx_out, sc.gb = bf16(A); the linear2 bias
     // gradient = column sums of A was accumulated by the LayerNorm backward that produced A)
     ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.h, kI, kI, const_cast<void*>(lg.l2_w), s));
-    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.l2_w, kI, nullptr, nullptr, sc.dpre, 1, r.pre, s, lg.l1_b));
+    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.l2_w, kI, nullptr, nullptr, sc.dpre, 3, r.pre, s, lg.l1_b));
     ETP_TRY(wgrad(sc.dpre, rows, kI, kI, r.y2b, kH, kH, const_cast<void*>(lg.l1_w), s));
     ETP_TRY(dgrad(sc.dpre, rows, kI, kI, lw.l1_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy2
     ETP_TRY(layernorm_bwd(Bf, x_mid, lw.n2_g, r.st2, r.st2 + rows, rows, kH, A, 1, sc.gb, F(lg.n2_g), F(lg.n2_b), s,

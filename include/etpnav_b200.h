@@ -58,7 +58,7 @@ int etp_prof_report(char* buf, size_t cap);
 /* D[M,N] = epilogue(alpha * A.B^T) on tcgen05 tensor cores; replaces torch.nn.Linear / matmul on the
  * reference path (vilmodel_cmt.py:108-110,326-328,151,178,190,654; common/transformer.py:174-181).
  * a_mn/b_mn = 0: operand stored [rows, K] (K contiguous); 1: stored [K, rows] (rows contiguous).
- * epilogue: x = alpha*acc + bias[n]; out_pre = bf16(x); x = act(x); x *= f(aux); x += resid;
+ * epilogue: x = alpha*acc + bias[n]; out_pre = bf16(x) (or bf16(gelu'(x)) if pre_mode); x = act(x); x *= f(aux); x += resid;
  *           out_f32 (=, or += atomically) x; out_bf16 = bf16(x); colsum[n] += sum_m x (bias gradients). */
 typedef struct {
   int32_t M, N, K;
@@ -67,7 +67,7 @@ typedef struct {
   float alpha;
   const float* bias;
   int32_t act;        /* 0 none, 1 gelu(erf), 2 relu */
-  int32_t aux_mode;   /* 0 none, 1: *= gelu'(aux), 2: *= (aux > 0) */
+  int32_t aux_mode;   /* 0 none, 1: *= gelu'(aux), 2: *= (aux > 0), 3: *= aux */
   const void* aux; int32_t ld_aux;
   const float* resid; int32_t ld_resid;
   float* out_f32; int32_t ld_f32; int32_t atomic;
@@ -76,6 +76,7 @@ typedef struct {
   int32_t k_splits;   /* >1 requires atomic */
   int32_t block_n;    /* 0 auto, 128, 256 */
   float* colsum;      /* optional fp32 [N]: += column sums of the final value x */
+  int32_t pre_mode;   /* 0: out_pre = pre-activation, 1: out_pre = gelu'(pre-activation) (act must be 1) */
 } etp_gemm_args;
 int etp_gemm(const etp_gemm_args* args, void* stream);
 

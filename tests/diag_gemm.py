@@ -101,10 +101,10 @@ def run_epi():
     h, pre = torch.empty(M, 3072, device="cuda", dtype=torch.bfloat16), torch.empty(M, 3072, device="cuda", dtype=torch.bfloat16)
     qkv = torch.empty(M, 2304, device="cuda", dtype=torch.bfloat16)
     dpre = torch.empty(M, 3072, device="cuda", dtype=torch.bfloat16)
-    cases.append(("ffn1 768->3072 +bias gelu -> bf16 + pre", 3072, 768, lambda: L.gemm(x768, W13, bias=b3072, act=1, out_bf16=h, out_pre=pre)))
+    cases.append(("ffn1 768->3072 +bias gelu -> bf16 + pre", 3072, 768, lambda: L.gemm(x768, W13, bias=b3072, act=1, out_bf16=h, out_pre=pre, pre_mode=1)))
     cases.append(("ffn2 3072->768 +bias +resid -> f32", 768, 3072, lambda: L.gemm(x3072, W31, bias=b768, resid=resid, out_f32=o32)))
     cases.append(("qkv 768->2304 +bias -> bf16", 2304, 768, lambda: L.gemm(x768, W1q, bias=b2304, out_bf16=qkv)))
-    cases.append(("dgrad ffn2 768->3072 *gelu'(pre) -> bf16", 3072, 768, lambda: L.gemm(x768, W31, b_mn=True, aux=x3072, aux_mode=1, out_bf16=dpre)))
+    cases.append(("dgrad ffn2 768->3072 *gelu'(pre) -> bf16", 3072, 768, lambda: L.gemm(x768, W31, b_mn=True, aux=x3072, aux_mode=3, out_bf16=dpre, colsum=b3072)))
     cases.append(("dgrad ffn1 3072->768 +resid -> f32", 768, 3072, lambda: L.gemm(x3072, W13, b_mn=True, resid=resid, out_f32=o32)))
     for name, N, K, fn in cases:
         for _ in range(3):

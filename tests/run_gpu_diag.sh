@@ -12,10 +12,6 @@ echo "=== pair perf" >> gpurun_out/diag_gemm.txt
 timeout 200 python tests/diag_gemm.py perf >> gpurun_out/diag_gemm.txt 2>&1
 echo "exit $?" >> gpurun_out/diag_gemm.txt
 timeout 200 python tests/diag_gemm.py epi >> gpurun_out/diag_gemm.txt 2>&1
-echo "=== legacy perf" >> gpurun_out/diag_gemm.txt
-ETP_GEMM_IMPL=1 timeout 200 python tests/diag_gemm.py perf >> gpurun_out/diag_gemm.txt 2>&1
-ETP_GEMM_IMPL=1 timeout 200 python tests/diag_gemm.py epi >> gpurun_out/diag_gemm.txt 2>&1
-echo "exit $?" >> gpurun_out/diag_gemm.txt
 timeout 300 python -m pytest tests/test_ops_gpu.py -q -m gpu -x --timeout 60 --timeout-method=thread > gpurun_out/pytest_ops.txt 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_ops.txt
 grep -v "^  \|^   " gpurun_out/diag_gemm.txt | tail -80

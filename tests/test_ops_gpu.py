@@ -94,6 +94,19 @@ def test_gemm_epilogues(L):
     L.gemm(A, W, aux=aux, aux_mode=2, out_f32=o32)
     ref = (A.float() @ W.float().t()) * (aux.float() > 0)
     assert (o32 - ref).abs().max() < 3e-3
+    # gelu that also emits gelu'(pre) for the backward (pre_mode=1), then the backward's plain multiply by the saved
+    # derivative (aux_mode=3) with the fused bias gradient (column sums)
+    dact = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(A, W, bias=bias, act=1, out_bf16=o16, out_pre=dact, pre_mode=1)
+    xd = lin.double().requires_grad_(True)
+    torch.nn.functional.gelu(xd).sum().backward()
+    assert (o16.float() - torch.nn.functional.gelu(lin)).abs().max() < 2e-2
+    assert (dact.float() - xd.grad.float()).abs().max() < 1e-2
+    cs = torch.zeros(N, device="cuda")
+    L.gemm(A, W, aux=dact, aux_mode=3, out_f32=o32, colsum=cs)
+    ref = (A.float() @ W.float().t()) * dact.float()
+    assert (o32 - ref).abs().max() < 3e-3
+    assert (cs - ref.sum(0)).abs().max() < 2e-2
     # strided output (write into a column slice of a wider buffer)
     wide = torch.zeros(M, 2 * N, device="cuda", dtype=torch.bfloat16)
     L.gemm(A, W, bias=bias, out_bf16=wide[:, N:])
