@@ -11,6 +11,7 @@ int prof_collect(double* ms, double* flops, long long* count, char* report, size
 int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream);
 int attention_dispatch(const AttnArgs& a, cudaStream_t stream);
 int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream);
+void attention_bwd_tc_set_debug(void* dev_buf);
 }
 
 using namespace etp;
@@ -33,6 +34,9 @@ ETP_API int etp_prof_report(char* buf, size_t cap) {
   ETP_REQUIRE(buf && cap > 0, "etp_prof_report: null argument");
   return prof_collect(nullptr, nullptr, nullptr, buf, cap);
 }
+
+/* developer hook (not part of the ported interface): CTA-0 timeline of the next tcgen05 attention-backward launches */
+ETP_API void etp_debug_attention_bwd_timeline(void* dev_buf_128_u64) { attention_bwd_tc_set_debug(dev_buf_128_u64); }
 
 ETP_API int etp_check_device(void) {
   int dev = 0;

@@ -2,7 +2,7 @@
 // (graph nodes: <= 128).  PERSISTENT: one CTA per SM walks over (batch, head) items; keys in blocks of 128.
 //
 //   per key block ("step"):  S = Q.K^T, dP = dO.V^T                 (2 x [M=128,N=128,K=64] into TMEM)
-//     8 softmax-backward warps — thread = (query row, 64-key half): P = exp2(s2 - lse2), dS = P * (dP - D) (x scale),
+//     16 softmax-backward warps — thread = (query row, 32-key slice): P = exp2(s2 - lse2), dS = P * (dP - D) (x scale),
 //     both written to shared memory as bf16 in the 128B-swizzled [query, key] layout, which the tensor core
 //     reads K-major (dQ += dS.K) AND MN-major (dV = P^T.dO, dK = dS^T.Q) — the same bytes, two descriptors;
 //     sprel_linear gradients (sum dS*pair, sum dS) accumulate per thread over the CTA's whole item list;
@@ -29,10 +29,11 @@ constexpr int kBK = 128;
 constexpr int kD = 64;
 constexpr int kTile = kBQ * kD * 2;     // 16 KB: Q, dO, K, V tiles
 constexpr int kPBytes = kBQ * kBK * 2;  // 32 KB: P and dS
-constexpr int kWarps = 8;               // softmax-backward warps
+constexpr int kWQ = 4;                  // warps per TMEM lane quadrant: each owns 32 of the block's 128 keys
+constexpr int kWarps = 4 * kWQ;         // softmax-backward warps
 constexpr int kMathThreads = kWarps * 32;
 constexpr int kThreads = kMathThreads + 32;  // + control warp
-constexpr int kSmemBytes = 8 * kTile + 2 * kPBytes + 2 * kBK * 4 + 64 + 1024 + 256;
+constexpr int kSmemBytes = 8 * kTile + 2 * kPBytes + 2 * kBK * 4 + kWQ * kBQ * 4 + 256 + 1024 + 256;
 constexpr uint32_t kTmemCols = 512;  // S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448)
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -51,7 +52,18 @@ struct BwdDev {
   bf16 *dq, *dk, *dv;
   int lddq, lddk, lddv;
   float *dpair_w, *dpair_b;
+  unsigned long long* dbg;  // optional timeline of CTA 0 (globaltimer ns): [0,64) control thread, [64,128) math thread 0
 };
+
+ETP_DEVICE unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define ETP_DBG(slot)                                                      \
+  do {                                                                     \
+    if (p.dbg && blockIdx.x == 0 && (slot) < 64) p.dbg[dbg_base + (slot)] = gtime(); \
+  } while (0)
 
 ETP_DEVICE uint4 pack8(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
@@ -62,10 +74,30 @@ ETP_DEVICE uint4 pack8u(const uint32_t* u) {
                     pack_bf16x2(__uint_as_float(u[4]), __uint_as_float(u[5])),
                     pack_bf16x2(__uint_as_float(u[6]), __uint_as_float(u[7])));
 }
+ETP_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+ETP_DEVICE float dot8(const uint4& a, const uint4& c) {
+  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 fa = __bfloat1622float2(ha[t]), fc = __bfloat1622float2(hc[t]);
+    s = fmaf(fa.x, fc.x, s);
+    s = fmaf(fa.y, fc.y, s);
+  }
+  return s;
+}
 
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
-                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BwdDev p) {
+                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                        const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
+                        const __grid_constant__ CUtensorMap tmDV, const BwdDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                 // [2][16 KB]
@@ -74,9 +106,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint8_t* sV = sK + 2 * kTile;       // [2][16 KB]
   uint8_t* sP = sV + 2 * kTile;
   uint8_t* sDS = sP + kPBytes;
-  float* sKb = reinterpret_cast<float*>(sDS + kPBytes);  // [2][128] per-key additive mask (log2 domain)
-  float* sRed = sKb + 2 * kBK;                            // [16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 16);
+  float* sKb = reinterpret_cast<float*>(sDS + kPBytes);  // [2][128] per-key additive bias (log2 domain)
+  float* sDp = sKb + 2 * kBK;                             // [kWQ][128] partial row dots of dO.O
+  float* sRed = sDp + kWQ * kBQ;                          // [2 * kWarps]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 2 * kWarps);
   uint64_t* q_full = bars + 0;    // [2]
   uint64_t* kv_full = bars + 2;   // [2]
   uint64_t* sdp_ready = bars + 4;
@@ -90,6 +123,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDQ); tma_prefetch_desc(&tmDK); tma_prefetch_desc(&tmDV);
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
     mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
     mbar_init(sdp_ready, 1);
@@ -129,6 +163,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tma_load_3d(sK + st * kTile, &tmK, &kv_full[st], h * kD, j * kBK, b);
         tma_load_3d(sV + st * kTile, &tmV, &kv_full[st], h * kD, j * kBK, b);
       };
+      const int dbg_base = 0;
+      ETP_DBG(0);
       load_q(blockIdx.x, 0);
       load_kv(blockIdx.x, 0, 0);
       int s = 0;   // step counter (item, key block) of this CTA
@@ -142,12 +178,18 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           if (j == 0) mbar_wait(&q_full[qst], (ii >> 1) & 1);
           mbar_wait(&kv_full[kst], (s >> 1) & 1);
           tc_fence_after();
+          ETP_DBG(1 + 4 * s);  // tiles landed
+          {
+            // descriptor low words advance by (bytes >> 4) per MMA; high words are loop constants
+            const uint64_t dq0 = make_smem_desc(aQ, 16, 1024), dk0 = make_smem_desc(aK, 16, 1024);
+            const uint64_t do0 = make_smem_desc(aDO, 16, 1024), dv0 = make_smem_desc(aV, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k)
-            umma_bf16(tS, make_smem_desc(aQ + k * 32, 16, 1024), make_smem_desc(aK + k * 32, 16, 1024), id_s, k > 0 ? 1u : 0u);
+            for (int k = 0; k < kD / 16; ++k)
+              umma_bf16_lh(tS, desc_lo(dq0) + 2 * k, desc_hi(dq0), desc_lo(dk0) + 2 * k, desc_hi(dk0), id_s, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k)
-            umma_bf16(tDP, make_smem_desc(aDO + k * 32, 16, 1024), make_smem_desc(aV + k * 32, 16, 1024), id_s, k > 0 ? 1u : 0u);
+            for (int k = 0; k < kD / 16; ++k)
+              umma_bf16_lh(tDP, desc_lo(do0) + 2 * k, desc_hi(do0), desc_lo(dv0) + 2 * k, desc_hi(dv0), id_s, k > 0 ? 1u : 0u);
+          }
           umma_commit(sdp_ready);
           // prefetch the tiles of the next step; its buffers were last read by the MMAs of step s-1
           const bool more_blocks = j + 1 < nblk;
@@ -161,64 +203,110 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               load_kv(next_item, 0, (s + 1) & 1);
             }
           }
+          ETP_DBG(2 + 4 * s);  // S/dP issued, next tiles requested
           mbar_wait(pds_ready, s & 1);
           tc_fence_after();
-          // reduction over the 128 queries, 16 per MMA: A panels are [query rows of 128 B] -> advance 16 rows = 2048 B,
-          // two 64-key panels 16 KB apart (LBO), 8-row groups 1 KB apart (SBO); B = dO / Q tile read MN-major.
+          ETP_DBG(3 + 4 * s);  // P/dS ready
+          // dV / dK: reduction over the 128 queries, 16 per MMA: A panels are [query rows of 128 B] -> advance 16 rows =
+          // 2048 B, two 64-key panels 16 KB apart (LBO), 8-row groups 1 KB apart (SBO); B = dO / Q tile read MN-major.
+          {
+            const uint64_t dpm = make_smem_desc(aP, 16384, 1024), dsm = make_smem_desc(aDS, 16384, 1024);   // MN-major A
+            const uint64_t dom = make_smem_desc(aDO, 8192, 1024), dqm = make_smem_desc(aQ, 8192, 1024);     // MN-major B
+            const uint64_t dsk = make_smem_desc(aDS, 16, 1024);                                             // K-major A
+            const uint64_t dkm = make_smem_desc(aK, 8192, 1024);                                            // MN-major B
 #pragma unroll
-          for (int k = 0; k < kBQ / 16; ++k) {
-            umma_bf16(tDV, make_smem_desc(aP + k * 2048, 16384, 1024), make_smem_desc(aDO + k * 2048, 8192, 1024), id_kv,
-                      k > 0 ? 1u : 0u);
-            umma_bf16(tDK, make_smem_desc(aDS + k * 2048, 16384, 1024), make_smem_desc(aQ + k * 2048, 8192, 1024), id_kv,
-                      k > 0 ? 1u : 0u);
+            for (int k = 0; k < kBQ / 16; ++k) {
+              umma_bf16_lh(tDV, desc_lo(dpm) + 128 * k, desc_hi(dpm), desc_lo(dom) + 128 * k, desc_hi(dom), id_kv, k > 0 ? 1u : 0u);
+              umma_bf16_lh(tDK, desc_lo(dsm) + 128 * k, desc_hi(dsm), desc_lo(dqm) + 128 * k, desc_hi(dqm), id_kv, k > 0 ? 1u : 0u);
+            }
+            // dQ += dS.K : reduction over the 128 keys of this block
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_lh(tDQ, desc_lo(dsk) + (k >> 2) * 1024 + (k & 3) * 2, desc_hi(dsk), desc_lo(dkm) + 128 * k, desc_hi(dkm),
+                           id_q, (j > 0 || k > 0) ? 1u : 0u);
           }
-          // dQ += dS.K : reduction over the 128 keys of this block
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16(tDQ, make_smem_desc(aDS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(aK + k * 2048, 8192, 1024), id_q, (j > 0 || k > 0) ? 1u : 0u);
           umma_commit(g_ready);
+          ETP_DBG(4 + 4 * s);  // dV/dK/dQ issued
         }
       }
     }
   } else {
-    // ======================= softmax-backward warps =======================
+    // ======================= softmax-backward warps: thread = (query row, 32-key slice) =======================
     const int quad = warp & 3;            // TMEM lane quadrant
-    const int hh = warp >> 2;             // which 64 keys of the block (softmax phase) / dV vs dK (read-back phase)
+    const int wq = warp >> 2;             // which 32 keys of the block (softmax phase) / which read-back slice
     const int r = quad * 32 + lane;       // query row (softmax phase) / key row of the block (dK, dV read-back)
     const bool qv = r < p.Sq;
-    const bool warp_live = quad * 32 < p.Sq;  // some row of this warp is a real query
+    const bool warp_live = quad * 32 < p.Sq;  // some row of this warp is a real query (warp-uniform)
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-    const float pw_raw = p.pair_w_dev ? __ldg(p.pair_w_dev) : p.pair_w;
-    const float pb_raw = p.pair_b_dev ? __ldg(p.pair_b_dev) : p.pair_b;
-    const float pw = pw_raw * kLog2e, pb = pb_raw * kLog2e;
+    const float pw2 = (p.pair_w_dev ? __ldg(p.pair_w_dev) : p.pair_w) * kLog2e;
+    const float pb2 = (p.pair_b_dev ? __ldg(p.pair_b_dev) : p.pair_b) * kLog2e;
     const float sl2 = p.scale * kLog2e;
     const float mask2 = p.mask_value * kLog2e;
     const bool pair_vec = (p.Sk & 3) == 0;  // rows of the pair bias are 16-byte aligned
-    float wsum = 0.f, bsum = 0.f;
+    const int dbg_base = 64;
+    const bool dbg_thread = threadIdx.x == 0;
+    float wsum = 0.f, bsum = 0.f;           // sum dS*scale*pair, sum dS*scale over everything this thread sees
     int s = 0;
+    // O / dO slices and lse of the row for the NEXT item are requested one item ahead (their latency hides behind
+    // the current item's math); D = sum_d dO * O: each of the row's four threads takes 16 of the 64 dims
+    uint4 nO0, nO1, nD0, nD1;
+    float n_lse = 0.f;
+    auto request_item = [&](int item) {
+      if (qv && item < n_items) {
+        const int b = item / p.heads, h = item % p.heads;
+        const size_t row = static_cast<size_t>(b) * p.Sq + r;
+        const uint4* po = reinterpret_cast<const uint4*>(p.out + row * p.ldo + h * kD + wq * 16);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.dout + row * p.lddo + h * kD + wq * 16);
+        nO0 = __ldg(po); nO1 = __ldg(po + 1); nD0 = __ldg(pd); nD1 = __ldg(pd + 1);
+        n_lse = p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Sq + r];
+      }
+    };
+    // per-step inputs fetched one step ahead as well: validity of key (k0 + tid) for the mask, and the first 16 pair
+    // biases of this thread's row
+    uint8_t kv_next = 1;
+    float pv[16];
+    auto load_pair_at = [&](const float* row_ptr, int key0) {
+      if constexpr (kPair) {
+        if (qv) {
+          if (pair_vec) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (key0 + i < p.Sk) f = __ldg(reinterpret_cast<const float4*>(row_ptr + key0 + i));
+              pv[i] = f.x; pv[i + 1] = f.y; pv[i + 2] = f.z; pv[i + 3] = f.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pv[i] = (key0 + i < p.Sk) ? __ldg(row_ptr + key0 + i) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pv[i] = 0.f;
+        }
+      }
+    };
+    auto request_step = [&](int item, int j) {
+      if (item >= n_items) return;
+      const int b = item / p.heads;
+      if (threadIdx.x < kBK) {
+        const int k = j * kBK + static_cast<int>(threadIdx.x);
+        kv_next = (p.key_valid && k < p.Sk) ? __ldg(p.key_valid + static_cast<size_t>(b) * p.Sk + k) : 1;
+      }
+      if constexpr (kPair) load_pair_at(p.pair + (static_cast<size_t>(b) * p.Sq + r) * p.Sk, j * kBK + wq * 32);
+    };
+    request_item(blockIdx.x);
+    request_step(blockIdx.x, 0);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.heads, h = item % p.heads;
-      const uint8_t* kvalid = p.key_valid ? p.key_valid + static_cast<size_t>(b) * p.Sk : nullptr;
-      const float* pair_row = p.pair ? p.pair + (static_cast<size_t>(b) * p.Sq + r) * p.Sk : nullptr;
-      // D = sum_d dO * O and the saved log-sum-exp of this query row
-      float Dv = 0.f, lse2 = 0.f;
-      if (qv) {
-        const size_t row = static_cast<size_t>(b) * p.Sq + r;
-        const uint4* po = reinterpret_cast<const uint4*>(p.out + row * p.ldo + h * kD);
-        const uint4* pd = reinterpret_cast<const uint4*>(p.dout + row * p.lddo + h * kD);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 a = __ldg(po + i), c = __ldg(pd + i);
-          const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
-          const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 fa = __bfloat1622float2(ha[t]), fc = __bfloat1622float2(hc[t]);
-            Dv += fa.x * fc.x + fa.y * fc.y;
-          }
+      const float* pair_row = kPair ? p.pair + (static_cast<size_t>(b) * p.Sq + r) * p.Sk : nullptr;
+      float nlse2 = -INFINITY, Ds = 0.f;  // -lse (log2 domain): -inf kills padding rows
+      {
+        float part = 0.f;
+        if (qv) {
+          part = dot8(nO0, nD0) + dot8(nO1, nD1);
+          nlse2 = -n_lse * kLog2e;
         }
-        lse2 = p.lse[(static_cast<size_t>(b) * p.heads + h) * p.Sq + r] * kLog2e;
+        sDp[wq * kBQ + r] = part;
       }
 
       for (int j = 0; j < nblk; ++j, ++s) {
@@ -228,64 +316,51 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (threadIdx.x < kBK) {
           const int k = k0 + static_cast<int>(threadIdx.x);
           float v = -INFINITY;
-          if (k < p.Sk) v = (kvalid && !kvalid[k]) ? mask2 : 0.f;
+          if (k < p.Sk) v = (kv_next ? 0.f : mask2) + (kPair ? pb2 : 0.f);
           kb[threadIdx.x] = v;
         }
-        // pair bias of this thread's row for its first 32 keys: in flight while the S / dP MMAs run
-        float pv[32];
-        auto load_pair = [&](int c0) {
-          const int key0 = k0 + c0;
-          if (pair_row != nullptr && qv) {
-            if (pair_vec) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (key0 + i < p.Sk) f = __ldg(reinterpret_cast<const float4*>(pair_row + key0 + i));
-                pv[i] = f.x; pv[i + 1] = f.y; pv[i + 2] = f.z; pv[i + 3] = f.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) pv[i] = (key0 + i < p.Sk) ? __ldg(pair_row + key0 + i) : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) pv[i] = 0.f;
-          }
-        };
-        load_pair(hh * 64);
-        named_bar_sync(1, kMathThreads);  // key mask visible
+        if (dbg_thread) ETP_DBG(0 + 6 * s);  // step begins
+        if (threadIdx.x == 0) tma_store_wait_read();  // the previous step's output tiles have left P / dS
+        named_bar_sync(1, kMathThreads);  // key bias (and, for j == 0, the partial row dots) visible
+        if (j == 0) Ds = (sDp[r] + sDp[kBQ + r] + sDp[2 * kBQ + r] + sDp[3 * kBQ + r]) * p.scale;
+        if (dbg_thread) ETP_DBG(1 + 6 * s);  // past the CTA barrier
         mbar_wait(sdp_ready, ph);
         tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = hh * 64 + cc * 32;  // first key column of this chunk inside the block
-          uint32_t vs[32], vd[32];
-          float pe[32], de[32];
+        if (dbg_thread) ETP_DBG(2 + 6 * s);  // S/dP ready
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int c = wq * 32 + sub * 16;  // first key column of this 16-key piece inside the block
+          float pe[16], de[16];
           if (warp_live) {  // warp-uniform: tcgen05.ld is a warp-collective instruction
-            tmem_ld32(tS + lane_sel + c, vs);
-            tmem_ld32(tDP + lane_sel + c, vd);
+            uint32_t vs[16], vd[16];
+            tmem_ld16(tS + lane_sel + c, vs);
+            tmem_ld16(tDP + lane_sel + c, vd);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float sc = fmaf(__uint_as_float(vs[i]), sl2, kb[c + i]);
-              if (pair_row) sc += fmaf(pw, pv[i], pb);
-              const float pr = qv ? exp2f(sc - lse2) : 0.f;
-              const float ds = pr * (__uint_as_float(vd[i]) - Dv);
-              wsum = fmaf(ds, pv[i], wsum);
-              bsum += ds;
-              pe[i] = pr;
-              de[i] = ds * p.scale;
+            for (int i = 0; i < 16; i += 4) {
+              const float4 kb4 = *reinterpret_cast<const float4*>(kb + c + i);
+              const float kbv[4] = {kb4.x, kb4.y, kb4.z, kb4.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float sc = fmaf(__uint_as_float(vs[i + t]), sl2, kbv[t]);
+                if constexpr (kPair) sc = fmaf(pw2, pv[i + t], sc);
+                const float pr = ex2_approx(sc + nlse2);                            // P (0 on padding rows)
+                const float dss = pr * fmaf(__uint_as_float(vd[i + t]), p.scale, -Ds);  // dS * scale
+                if constexpr (kPair) { wsum = fmaf(dss, pv[i + t], wsum); bsum += dss; }
+                pe[i + t] = pr;
+                de[i + t] = dss;
+              }
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { pe[i] = 0.f; de[i] = 0.f; }
+            for (int i = 0; i < 16; ++i) { pe[i] = 0.f; de[i] = 0.f; }
           }
-          if (cc == 0) load_pair(hh * 64 + 32);  // next chunk's bias while this one is packed and stored
+          if (sub == 0) load_pair_at(pair_row, k0 + wq * 32 + 16);  // next piece's bias while this one is packed
           uint8_t* prow = sP + (c >> 6) * 16384 + r * 128;
           uint8_t* drow = sDS + (c >> 6) * 16384 + r * 128;
           const int ch0 = (c & 63) >> 3;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
             const int off = (((ch0 + g) ^ (r & 7)) << 4);
             *reinterpret_cast<uint4*>(prow + off) = pack8(pe + 8 * g);
             *reinterpret_cast<uint4*>(drow + off) = pack8(de + 8 * g);
@@ -294,51 +369,64 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(pds_ready);
-        // dK / dV of this key block: thread r now owns key k0 + r; warps 0-3 store dV, warps 4-7 store dK
+        if (dbg_thread) ETP_DBG(3 + 6 * s);  // P/dS written
+        // next step's mask / bias and, at an item boundary, the next item's O / dO / lse: in flight during the read-back
+        if (j == nblk - 1) {
+          request_item(item + gridDim.x);
+          request_step(item + gridDim.x, 0);
+        } else {
+          request_step(item, j + 1);
+        }
+        // dK / dV of this key block (thread r now owns key k0 + r; slices 0,1 take dV columns, slices 2,3 dK columns)
+        // and, after the last block, dQ: TMEM -> bf16 -> the (now idle) P / dS buffers in the TMA 128B-swizzled
+        // layout -> one TMA store per tile.  Row-per-thread global stores would touch 32 cache lines per warp
+        // instruction; the TMA store is asynchronous and clips rows past the sequence end.
         mbar_wait(g_ready, ph);
         tc_fence_after();
-        const int key = k0 + r;
+        if (dbg_thread) ETP_DBG(4 + 6 * s);  // dV/dK/dQ ready
         {
-          const uint32_t tsrc = (hh == 0 ? tDV : tDK) + lane_sel;
-          bf16* gbase = (hh == 0) ? p.dv : p.dk;
-          const int ldg = (hh == 0) ? p.lddv : p.lddk;
-#pragma unroll
-          for (int c = 0; c < kD; c += 32) {
-            uint32_t vv[32];
-            tmem_ld32(tsrc + c, vv);
-            tmem_ld_wait();
-            if (key < p.Sk) {
-              bf16* g = gbase + (static_cast<size_t>(b) * p.Sk + key) * ldg + h * kD + c;
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(g + i) = pack8u(vv + i);
-            }
-          }
-        }
-        if (j == nblk - 1) {
-          // dQ of this item (complete with this step's commit): each warp group stores 32 of the 64 columns
-          uint32_t v[32];
-          tmem_ld32(tDQ + lane_sel + hh * 32, v);
+          const int cs = (wq & 1) * 32;
+          uint32_t vv[32];
+          tmem_ld32((wq < 2 ? tDV : tDK) + lane_sel + cs, vv);
           tmem_ld_wait();
-          if (qv) {
-            bf16* gq = p.dq + (static_cast<size_t>(b) * p.Sq + r) * p.lddq + h * kD + hh * 32;
+          uint8_t* trow = sP + (wq < 2 ? 0 : kTile) + r * 128;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(gq + i) = pack8u(v + i);
-          }
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(trow + ((((wq & 1) * 4 + g) ^ (r & 7)) << 4)) = pack8u(vv + 8 * g);
         }
+        if (j == nblk - 1 && wq < 2) {
+          uint32_t v[32];
+          tmem_ld32(tDQ + lane_sel + wq * 32, v);
+          tmem_ld_wait();
+          uint8_t* trow = sDS + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(trow + (((wq * 4 + g) ^ (r & 7)) << 4)) = pack8u(v + 8 * g);
+        }
+        fence_proxy_async();
         tc_fence_before();
+        named_bar_sync(2, kMathThreads);  // tiles complete
+        if (threadIdx.x == 0) {
+          tma_store_3d(&tmDV, sP, h * kD, k0, b);
+          tma_store_3d(&tmDK, sP + kTile, h * kD, k0, b);
+          if (j == nblk - 1) tma_store_3d(&tmDQ, sDS, h * kD, 0, b);
+          tma_store_commit();
+        }
+        if (dbg_thread) ETP_DBG(5 + 6 * s);  // read-back stored
       }
     }
-    if (p.dpair_w) {
+    if (threadIdx.x == 0) tma_store_wait_all();
+    if (kPair && p.dpair_w) {
       wsum = warp_sum(wsum);
       bsum = warp_sum(bsum);
-      if (lane == 0) { sRed[warp] = wsum; sRed[8 + warp] = bsum; }
+      if (lane == 0) { sRed[warp] = wsum; sRed[kWarps + warp] = bsum; }
       named_bar_sync(1, kMathThreads);
       if (threadIdx.x == 0) {
         float a = 0.f, c = 0.f;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) { a += sRed[w]; c += sRed[8 + w]; }
-        atomicAdd(p.dpair_w, a);
-        atomicAdd(p.dpair_b, c);
+        for (int w = 0; w < kWarps; ++w) { a += sRed[w]; c += sRed[kWarps + w]; }
+        const float inv = 1.0f / p.scale;  // the sums were taken over dS * scale
+        atomicAdd(p.dpair_w, a * inv);
+        atomicAdd(p.dpair_b, c * inv);
       }
     }
   }
@@ -352,6 +440,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 }  // namespace
+
+// debug timeline buffer (device, 128 x u64) of the next launches; null = off
+static unsigned long long* g_attn_bwd_dbg = nullptr;
+void attention_bwd_tc_set_debug(void* dev_buf) { g_attn_bwd_dbg = static_cast<unsigned long long*>(dev_buf); }
 
 bool attention_bwd_tc_supported(const AttnBwdArgs& a) {
   if (a.Sq > kBQ) return false;
@@ -374,9 +466,17 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = get_tmap_3d(a.v, W, a.Sk, a.B, a.ldv, static_cast<uint64_t>(a.Sk) * a.ldv, kD, kBK, &tv);
   if (rc) return rc;
+  CUtensorMap tdq, tdk, tdv;
+  rc = get_tmap_3d(a.dq, W, a.Sq, a.B, a.lddq, static_cast<uint64_t>(a.Sq) * a.lddq, kD, kBQ, &tdq);
+  if (rc) return rc;
+  rc = get_tmap_3d(a.dk, W, a.Sk, a.B, a.lddk, static_cast<uint64_t>(a.Sk) * a.lddk, kD, kBK, &tdk);
+  if (rc) return rc;
+  rc = get_tmap_3d(a.dv, W, a.Sk, a.B, a.lddv, static_cast<uint64_t>(a.Sk) * a.lddv, kD, kBK, &tdv);
+  if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    ETP_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    ETP_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    ETP_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   BwdDev d;
@@ -385,9 +485,13 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream) {
   d.pair_b_dev = a.pair_b_dev; d.out = a.out; d.ldo = a.ldo; d.dout = a.dout; d.lddo = a.lddo; d.lse = a.lse;
   d.dq = a.dq; d.dk = a.dk; d.dv = a.dv; d.lddq = a.lddq; d.lddk = a.lddk; d.lddv = a.lddv;
   d.dpair_w = a.dpair_w; d.dpair_b = a.dpair_b;
+  d.dbg = g_attn_bwd_dbg;
   const int items = a.B * a.heads;
   const int grid = items < num_sms() ? items : num_sms();
-  ETP_CHECK_CUDA(launch_pdl(attention_bwd_tc_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, tq, tdo, tk, tv, d));
+  if (a.pair)
+    ETP_CHECK_CUDA(launch_pdl(attention_bwd_tc_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tq, tdo, tk, tv, tdq, tdk, tdv, d));
+  else
+    ETP_CHECK_CUDA(launch_pdl(attention_bwd_tc_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tq, tdo, tk, tv, tdq, tdk, tdv, d));
   ETP_LAUNCHED();
   return ETP_OK;
 }

@@ -85,6 +85,20 @@ ETP_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// TMA store (tile mode) shared -> global, bulk-group completion.  Rows / columns of the box that fall outside the
+// tensor are not written.  The shared-memory tile must have been made visible with fence_proxy_async().
+ETP_DEVICE void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+ETP_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk stores committed by this thread have finished READING shared memory (it may be reused)
+ETP_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and until they are complete (global writes performed)
+ETP_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, loads
 // ----------------------------------------------------------------------------------------------
@@ -111,6 +125,22 @@ ETP_DEVICE void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uin
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the two descriptors given as (lo, hi) words: inside an unrolled issue loop only the 14-bit address field
+// of the low word changes, so advancing a descriptor is one 32-bit add instead of a 64-bit rebuild (the issuing
+// thread is a single lane: its instruction count is on the critical path of every MMA phase).
+ETP_DEVICE void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+ETP_DEVICE uint32_t desc_lo(uint64_t d) { return static_cast<uint32_t>(d); }
+ETP_DEVICE uint32_t desc_hi(uint64_t d) { return static_cast<uint32_t>(d >> 32); }
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 ETP_DEVICE void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -71,10 +71,9 @@ ETP_DEVICE void flush(float* dst, const float* s, int n) {
 ETP_DEVICE void zero_smem(float* s, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = 0.f;
 }
-// Every CTA of these kernels ends by adding its shared-memory partials (thousands of floats) to global memory, so
-// the grid is kept small: the row loop is short either way, the flush traffic scales with the CTA count.
-int grid_for(int rows, int cap = 64) {
+int grid_for(int rows) {
   int g = (rows + 7) / 8;
+  const int cap = 2 * num_sms();
   return g > cap ? cap : (g < 1 ? 1 : g);
 }
 }  // namespace
@@ -204,7 +203,8 @@ int node_pack_bwd(const float* dx, const int64_t* step_ids, const float* pos_fts
     ETP_CHECK_CUDA(cudaFuncSetAttribute(node_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  int grid = grid_for(rows, 48);
+  int grid = grid_for(rows);
+  if (grid > num_sms()) grid = num_sms();
   ETP_CHECK_CUDA(launch_pdl(node_pack_bwd_kernel, dim3(grid), dim3(256), smem, stream, dx, step_ids, pos_fts, pos_lin, stats, pos_g, rows, dstep_emb, dpos_w,
                                                     dpos_b, dpos_g, dpos_bb));
   ETP_LAUNCHED();
@@ -284,7 +284,8 @@ int pano_pack_bwd(const PanoPackBwdArgs& a, cudaStream_t stream) {
     ETP_CHECK_CUDA(cudaFuncSetAttribute(pano_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  const int grid = grid_for(a.rows, 24);
+  int grid = grid_for(a.rows);
+  if (grid > num_sms()) grid = num_sms();
   ETP_CHECK_CUDA(launch_pdl(pano_pack_bwd_kernel, dim3(grid), dim3(256), smem, stream, a));
   ETP_LAUNCHED();
   return ETP_OK;
