@@ -28,6 +28,7 @@
 // Replaces the cuBLAS calls behind torch.nn.Linear / torch.matmul on the reference path
 // (vilmodel_cmt.py:108-110,326-328,151,178,190,654; common/transformer.py:174-181).
 #include <cstdio>
+#include <cstring>
 
 #include "common.cuh"
 #include "gemm_dev.h"
@@ -55,9 +56,31 @@ struct PairCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+// Grouped mode: several independent problems  dW_g += A_g^T.B_g  (the weight gradients of one transformer layer)
+// share one persistent launch; a tile index maps to (problem, m block, n block).  Every tile owns its output and
+// accumulates with a plain read-add-write.  One launch instead of seven removes six prologues / pipeline fills and
+// lets the tiles of the small problems fill the waves of the large ones.
+constexpr int kMaxGroup = 8;
+struct GroupProblem {
+  CUtensorMap tmA, tmB;
+  int M, N, K;
+  int tiles_n, tile_start;
+  int ld;
+  float* out;
+};
+struct GroupParams {
+  int n, total_tiles;
+  GroupProblem prob[kMaxGroup];
+};
+
+// what one tile index means (both modes)
+struct TileRef {
+  const CUtensorMap *tmA, *tmB;
+  int m_blk, n_blk, kb0, kb1, g;
+};
+
+template <int BN, bool A_MN, bool B_MN, bool kGrouped>
+ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, const GroupParams* gp) {
   using Cfg = PairCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -74,8 +97,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    if constexpr (kGrouped) {
+      for (int g = 0; g < gp->n; ++g) {
+        tma_prefetch_desc(&gp->prob[g].tmA);
+        tma_prefetch_desc(&gp->prob[g].tmB);
+      }
+    } else {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 2);   // one arrival per CTA's producer (+ the bytes of both)
       mbar_init(&empty_bar[s], 1);  // the MMA commit
@@ -101,10 +131,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.tiles_m * p.tiles_n * p.k_splits;
-  const int total_kb = (p.K + BK - 1) / BK;
+  const int num_tiles = kGrouped ? gp->total_tiles : p.tiles_m * p.tiles_n * p.k_splits;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  auto decode = [&](int t) -> TileRef {
+    TileRef r;
+    if constexpr (kGrouped) {
+      int g = 0;
+      while (g + 1 < gp->n && t >= gp->prob[g + 1].tile_start) ++g;
+      const GroupProblem& pr = gp->prob[g];
+      const int local = t - pr.tile_start;
+      r.g = g; r.tmA = &pr.tmA; r.tmB = &pr.tmB;
+      r.n_blk = local % pr.tiles_n; r.m_blk = local / pr.tiles_n;
+      r.kb0 = 0; r.kb1 = (pr.K + BK - 1) / BK;
+    } else {
+      const int total_kb = (p.K + BK - 1) / BK;
+      r.g = 0; r.tmA = &tmA; r.tmB = &tmB;
+      r.n_blk = t % p.tiles_n;
+      r.m_blk = (t / p.tiles_n) % p.tiles_m;
+      const int ks = t / (p.tiles_n * p.tiles_m);
+      r.kb0 = ks * p.kb_per_split;
+      r.kb1 = min(total_kb, r.kb0 + p.kb_per_split);
+    }
+    return r;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -113,14 +163,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int n_blk = t % p.tiles_n;
-        const int m_blk = (t / p.tiles_n) % p.tiles_m;
-        const int ks = t / (p.tiles_n * p.tiles_m);
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
-        const int m0 = m_blk * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n0 = n_blk * BN + static_cast<int>(rank) * (BN / 2);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const TileRef tr = decode(t);
+        const CUtensorMap* mA = tr.tmA;
+        const CUtensorMap* mB = tr.tmB;
+        const int m0 = tr.m_blk * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = tr.n_blk * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = tr.kb0; kb < tr.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -129,16 +177,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else        mbar_arrive_cluster(bar);
           const int k0 = kb * BK;
           if (!A_MN) {
-            tma_load_2d_pair(sa, &tmA, bar, k0, m0);
+            tma_load_2d_pair(sa, mA, bar, k0, m0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tmA, bar, m0 + j * 64, k0);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * 8192, mA, bar, m0 + j * 64, k0);
           }
           if (!B_MN) {
-            tma_load_2d_pair(sb, &tmB, bar, k0, n0);
+            tma_load_2d_pair(sb, mB, bar, k0, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * 8192, &tmB, bar, n0 + j * 64, k0);
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * 8192, mB, bar, n0 + j * 64, k0);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -153,9 +201,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int ks = t / (p.tiles_n * p.tiles_m);
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const TileRef tr = decode(t);
+        const int kb0 = tr.kb0, kb1 = tr.kb1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -192,24 +239,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int n_blk = t % p.tiles_n;
-      const int m_blk = (t / p.tiles_n) % p.tiles_m;
+      const TileRef tr = decode(t);
+      const int n_blk = tr.n_blk, m_blk = tr.m_blk;
+      GemmDev e = p;  // epilogue view of this tile's problem
+      if constexpr (kGrouped) {
+        const GroupProblem& pr = gp->prob[tr.g];
+        e.M = pr.M; e.N = pr.N;
+        e.out_f32 = pr.out; e.ld_f32 = pr.ld;
+        e.resid = pr.out; e.ld_resid = pr.ld;  // dW += acc
+      }
       const int row0 = m_blk * (2 * BM) + static_cast<int>(rank) * BM + quad * 32 + rh * 16;  // first row of this lane
       const int colbase = n_blk * BN + half * (BN / 2) + 2 * cp;
-      const int nrows = min(16, p.M - row0);  // <= 0: nothing of this lane's rows is inside the matrix
+      const int nrows = min(16, e.M - row0);  // <= 0: nothing of this lane's rows is inside the matrix
 
       // residual of chunk `c` in the transposed layout: 16 independent row segments in flight per lane
       float2 R[16];
       auto load_resid = [&](int c, float2 (&dst)[16]) {
         const int col = colbase + c * 32;
-        const float* rp = p.resid + static_cast<size_t>(row0) * p.ld_resid + col;
-        const bool ok = col < p.N;
+        const float* rp = e.resid + static_cast<size_t>(row0) * e.ld_resid + col;
+        const bool ok = col < e.N;
 #pragma unroll
         for (int k = 0; k < 16; ++k)
-          dst[k] = (ok && k < nrows) ? __ldg(reinterpret_cast<const float2*>(rp + static_cast<size_t>(k) * p.ld_resid))
+          dst[k] = (ok && k < nrows) ? __ldg(reinterpret_cast<const float2*>(rp + static_cast<size_t>(k) * e.ld_resid))
                                      : make_float2(0.f, 0.f);
       };
-      if (p.resid) load_resid(0, R);  // lands while the main loop of this tile is still running
+      if (e.resid) load_resid(0, R);  // lands while the main loop of this tile is still running
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -217,17 +271,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int col = colbase + c * 32;
-        const bool colok = col < p.N;
+        const bool colok = col < e.N;
         uint32_t r[32];
         tmem_ld32(taddr0 + c * 32, r);
         float2 Rn[16];
-        if (p.resid && c + 1 < kChunks) load_resid(c + 1, Rn);
+        if (e.resid && c + 1 < kChunks) load_resid(c + 1, Rn);
         uint32_t ax[16];
-        if (p.aux_mode) {
-          const __nv_bfloat16* ap = p.aux + static_cast<size_t>(row0) * p.ld_aux + col;
+        if (e.aux_mode) {
+          const __nv_bfloat16* ap = e.aux + static_cast<size_t>(row0) * e.ld_aux + col;
 #pragma unroll
           for (int k = 0; k < 16; ++k)
-            ax[k] = (colok && k < nrows) ? __ldg(reinterpret_cast<const unsigned int*>(ap + static_cast<size_t>(k) * p.ld_aux)) : 0u;
+            ax[k] = (colok && k < nrows) ? __ldg(reinterpret_cast<const unsigned int*>(ap + static_cast<size_t>(k) * e.ld_aux)) : 0u;
         }
         tmem_ld_wait();
         if (c == kChunks - 1) {
@@ -253,21 +307,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
         if (nrows > 0 && colok) {
           float2 bias = make_float2(0.f, 0.f);
-          if (p.bias) bias = __ldg(reinterpret_cast<const float2*>(p.bias + col));
+          if (e.bias) bias = __ldg(reinterpret_cast<const float2*>(e.bias + col));
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            v[2 * k] = fmaf(v[2 * k], p.alpha, bias.x);
-            v[2 * k + 1] = fmaf(v[2 * k + 1], p.alpha, bias.y);
+            v[2 * k] = fmaf(v[2 * k], e.alpha, bias.x);
+            v[2 * k + 1] = fmaf(v[2 * k + 1], e.alpha, bias.y);
           }
-          if (p.out_pre && !p.pre_mode) {
-            __nv_bfloat16* o = p.out_pre + static_cast<size_t>(row0) * p.ld_pre + col;
+          if (e.out_pre && !e.pre_mode) {
+            __nv_bfloat16* o = e.out_pre + static_cast<size_t>(row0) * e.ld_pre + col;
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-              if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * p.ld_pre) = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+              if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * e.ld_pre) = pack_bf16x2(v[2 * k], v[2 * k + 1]);
           }
-          if (p.act == 1 && p.pre_mode) {
+          if (e.act == 1 && e.pre_mode) {
             // GELU and its derivative from one Phi / exp evaluation; the derivative is what the backward multiplies by
-            __nv_bfloat16* o = p.out_pre + static_cast<size_t>(row0) * p.ld_pre + col;
+            __nv_bfloat16* o = e.out_pre + static_cast<size_t>(row0) * e.ld_pre + col;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               float c0, e0, c1, e1;
@@ -275,64 +329,64 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               phi_parts(v[2 * k + 1], c1, e1);
               const float d0 = fmaf(v[2 * k] * 0.39894228040143267794f, e0, c0);
               const float d1 = fmaf(v[2 * k + 1] * 0.39894228040143267794f, e1, c1);
-              if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * p.ld_pre) = pack_bf16x2(d0, d1);
+              if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * e.ld_pre) = pack_bf16x2(d0, d1);
               v[2 * k] *= c0;
               v[2 * k + 1] *= c1;
             }
-          } else if (p.act == 1) {
+          } else if (e.act == 1) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
-          } else if (p.act == 2) {
+          } else if (e.act == 2) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
           }
-          if (p.aux_mode == 1) {
+          if (e.aux_mode == 1) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               v[2 * k] *= dgelu_fast(__uint_as_float(ax[k] << 16));
               v[2 * k + 1] *= dgelu_fast(__uint_as_float(ax[k] & 0xffff0000u));
             }
-          } else if (p.aux_mode == 2) {
+          } else if (e.aux_mode == 2) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               v[2 * k] = (__uint_as_float(ax[k] << 16) > 0.0f) ? v[2 * k] : 0.0f;
               v[2 * k + 1] = (__uint_as_float(ax[k] & 0xffff0000u) > 0.0f) ? v[2 * k + 1] : 0.0f;
             }
           }
-          if (p.aux_mode == 3) {
+          if (e.aux_mode == 3) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               v[2 * k] *= __uint_as_float(ax[k] << 16);
               v[2 * k + 1] *= __uint_as_float(ax[k] & 0xffff0000u);
             }
           }
-          if (p.resid) {
+          if (e.resid) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) { v[2 * k] += R[k].x; v[2 * k + 1] += R[k].y; }
           }
-          if (p.out_f32) {
-            float* o = p.out_f32 + static_cast<size_t>(row0) * p.ld_f32 + col;
-            if (p.atomic) {
+          if (e.out_f32) {
+            float* o = e.out_f32 + static_cast<size_t>(row0) * e.ld_f32 + col;
+            if (e.atomic) {
 #pragma unroll
               for (int k = 0; k < 16; ++k)
                 if (k < nrows)
-                  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + static_cast<size_t>(k) * p.ld_f32), "f"(v[2 * k]),
+                  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + static_cast<size_t>(k) * e.ld_f32), "f"(v[2 * k]),
                                "f"(v[2 * k + 1])
                                : "memory");
             } else {
 #pragma unroll
               for (int k = 0; k < 16; ++k)
-                if (k < nrows) *reinterpret_cast<float2*>(o + static_cast<size_t>(k) * p.ld_f32) = make_float2(v[2 * k], v[2 * k + 1]);
+                if (k < nrows) *reinterpret_cast<float2*>(o + static_cast<size_t>(k) * e.ld_f32) = make_float2(v[2 * k], v[2 * k + 1]);
             }
           }
-          if (p.out_bf16) {
-            __nv_bfloat16* o = p.out_bf16 + static_cast<size_t>(row0) * p.ld_bf16 + col;
+          if (e.out_bf16) {
+            __nv_bfloat16* o = e.out_bf16 + static_cast<size_t>(row0) * e.ld_bf16 + col;
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-              if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * p.ld_bf16) = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+              if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * e.ld_bf16) = pack_bf16x2(v[2 * k], v[2 * k + 1]);
           }
         }
-        if (p.colsum) {
+        if (e.colsum) {
           // bias gradient: column sums of the final values (rows outside the matrix contribute 0)
           float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
@@ -343,9 +397,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
           s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
           if (rh == 0 && colok)
-            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p.colsum + col), "f"(s0), "f"(s1) : "memory");
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(e.colsum + col), "f"(s0), "f"(s1) : "memory");
         }
-        if (p.resid && c + 1 < kChunks) {
+        if (e.resid && c + 1 < kChunks) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) R[k] = Rn[k];
         }
@@ -363,6 +417,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  gemm_body<BN, A_MN, B_MN, false>(tmA, tmB, p, nullptr);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tcgen05_grouped_kernel(const __grid_constant__ GroupParams gp, const GemmDev p) {
+  gemm_body<BN, A_MN, B_MN, true>(gp.prob[0].tmA, gp.prob[0].tmB, p, &gp);
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -395,6 +461,50 @@ int launch_pair(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
     prof_tag(tag, 2.0 * a.M * a.N * a.K);
   }
   ETP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, dev));
+  ETP_LAUNCHED();
+  return ETP_OK;
+}
+
+template <int BN>
+int launch_grouped_tt(const GemmArgs* a, int n, cudaStream_t stream) {
+  using Cfg = PairCfg<BN>;
+  GroupParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.n = n;
+  int tiles = 0;
+  double flops = 0.0;
+  for (int g = 0; g < n; ++g) {
+    GroupProblem& pr = gp.prob[g];
+    int rc = get_tmap_2d(a[g].A, a[g].K, a[g].M, a[g].lda, BK, 64, &pr.tmA);  // MN-major: global [K, M], box [64 k, 64 m]
+    if (rc) return rc;
+    rc = get_tmap_2d(a[g].B, a[g].K, a[g].N, a[g].ldb, BK, 64, &pr.tmB);
+    if (rc) return rc;
+    pr.M = a[g].M; pr.N = a[g].N; pr.K = a[g].K;
+    pr.tiles_n = (a[g].N + BN - 1) / BN;
+    pr.tile_start = tiles;
+    pr.ld = a[g].ld_f32;
+    pr.out = a[g].out_f32;
+    tiles += ((a[g].M + 2 * BM - 1) / (2 * BM)) * pr.tiles_n;
+    flops += 2.0 * a[g].M * a[g].N * a[g].K;
+  }
+  gp.total_tiles = tiles;
+  GemmDev d;
+  memset(&d, 0, sizeof(d));
+  d.alpha = 1.0f;
+  auto kern = gemm_tcgen05_grouped_kernel<BN, true, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ETP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  if (g_prof_on) {
+    char tag[96];
+    snprintf(tag, sizeof(tag), "grouped wgrad x%d bn%d TT K%d tiles%d", n, BN, a[0].K, tiles);
+    prof_tag(tag, flops);
+  }
+  ETP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, gp, d));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -456,6 +566,37 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   if (bn == 256) { ETP_PAIR_DISPATCH(256) }
   ETP_PAIR_DISPATCH(128)
 #undef ETP_PAIR_DISPATCH
+}
+
+// Several weight-gradient problems  out_g[M_g, N_g] += A_g^T . B_g  (A_g stored [K_g, M_g], B_g stored [K_g, N_g]) in ONE
+// persistent launch.  Every problem: a_mn = b_mn = 1, fp32 output accumulated in place, no other epilogue.
+int gemm_grouped_wgrad(const GemmArgs* a, int n, cudaStream_t stream) {
+  ETP_REQUIRE(a != nullptr && n >= 1 && n <= kMaxGroup, "gemm_grouped_wgrad: 1..8 problems");
+  bool all256 = true;
+  for (int g = 0; g < n; ++g) {
+    ETP_REQUIRE(a[g].M > 0 && a[g].N > 0 && a[g].K > 0 && a[g].A && a[g].B && a[g].out_f32, "gemm_grouped_wgrad: bad problem");
+    ETP_REQUIRE(a[g].a_mn && a[g].b_mn && a[g].N % 2 == 0 && a[g].ld_f32 % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a[g].out_f32) & 15) == 0,
+                "gemm_grouped_wgrad: operands must be MN-major, outputs 16-byte aligned");
+    all256 = all256 && (a[g].N % 256 == 0);
+  }
+  // tile width by the same cost model as the single-problem path: waves x (k-blocks + epilogue)
+  const int pairs = num_sms() / 2;
+  double best = 1e30;
+  int bn = 128;
+  for (int cand = 128; cand <= 256; cand += 128) {
+    if (cand == 256 && !all256) continue;
+    int tiles = 0, kbmax = 0;
+    for (int g = 0; g < n; ++g) {
+      tiles += ((a[g].M + 2 * BM - 1) / (2 * BM)) * ((a[g].N + cand - 1) / cand);
+      kbmax = max(kbmax, (a[g].K + BK - 1) / BK);
+    }
+    const int waves = (tiles + pairs - 1) / pairs;
+    const double w = cand / 256.0;
+    const double cost = waves * (kbmax * w + 8.0 * w + 4.0);
+    if (cost < best) { best = cost; bn = cand; }
+  }
+  return bn == 256 ? launch_grouped_tt<256>(a, n, stream) : launch_grouped_tt<128>(a, n, stream);
 }
 
 }  // namespace etp

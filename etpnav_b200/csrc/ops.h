@@ -37,6 +37,8 @@ struct GemmArgs {
   float* colsum = nullptr;  // fp32 [N]: += column sums of the final value (bias gradient of the producing Linear)
 };
 int gemm(const GemmArgs& a, cudaStream_t stream);
+// n <= 8 weight-gradient problems (a_mn = b_mn = 1, out_f32 += A^T.B, nothing else) in one persistent launch
+int gemm_grouped_wgrad(const GemmArgs* a, int n, cudaStream_t stream);
 
 // ---- row-wise kernels (elementwise.cu) ------------------------------------------------------------
 // y = LayerNorm(x) * gamma + beta over the last dim (H = 768), biased variance, eps inside sqrt.

@@ -19,7 +19,9 @@ namespace etp {
 
 struct BwdScratch {
   float *g0 = nullptr, *g1 = nullptr, *g2 = nullptr;  // fp32 [rows,768]
-  bf16 *gb = nullptr, *dctx = nullptr, *dq = nullptr;  // bf16 [rows,768]
+  bf16 *gb = nullptr, *gb2 = nullptr, *gb3 = nullptr;  // bf16 [rows,768]: dY of the three 768-wide Linears of a layer,
+                                                        // kept until the layer's weight gradients run as one launch
+  bf16 *dctx = nullptr, *dq = nullptr;                  // bf16 [rows,768]
   bf16* dqkv = nullptr;                                 // bf16 [rows,2304]
   bf16* dpre = nullptr;                                 // bf16 [rows,3072]
   bf16* dkv = nullptr;                                  // bf16 [kv_rows,1536]
@@ -27,7 +29,8 @@ struct BwdScratch {
   float* dtxt = nullptr;                                // fp32 [kv_rows,768]
   void carve(Arena& ar, size_t rows, size_t kv_rows, size_t bhs, size_t kv_layers = 1) {
     g0 = ar.take<float>(rows * kH); g1 = ar.take<float>(rows * kH); g2 = ar.take<float>(rows * kH);
-    gb = ar.take<bf16>(rows * kH); dctx = ar.take<bf16>(rows * kH); dq = ar.take<bf16>(rows * kH);
+    gb = ar.take<bf16>(rows * kH); gb2 = ar.take<bf16>(rows * kH); gb3 = ar.take<bf16>(rows * kH);
+    dctx = ar.take<bf16>(rows * kH); dq = ar.take<bf16>(rows * kH);
     dqkv = ar.take<bf16>(rows * 3 * kH);
     dpre = ar.take<bf16>(rows * kI);
     dkv = ar.take<bf16>(kv_rows * 2 * kH * kv_layers);  // all layers' dK|dV side by side
@@ -89,6 +92,32 @@ static int wgrad(const bf16* dY, int rows, int N_out, int ldy, const bf16* X, in
   return gemm(g, s);
 }
 
+// The weight gradients of one layer do not feed anything else in the backward pass: they are collected here and run
+// as ONE grouped launch when the layer's data gradients are done (gemm_grouped_wgrad).  The dY operands must stay
+// untouched until flush().
+struct WgradBatch {
+  GemmArgs a[8];
+  int n = 0;
+  int add(const bf16* dY, int rows, int N_out, int ldy, const bf16* X, int K_in, int ldx, const void* dW, cudaStream_t s) {
+    if (dW == nullptr) return ETP_OK;
+    if (n == 8) ETP_TRY(flush(s));
+    GemmArgs& g = a[n++];
+    g = GemmArgs();
+    g.M = N_out; g.N = K_in; g.K = rows;
+    g.A = dY; g.lda = ldy; g.a_mn = 1;
+    g.B = X; g.ldb = ldx; g.b_mn = 1;
+    g.out_f32 = static_cast<float*>(const_cast<void*>(dW)); g.ld_f32 = K_in;
+    return ETP_OK;
+  }
+  int flush(cudaStream_t s) {
+    int rc = ETP_OK;
+    if (n == 1) rc = wgrad(a[0].A, a[0].K, a[0].M, a[0].lda, a[0].B, a[0].N, a[0].ldb, a[0].out_f32, s);
+    else if (n > 1) rc = gemm_grouped_wgrad(a, n, s);
+    n = 0;
+    return rc;
+  }
+};
+
 static int bias_grad(const bf16* dY, int rows, int cols, int ld, const void* db, cudaStream_t s) {
   if (db == nullptr) return ETP_OK;
   return colsum_bf16(dY, rows, cols, ld, static_cast<float*>(const_cast<void*>(db)), s);
@@ -100,24 +129,29 @@ static inline float* F(const void* p) { return static_cast<float*>(const_cast<vo
 static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weights& g, const LayerRecord& rec,
                               const bf16* a_bf16, const float* dx_out, float* da, int B, int S, const uint8_t* key_valid,
                               const float* pair, const float* pair_w, const float* pair_b, float* dpair_w, float* dpair_b,
-                              BwdScratch& sc, cudaStream_t s) {
+                              BwdScratch& sc, WgradBatch& wb, cudaStream_t s) {
   const int rows = B * S;
   // x = LN(t3)
   // (bias gradients ride along: column sums of dt3 inside the LayerNorm backward, of dpre inside the dgrad epilogue)
-  ETP_TRY(layernorm_bwd(dx_out, rec.t3, w.fln_g, rec.st3, rec.st3 + rows, rows, kH, sc.g0, 0, sc.gb, F(g.fln_g), F(g.fln_b), s,
+  ETP_TRY(layernorm_bwd(dx_out, rec.t3, w.fln_g, rec.st3, rec.st3 + rows, rows, kH, sc.g0, 0, sc.gb3, F(g.fln_g), F(g.fln_b), s,
                         F(g.f2_b)));
   // t3 = h.W2^T + b2 + c
-  ETP_TRY(wgrad(sc.gb, rows, kH, kH, rec.h, kI, kI, const_cast<void*>(g.f2_w), s));
-  ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.f2_w, kI, nullptr, nullptr, sc.dpre, 3, rec.pre, s, g.f1_b));  // * gelu'(pre), saved by the forward
+  ETP_TRY(wb.add(sc.gb3, rows, kH, kH, rec.h, kI, kI, g.f2_w, s));
+  ETP_TRY(dgrad(sc.gb3, rows, kH, kH, w.f2_w, kI, nullptr, nullptr, sc.dpre, 3, rec.pre, s, g.f1_b));  // * gelu'(pre), saved by the forward
   // pre = c.W1^T + b1
-  ETP_TRY(wgrad(sc.dpre, rows, kI, kI, rec.cb, kH, kH, const_cast<void*>(g.f1_w), s));
+  ETP_TRY(wb.add(sc.dpre, rows, kI, kI, rec.cb, kH, kH, g.f1_w, s));
   ETP_TRY(dgrad(sc.dpre, rows, kI, kI, w.f1_w, kH, sc.g0, sc.g1, nullptr, 0, nullptr, s));  // dc = dpre.W1 + dt3
   // c = LN(t2)
-  ETP_TRY(layernorm_bwd(sc.g1, rec.t2, w.sln_g, rec.st2, rec.st2 + rows, rows, kH, sc.g0, 0, sc.gb, F(g.sln_g), F(g.sln_b), s,
+  ETP_TRY(layernorm_bwd(sc.g1, rec.t2, w.sln_g, rec.st2, rec.st2 + rows, rows, kH, sc.g0, 0, sc.gb2, F(g.sln_g), F(g.sln_b), s,
                         F(g.so_b)));
   // t2 = ctx2.Wo^T + bo + a
-  ETP_TRY(wgrad(sc.gb, rows, kH, kH, rec.ctx2, kH, kH, const_cast<void*>(g.so_w), s));
-  ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.so_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
+  ETP_TRY(wb.add(sc.gb2, rows, kH, kH, rec.ctx2, kH, kH, g.so_w, s));
+  // Bias gradients of the fused q|k|v projection, without touching dK / dV:  the context is  P.(x.Wv + b_v)  and the
+  // rows of P sum to one, so  d b_v = column sums of dctx  (taken in this dgrad's epilogue);  a key bias shifts all
+  // scores of a query row equally, which softmax ignores, so  d b_k = 0  exactly;  only  d b_q = column sums of dQ
+  // needs a pass over the attention backward's output.
+  ETP_TRY(dgrad(sc.gb2, rows, kH, kH, w.so_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s,
+                g.sqkv_b ? F(g.sqkv_b) + 2 * kH : nullptr));
   // attention
   AttnBwdArgs at;
   at.B = B; at.heads = kHeads; at.Sq = S; at.Sk = S;
@@ -129,8 +163,8 @@ static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weight
   at.dq = sc.dqkv; at.dk = sc.dqkv + kH; at.dv = sc.dqkv + 2 * kH; at.lddq = at.lddk = at.lddv = 3 * kH;
   ETP_TRY(attention_bwd_dispatch(at, s));
   // qkv = a.Wqkv^T + b
-  ETP_TRY(bias_grad(sc.dqkv, rows, 3 * kH, 3 * kH, g.sqkv_b, s));
-  ETP_TRY(wgrad(sc.dqkv, rows, 3 * kH, 3 * kH, a_bf16, kH, kH, const_cast<void*>(g.sqkv_w), s));
+  ETP_TRY(bias_grad(sc.dqkv, rows, kH, 3 * kH, g.sqkv_b, s));  // query part only (see above)
+  ETP_TRY(wb.add(sc.dqkv, rows, 3 * kH, 3 * kH, a_bf16, kH, kH, g.sqkv_w, s));
   ETP_TRY(dgrad(sc.dqkv, rows, 3 * kH, 3 * kH, w.sqkv_w, kH, sc.g0, da, nullptr, 0, nullptr, s));  // da = dqkv.Wqkv + dt2
   return ETP_OK;
 }
@@ -169,13 +203,16 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     const etp_layer_weights& lg = g.layers[i];
     const LayerRecord& r = rec.layers[i];
     const bf16* x_in = i > 0 ? rec.layers[i - 1].xb : rec.x0b;
+    WgradBatch wb;
     ETP_TRY(self_ffn_block_bwd(lw, lg, r, r.ab, P, Q, B, N, in.gmap_masks, w.sprel_w ? in.gmap_pair_dists : nullptr, w.sprel_w,
-                               w.sprel_b, F(g.sprel_w), F(g.sprel_b), sc, s));
+                               w.sprel_b, F(g.sprel_w), F(g.sprel_b), sc, wb, s));
     // a = LN(t1),  t1 = ctx1.Wo^T + bo + x_in
     ETP_TRY(layernorm_bwd(Q, r.t1, lw.xln_g, r.st1, r.st1 + rows, rows, kH, sc.g0, 0, sc.gb, F(lg.xln_g), F(lg.xln_b), s,
                           F(lg.xo_b)));
-    ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.ctx1, kH, kH, const_cast<void*>(lg.xo_w), s));
-    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.xo_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
+    ETP_TRY(wb.add(sc.gb, rows, kH, kH, r.ctx1, kH, kH, lg.xo_w, s));
+    // d b_v (text value bias of this layer) = column sums of dctx; d b_k = 0 (see self_ffn_block_bwd)
+    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.xo_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s,
+                  lg.xkv_b ? F(lg.xkv_b) + kH : nullptr));
     AttnBwdArgs at;
     at.B = B; at.heads = kHeads; at.Sq = N; at.Sk = L;
     at.q = r.q; at.ldq = kH; at.k = r.kv; at.ldk = r.ldkv; at.v = r.kv + kH; at.ldv = r.ldkv;
@@ -185,12 +222,12 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     at.dq = sc.dq; at.lddq = kH; at.dk = dkv_i; at.lddk = ldkv; at.dv = dkv_i + kH; at.lddv = ldkv;
     ETP_TRY(attention_bwd_dispatch(at, s));
     ETP_TRY(bias_grad(sc.dq, rows, kH, kH, lg.xq_b, s));
-    ETP_TRY(wgrad(sc.dq, rows, kH, kH, x_in, kH, kH, const_cast<void*>(lg.xq_w), s));
+    ETP_TRY(wb.add(sc.dq, rows, kH, kH, x_in, kH, kH, lg.xq_w, s));
     ETP_TRY(dgrad(sc.dq, rows, kH, kH, lw.xq_w, kH, sc.g0, P, nullptr, 0, nullptr, s));  // dx_in = dq.Wq + dt1
+    ETP_TRY(wb.flush(s));  // the layer's six weight gradients, one launch
   }
-  // text side, all layers at once: kv_all = txt . Wkv_all^T + b  ->  one bias-grad, one wgrad, one dgrad
+  // text side, all layers at once: kv_all = txt . Wkv_all^T + b  ->  one wgrad, one dgrad (bias grads: above)
   if (X > 0) {
-    ETP_TRY(bias_grad(sc.dkv, kv_rows, ldkv, ldkv, g.xkv_all_b, s));
     ETP_TRY(wgrad(sc.dkv, kv_rows, ldkv, ldkv, rec.txtb, kH, kH, const_cast<void*>(g.xkv_all_w), s));
     if (d_txt_embeds) ETP_TRY(dgrad(sc.dkv, kv_rows, ldkv, ldkv, w.xkv_all_w, kH, nullptr, dtxt, nullptr, 0, nullptr, s));
   } else if (d_txt_embeds) {
@@ -233,15 +270,17 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
     const float* x_mid = rec.xs[2 * i + 1];
     // x_out = x_mid + gelu(LN2(x_mid).W1^T + b1).W2^T + b2      (A = dx_out, sc.gb = bf16(A); the linear2 bias
     // gradient = column sums of A was accumulated by the LayerNorm backward that produced A)
-    ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.h, kI, kI, const_cast<void*>(lg.l2_w), s));
+    WgradBatch wb;
+    ETP_TRY(wb.add(sc.gb, rows, kH, kH, r.h, kI, kI, lg.l2_w, s));
     ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.l2_w, kI, nullptr, nullptr, sc.dpre, 3, r.pre, s, lg.l1_b));
-    ETP_TRY(wgrad(sc.dpre, rows, kI, kI, r.y2b, kH, kH, const_cast<void*>(lg.l1_w), s));
+    ETP_TRY(wb.add(sc.dpre, rows, kI, kI, r.y2b, kH, kH, lg.l1_w, s));
     ETP_TRY(dgrad(sc.dpre, rows, kI, kI, lw.l1_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy2
-    ETP_TRY(layernorm_bwd(Bf, x_mid, lw.n2_g, r.st2, r.st2 + rows, rows, kH, A, 1, sc.gb, F(lg.n2_g), F(lg.n2_b), s,
+    ETP_TRY(layernorm_bwd(Bf, x_mid, lw.n2_g, r.st2, r.st2 + rows, rows, kH, A, 1, sc.gb2, F(lg.n2_g), F(lg.n2_b), s,
                           F(lg.out_b)));  // A = dx_mid
     // x_mid = x + attn(LN1(x)).Wout^T + bout
-    ETP_TRY(wgrad(sc.gb, rows, kH, kH, r.ctx, kH, kH, const_cast<void*>(lg.out_w), s));
-    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.out_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s));
+    ETP_TRY(wb.add(sc.gb2, rows, kH, kH, r.ctx, kH, kH, lg.out_w, s));
+    ETP_TRY(dgrad(sc.gb2, rows, kH, kH, lw.out_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s,
+                  lg.in_b ? F(lg.in_b) + 2 * kH : nullptr));  // d b_v of in_proj_bias (q|k|v); d b_k = 0
     AttnBwdArgs at;
     at.B = B; at.heads = kHeads; at.Sq = V; at.Sk = V;
     at.q = r.qkv; at.k = r.qkv + kH; at.v = r.qkv + 2 * kH; at.ldq = at.ldk = at.ldv = 3 * kH;
@@ -249,9 +288,10 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
     at.scale = 0.125f; at.key_valid = pano_masks; at.mask_value = -INFINITY;
     at.dq = sc.dqkv; at.dk = sc.dqkv + kH; at.dv = sc.dqkv + 2 * kH; at.lddq = at.lddk = at.lddv = 3 * kH;
     ETP_TRY(attention_bwd(at, s));
-    ETP_TRY(bias_grad(sc.dqkv, rows, 3 * kH, 3 * kH, lg.in_b, s));
-    ETP_TRY(wgrad(sc.dqkv, rows, 3 * kH, 3 * kH, r.y1b, kH, kH, const_cast<void*>(lg.in_w), s));
+    ETP_TRY(bias_grad(sc.dqkv, rows, kH, 3 * kH, lg.in_b, s));  // query part
+    ETP_TRY(wb.add(sc.dqkv, rows, 3 * kH, 3 * kH, r.y1b, kH, kH, lg.in_w, s));
     ETP_TRY(dgrad(sc.dqkv, rows, 3 * kH, 3 * kH, lw.in_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy1
+    ETP_TRY(wb.flush(s));  // the layer's four weight gradients, one launch (sc.gb is rewritten just below)
     ETP_TRY(layernorm_bwd(Bf, x, lw.n1_g, r.st1, r.st1 + rows, rows, kH, A, 1, sc.gb, F(lg.n1_g), F(lg.n1_b), s,
                           i > 0 ? F(g.layers[i - 1].l2_b) : nullptr));  // A = dx (= dx_out of layer i-1)
   }
@@ -293,8 +333,10 @@ int backward_txt(const etp_txt_weights& w, const etp_txt_weights& g, const int64
   for (int i = NL - 1; i >= 0; --i) {
     const bf16* a_bf16 = i > 0 ? rec.layers[i - 1].xb : rec.x0b;
     float* da = (dx == P) ? Q : P;
+    WgradBatch wb;
     ETP_TRY(self_ffn_block_bwd(w.layers[i], g.layers[i], rec.layers[i], a_bf16, dx, da, B, L, txt_masks, nullptr, nullptr,
-                               nullptr, nullptr, nullptr, sc, s));
+                               nullptr, nullptr, nullptr, sc, wb, s));
+    ETP_TRY(wb.flush(s));
     dx = da;
   }
   ETP_TRY(embed_txt_bwd(dx, txt_ids, rec.sum_pre, rec.emb_stats, w.emb_g, B, L, F(g.word_emb), F(g.pos_emb), F(g.type_emb0),
