@@ -333,15 +333,23 @@ def main():
     ms_per_step = total_ms / a.steps
     value = world / (ms_per_step * 1e-3)
 
-    # end-to-end: host inputs -> H2D -> step -> D2H logits
-    def e2e_step():
-        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        lg = step(d)
-        logits_host.copy_(lg, non_blocking=True)
+    # end-to-end: host inputs -> H2D -> step -> D2H logits, through the public API.  Every step's inputs are copied
+    # from pinned host memory inside the timed region; the copy of step t+1 is staged on a side stream while step t
+    # computes (etpnav_b200.pipeline.HostInputPrefetcher), the compute stream waits on its event.
+    from etpnav_b200.pipeline import HostInputPrefetcher
+    pf = HostInputPrefetcher(dev)
 
-    for _ in range(3):
-        e2e_step()
-    e2e_ms = timed(e2e_step, a.steps) / a.steps
+    def e2e_run(n):
+        pf.submit(pinned)
+        for i in range(n):
+            d = pf.get()
+            if i + 1 < n:
+                pf.submit(pinned)      # next step's inputs start crossing PCIe now
+            lg = step(d)
+            logits_host.copy_(lg, non_blocking=True)
+
+    e2e_run(3)
+    e2e_ms = timed(lambda: e2e_run(a.steps), 1) / a.steps
     e2e_val = world / (e2e_ms * 1e-3)
 
     # roofline of the dominant kernel (tcgen05 GEMM): profiled pass with per-launch CUDA events

@@ -1,7 +1,9 @@
 // Backward of the token-packing kernels, the SAP-head tail and the text embedding (pack.cu), plus AdamW.
-// Same mapping as the forward: one warp per 768-wide row, 24 values per lane.  Parameter gradients are
-// accumulated per CTA in shared memory (shared atomics) and flushed with one global atomicAdd per
-// element per CTA; rows are visited in a grid-stride loop so the number of flushes stays ~2 per SM.
+// Same mapping as the forward: one warp per 768-wide row, 24 values per lane.  Parameter gradients are accumulated
+// as per-lane register partials over a grid-stride loop of rows and reduced once per CTA (layernorm_bwd pattern),
+// or, where only a few hundred rows exist, added straight to global memory with 128-bit vector reductions.
+// (Shared-memory float atomics are CAS loops: with eight warps adding to the same 768 addresses they cost ~20 us
+// per ROW in the first version of these kernels.)
 #include "common.cuh"
 #include "host.h"
 #include "ops.h"
@@ -26,11 +28,6 @@ ETP_DEVICE void st24_bf16(bf16* p, int lane, const float (&v)[24]) {
     *reinterpret_cast<uint2*>(p + (i * 32 + lane) * 4) =
         make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3]));
 }
-// shared-memory accumulation of a per-lane 24-vector into s[768]
-ETP_DEVICE void sacc(float* s, int lane, const float (&v)[24]) {
-#pragma unroll
-  for (int i = 0; i < 24; ++i) atomicAdd(&s[col_of(i, lane)], v[i]);
-}
 // LayerNorm backward of one row held across the warp.  In: dy, x (overwritten by xhat), mean, rstd, gamma.
 // Out: dx (in dy).  dgam/dbet receive this row's contributions (dy * xhat, dy).
 ETP_DEVICE void ln_bwd_row(float (&dy)[24], float (&x)[24], float mean, float rstd, const float (&g)[24],
@@ -50,26 +47,29 @@ ETP_DEVICE void ln_bwd_row(float (&dy)[24], float (&x)[24], float mean, float rs
 #pragma unroll
   for (int i = 0; i < 24; ++i) dy[i] = rstd * (dy[i] - s1 - x[i] * s2);
 }
-// CTA partial -> global gradient.  128-bit vector reductions (4x fewer L2 atomic operations) when the destination
-// is 16-byte aligned, which every parameter gradient in the flat buffer is; all-zero quads are skipped.
-ETP_DEVICE void flush(float* dst, const float* s, int n) {
+// one row's contribution straight to global memory: six 128-bit reductions per lane (512 B per warp instruction)
+ETP_DEVICE void gred24(float* dst, int lane, const float (&v)[24]) {
   if (dst == nullptr) return;
-  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (n & 3) == 0) {
-    for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
-      const float4 v = *reinterpret_cast<const float4*>(s + i);
-      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                     : "memory");
-    }
-    return;
-  }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = s[i];
-    if (v != 0.f) atomicAdd(dst + i, v);
-  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (i * 32 + lane) * 4), "f"(v[4 * i]),
+                 "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                 : "memory");
 }
-ETP_DEVICE void zero_smem(float* s, int n) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = 0.f;
+// CTA reduction of per-lane register partials (one 24-vector per warp) through red[8][768], then one atomicAdd per
+// column per CTA (the layernorm_bwd pattern).  Every thread of the 256-thread CTA must call it.
+ETP_DEVICE void cta_reduce_add(float (*red)[kH], int warp, int lane, const float (&v)[24], float* dst) {
+  if (dst == nullptr) return;  // uniform across the CTA
+#pragma unroll
+  for (int i = 0; i < 24; ++i) red[warp][col_of(i, lane)] = v[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < kH; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][c];
+    atomicAdd(dst + c, t);
+  }
+  __syncthreads();
 }
 int grid_for(int rows) {
   int g = (rows + 7) / 8;
@@ -87,58 +87,59 @@ __global__ void __launch_bounds__(256) sap_tail_bwd_kernel(const float* __restri
                                                             float* dgamma, float* dbeta, float* dw4, float* db4) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
-  extern __shared__ float sm[];  // [3][768] + [1]
-  float* s_g = sm; float* s_b = sm + kH; float* s_w = sm + 2 * kH; float* s_b4 = sm + 3 * kH;
-  zero_smem(sm, 3 * kH + 1);
-  __syncthreads();
+  __shared__ float red[8][kH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g[24], bt[24], w[24];
   ld24(gamma, lane, g);
   ld24(beta, lane, bt);
   ld24(w4, lane, w);
+  // parameter-gradient partials of this lane over the warp's rows (registers), reduced once at the end
+  float ag[24], ab[24], aw[24], ab4 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { ag[i] = 0.f; ab[i] = 0.f; aw[i] = 0.f; }
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const bool dead = (visited && visited[row]) || (valid && !valid[row]);
     const float dl = dead ? 0.f : dlogits[row];
-    float r[24], dh[24], x[24], dgm[24], dbt[24], dw[24];
+    float r[24], dh[24], x[24], dgm[24], dbt[24];
     ld24(relu_out + static_cast<size_t>(row) * kH, lane, r);
     const float mu = mean[row], rs = rstd[row];
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
       x[i] = r[i];
       dh[i] = dl * w[i];
-      dw[i] = dl * ((r[i] - mu) * rs * g[i] + bt[i]);
+      aw[i] = fmaf(dl, (r[i] - mu) * rs * g[i] + bt[i], aw[i]);
     }
     ln_bwd_row(dh, x, mu, rs, g, dgm, dbt);
 #pragma unroll
-    for (int i = 0; i < 24; ++i) dh[i] = r[i] > 0.f ? dh[i] : 0.f;
-    st24_bf16(dpre + static_cast<size_t>(row) * kH, lane, dh);
-    if (dl != 0.f) {
-      sacc(s_g, lane, dgm);
-      sacc(s_b, lane, dbt);
-      sacc(s_w, lane, dw);
-      if (lane == 0) atomicAdd(s_b4, dl);
+    for (int i = 0; i < 24; ++i) {
+      ag[i] += dgm[i];
+      ab[i] += dbt[i];
+      dh[i] = r[i] > 0.f ? dh[i] : 0.f;
     }
+    st24_bf16(dpre + static_cast<size_t>(row) * kH, lane, dh);
+    ab4 += dl;
   }
-  __syncthreads();
-  flush(dgamma, s_g, kH);
-  flush(dbeta, s_b, kH);
-  flush(dw4, s_w, kH);
-  flush(db4, s_b4, 1);
+  cta_reduce_add(red, warp, lane, ag, dgamma);
+  cta_reduce_add(red, warp, lane, ab, dbeta);
+  cta_reduce_add(red, warp, lane, aw, dw4);
+  if (db4 != nullptr && lane == 0 && ab4 != 0.f) atomicAdd(db4, ab4);
 }
 
 int sap_tail_bwd(const float* dlogits, const float* relu_out, const float* gamma, const float* beta, const float* w4,
                  const float* mean, const float* rstd, const uint8_t* visited, const uint8_t* valid, int rows,
                  bf16* dpre_bf16, float* dgamma, float* dbeta, float* dw4, float* db4, cudaStream_t stream) {
   if (rows <= 0) return ETP_OK;
-  ETP_CHECK_CUDA(launch_pdl(sap_tail_bwd_kernel, dim3(grid_for(rows)), dim3(256), (3 * kH + 1) * sizeof(float), stream, 
+  ETP_CHECK_CUDA(launch_pdl(sap_tail_bwd_kernel, dim3(grid_for(rows)), dim3(256), 0, stream, 
       dlogits, relu_out, gamma, beta, w4, mean, rstd, visited, valid, rows, dpre_bf16, dgamma, dbeta, dw4, db4));
   ETP_LAUNCHED();
   return ETP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
-constexpr int kStepCache = 16;  // step ids below this accumulate in shared memory first
-
+// x0 = img_fts + E_step[ids] + LN(pos_fts.W^T + b): LayerNorm backward per row (one warp per row); gamma / beta /
+// bias / step-0 gradients as per-lane register partials; the [768,7] weight gradient d^T.pos_fts by staging the 8 rows
+// of an iteration in shared memory and letting each thread own 3 columns (21 fp32 accumulators); rows with a
+// non-zero step id (visited nodes, a minority) add straight to their embedding row with vector reductions.
 __global__ void __launch_bounds__(256) node_pack_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ step_ids,
                                                              const float* __restrict__ pos_fts, const float* __restrict__ pos_lin,
                                                              const float* __restrict__ stats, const float* __restrict__ pos_g,
@@ -146,79 +147,95 @@ __global__ void __launch_bounds__(256) node_pack_bwd_kernel(const float* __restr
                                                              float* dpos_g, float* dpos_bb) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
-  extern __shared__ float sm[];
-  float* s_w = sm;                       // [768*7]
-  float* s_b = s_w + kH * 7;             // [768]
-  float* s_g = s_b + kH;                 // [768]
-  float* s_bb = s_g + kH;                // [768]
-  float* s_step = s_bb + kH;             // [kStepCache][768]
-  zero_smem(sm, kH * 10 + kStepCache * kH);
-  __syncthreads();
+  __shared__ float red[8][kH];  // row staging for the weight gradient, then the CTA reduction buffer
+  __shared__ float sf[8][8];    // pos_fts of the 8 rows of this iteration
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g[24];
   ld24(pos_g, lane, g);
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-    float d[24], x[24], dgm[24], dbt[24];
-    ld24(dx + static_cast<size_t>(row) * kH, lane, d);
-    const int64_t id = step_ids[row];
-    if (dstep_emb) {
-      if (id < kStepCache) {
-        sacc(s_step + id * kH, lane, d);
-      } else {
+  float ag[24], ab[24], abias[24], astep0[24];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) atomicAdd(dstep_emb + id * kH + col_of(i, lane), d[i]);
+  for (int i = 0; i < 24; ++i) { ag[i] = 0.f; ab[i] = 0.f; abias[i] = 0.f; astep0[i] = 0.f; }
+  float aw[3][7];  // thread-owned columns threadIdx.x, +256, +512 of dpos_w
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) aw[c][j] = 0.f;
+  const int iters = (rows + gridDim.x * 8 - 1) / (gridDim.x * 8);
+  for (int it = 0; it < iters; ++it) {
+    const int row = (it * gridDim.x + blockIdx.x) * 8 + warp;
+    float d[24];
+    if (row < rows) {
+      float x[24], dgm[24], dbt[24];
+      ld24(dx + static_cast<size_t>(row) * kH, lane, d);
+      const int64_t id = step_ids[row];
+      if (dstep_emb) {
+        if (id == 0) {
+#pragma unroll
+          for (int i = 0; i < 24; ++i) astep0[i] += d[i];
+        } else {
+          gred24(dstep_emb + id * kH, lane, d);
+        }
+      }
+      ld24(pos_lin + static_cast<size_t>(row) * kH, lane, x);
+      ln_bwd_row(d, x, stats[static_cast<size_t>(row) * 2], stats[static_cast<size_t>(row) * 2 + 1], g, dgm, dbt);
+#pragma unroll
+      for (int i = 0; i < 24; ++i) { ag[i] += dgm[i]; ab[i] += dbt[i]; abias[i] += d[i]; }
+      if (lane < 7) sf[warp][lane] = pos_fts[static_cast<size_t>(row) * 7 + lane];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 24; ++i) d[i] = 0.f;
+      if (lane < 7) sf[warp][lane] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 24; ++i) red[warp][col_of(i, lane)] = d[i];
+    __syncthreads();
+    if (dpos_w) {
+#pragma unroll
+      for (int r8 = 0; r8 < 8; ++r8) {
+        float f[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) f[j] = sf[r8][j];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float dv = red[r8][threadIdx.x + 256 * c];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) aw[c][j] = fmaf(dv, f[j], aw[c][j]);
+        }
       }
     }
-    ld24(pos_lin + static_cast<size_t>(row) * kH, lane, x);
-    ln_bwd_row(d, x, stats[static_cast<size_t>(row) * 2], stats[static_cast<size_t>(row) * 2 + 1], g, dgm, dbt);
-    sacc(s_g, lane, dgm);
-    sacc(s_bb, lane, dbt);
-    sacc(s_b, lane, d);
-    float f[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) f[j] = pos_fts[static_cast<size_t>(row) * 7 + j];
-#pragma unroll
-    for (int i = 0; i < 24; ++i) {
-      const int c = col_of(i, lane);
-#pragma unroll
-      for (int j = 0; j < 7; ++j)
-        if (f[j] != 0.f) atomicAdd(&s_w[c * 7 + j], d[i] * f[j]);
-    }
+    __syncthreads();
   }
-  __syncthreads();
-  flush(dpos_w, s_w, kH * 7);
-  flush(dpos_b, s_b, kH);
-  flush(dpos_g, s_g, kH);
-  flush(dpos_bb, s_bb, kH);
-  flush(dstep_emb, s_step, kStepCache * kH);
+  cta_reduce_add(red, warp, lane, ag, dpos_g);
+  cta_reduce_add(red, warp, lane, ab, dpos_bb);
+  cta_reduce_add(red, warp, lane, abias, dpos_b);
+  cta_reduce_add(red, warp, lane, astep0, dstep_emb);  // row 0 of the step-embedding table
+  if (dpos_w) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 7; ++j) atomicAdd(dpos_w + (threadIdx.x + 256 * c) * 7 + j, aw[c][j]);
+  }
 }
 
 int node_pack_bwd(const float* dx, const int64_t* step_ids, const float* pos_fts, const float* pos_lin,
                   const float* stats, const float* pos_g, int rows, float* dstep_emb, float* dpos_w, float* dpos_b,
                   float* dpos_g, float* dpos_bb, cudaStream_t stream) {
   if (rows <= 0) return ETP_OK;
-  const size_t smem = (kH * 10 + kStepCache * kH) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    ETP_CHECK_CUDA(cudaFuncSetAttribute(node_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  int grid = grid_for(rows);
+  int grid = (rows + 7) / 8;
   if (grid > num_sms()) grid = num_sms();
-  ETP_CHECK_CUDA(launch_pdl(node_pack_bwd_kernel, dim3(grid), dim3(256), smem, stream, dx, step_ids, pos_fts, pos_lin, stats, pos_g, rows, dstep_emb, dpos_w,
+  ETP_CHECK_CUDA(launch_pdl(node_pack_bwd_kernel, dim3(grid), dim3(256), 0, stream, dx, step_ids, pos_fts, pos_lin, stats, pos_g, rows, dstep_emb, dpos_w,
                                                     dpos_b, dpos_g, dpos_bb));
   ETP_LAUNCHED();
   return ETP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Backward of the view-token packing (4 LayerNorms, nav-type / token-type embeddings, the K=4 location Linear).
+// Only B*V rows (<= a few thousand): one warp per row and every parameter gradient goes straight to global memory
+// with 128-bit vector reductions (512 B per warp instruction) — no shared-memory accumulation, no CTA reduction.
 __global__ void __launch_bounds__(256) pano_pack_bwd_kernel(const PanoPackBwdArgs a) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
-  extern __shared__ float sm[];
-  // [0] out_g [1] out_b [2] img_g [3] img_b [4] dep_g [5] dep_b [6] loc_g [7] loc_b [8] loc_bias [9] tok [10,11] nav [12..15] loc_w
-  zero_smem(sm, 16 * kH);
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float og[24];
   ld24(a.out_g, lane, og);
@@ -228,10 +245,10 @@ __global__ void __launch_bounds__(256) pano_pack_bwd_kernel(const PanoPackBwdArg
     ld24(a.dx + static_cast<size_t>(row) * kH, lane, d);
     ld24(a.sum_pre + static_cast<size_t>(row) * kH, lane, x);
     ln_bwd_row(d, x, st[6], st[7], og, dgm, dbt);   // d = dsum
-    sacc(sm + 0 * kH, lane, dgm);
-    sacc(sm + 1 * kH, lane, dbt);
-    sacc(sm + 9 * kH, lane, d);
-    sacc(sm + (10 + static_cast<int>(a.nav_types[row])) * kH, lane, d);
+    gred24(a.dout_g, lane, dgm);
+    gred24(a.dout_b, lane, dbt);
+    gred24(a.dtok_emb1, lane, d);
+    if (a.dnav_emb) gred24(a.dnav_emb + static_cast<int>(a.nav_types[row]) * kH, lane, d);
     float t[24];
     // img branch
 #pragma unroll
@@ -239,8 +256,8 @@ __global__ void __launch_bounds__(256) pano_pack_bwd_kernel(const PanoPackBwdArg
     ld24(a.rgb_lin + static_cast<size_t>(row) * kH, lane, x);
     ld24(a.img_g, lane, g);
     ln_bwd_row(t, x, st[0], st[1], g, dgm, dbt);
-    sacc(sm + 2 * kH, lane, dgm);
-    sacc(sm + 3 * kH, lane, dbt);
+    gred24(a.dimg_g, lane, dgm);
+    gred24(a.dimg_b, lane, dbt);
     st24_bf16(a.drgb_lin + static_cast<size_t>(row) * kH, lane, t);
     if (a.dep_lin) {
 #pragma unroll
@@ -248,45 +265,33 @@ __global__ void __launch_bounds__(256) pano_pack_bwd_kernel(const PanoPackBwdArg
       ld24(a.dep_lin + static_cast<size_t>(row) * kH, lane, x);
       ld24(a.dep_g, lane, g);
       ln_bwd_row(t, x, st[2], st[3], g, dgm, dbt);
-      sacc(sm + 4 * kH, lane, dgm);
-      sacc(sm + 5 * kH, lane, dbt);
+      gred24(a.ddep_g, lane, dgm);
+      gred24(a.ddep_b, lane, dbt);
       st24_bf16(a.ddep_lin + static_cast<size_t>(row) * kH, lane, t);
     }
     ld24(a.loc_lin + static_cast<size_t>(row) * kH, lane, x);
     ld24(a.loc_g, lane, g);
     ln_bwd_row(d, x, st[4], st[5], g, dgm, dbt);   // d = dloc_lin
-    sacc(sm + 6 * kH, lane, dgm);
-    sacc(sm + 7 * kH, lane, dbt);
-    sacc(sm + 8 * kH, lane, d);
-    const float4 f = *reinterpret_cast<const float4*>(a.loc_fts + static_cast<size_t>(row) * 4);
+    gred24(a.dloc_g, lane, dgm);
+    gred24(a.dloc_b, lane, dbt);
+    gred24(a.dloc_bias, lane, d);
+    if (a.dloc_w) {
+      // dW[c, 0..3] += d[c] * loc_fts[row, 0..3]: the 4 columns a lane holds per float4 group are 16 consecutive floats
+      const float4 f = *reinterpret_cast<const float4*>(a.loc_fts + static_cast<size_t>(row) * 4);
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
-      float* w = sm + 12 * kH + col_of(i, lane) * 4;
-      atomicAdd(w + 0, d[i] * f.x); atomicAdd(w + 1, d[i] * f.y); atomicAdd(w + 2, d[i] * f.z); atomicAdd(w + 3, d[i] * f.w);
+      for (int i = 0; i < 24; ++i)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.dloc_w + col_of(i, lane) * 4), "f"(d[i] * f.x),
+                     "f"(d[i] * f.y), "f"(d[i] * f.z), "f"(d[i] * f.w)
+                     : "memory");
     }
   }
-  __syncthreads();
-  flush(a.dout_g, sm + 0 * kH, kH); flush(a.dout_b, sm + 1 * kH, kH);
-  flush(a.dimg_g, sm + 2 * kH, kH); flush(a.dimg_b, sm + 3 * kH, kH);
-  flush(a.ddep_g, sm + 4 * kH, kH); flush(a.ddep_b, sm + 5 * kH, kH);
-  flush(a.dloc_g, sm + 6 * kH, kH); flush(a.dloc_b, sm + 7 * kH, kH);
-  flush(a.dloc_bias, sm + 8 * kH, kH); flush(a.dtok_emb1, sm + 9 * kH, kH);
-  flush(a.dnav_emb, sm + 10 * kH, 2 * kH);
-  flush(a.dloc_w, sm + 12 * kH, 4 * kH);
 }
 
 int pano_pack_bwd(const PanoPackBwdArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return ETP_OK;
   ETP_REQUIRE(a.dx && a.rgb_lin && a.loc_lin && a.sum_pre && a.stats && a.drgb_lin, "pano_pack_bwd: null argument");
-  const size_t smem = 16 * kH * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    ETP_CHECK_CUDA(cudaFuncSetAttribute(pano_pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  int grid = grid_for(a.rows);
-  if (grid > num_sms()) grid = num_sms();
-  ETP_CHECK_CUDA(launch_pdl(pano_pack_bwd_kernel, dim3(grid), dim3(256), smem, stream, a));
+  const int grid = (a.rows + 7) / 8;
+  ETP_CHECK_CUDA(launch_pdl(pano_pack_bwd_kernel, dim3(grid), dim3(256), 0, stream, a));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -298,33 +303,28 @@ __global__ void __launch_bounds__(256) embed_txt_bwd_kernel(const float* __restr
                                                              float* dpos, float* dtype0, float* dgamma, float* dbeta) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
-  extern __shared__ float sm[];  // [3][768]: gamma, beta, type0
-  zero_smem(sm, 3 * kH);
-  __syncthreads();
+  __shared__ float red[8][kH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g[24];
   ld24(gamma, lane, g);
+  float ag[24], ab[24], at0[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { ag[i] = 0.f; ab[i] = 0.f; at0[i] = 0.f; }
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     float d[24], x[24], dgm[24], dbt[24];
     ld24(dx + static_cast<size_t>(row) * kH, lane, d);
     ld24(sum_pre + static_cast<size_t>(row) * kH, lane, x);
     ln_bwd_row(d, x, stats[static_cast<size_t>(row) * 2], stats[static_cast<size_t>(row) * 2 + 1], g, dgm, dbt);
-    sacc(sm, lane, dgm);
-    sacc(sm + kH, lane, dbt);
-    sacc(sm + 2 * kH, lane, d);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { ag[i] += dgm[i]; ab[i] += dbt[i]; at0[i] += d[i]; }
     const int64_t id = ids[row];
     const int pos = row % L;
-#pragma unroll
-    for (int i = 0; i < 24; ++i) {
-      const int c = col_of(i, lane);
-      if (dword && id != 0) atomicAdd(dword + id * kH + c, d[i]);  // padding_idx = 0 receives no gradient
-      if (dpos) atomicAdd(dpos + static_cast<size_t>(pos) * kH + c, d[i]);
-    }
+    if (dword && id != 0) gred24(dword + id * kH, lane, d);  // padding_idx = 0 receives no gradient
+    if (dpos) gred24(dpos + static_cast<size_t>(pos) * kH, lane, d);
   }
-  __syncthreads();
-  flush(dgamma, sm, kH);
-  flush(dbeta, sm + kH, kH);
-  flush(dtype0, sm + 2 * kH, kH);
+  cta_reduce_add(red, warp, lane, ag, dgamma);
+  cta_reduce_add(red, warp, lane, ab, dbeta);
+  cta_reduce_add(red, warp, lane, at0, dtype0);
 }
 
 int embed_txt_bwd(const float* dx, const int64_t* ids, const float* sum_pre, const float* stats, const float* gamma,
@@ -332,7 +332,7 @@ int embed_txt_bwd(const float* dx, const int64_t* ids, const float* sum_pre, con
                   cudaStream_t stream) {
   const int rows = B * L;
   if (rows <= 0) return ETP_OK;
-  ETP_CHECK_CUDA(launch_pdl(embed_txt_bwd_kernel, dim3(grid_for(rows)), dim3(256), 3 * kH * sizeof(float), stream, dx, ids, sum_pre, stats, gamma, rows, L,
+  ETP_CHECK_CUDA(launch_pdl(embed_txt_bwd_kernel, dim3(grid_for(rows)), dim3(256), 0, stream, dx, ids, sum_pre, stats, gamma, rows, L,
                                                                                  dword, dpos, dtype0, dgamma, dbeta));
   ETP_LAUNCHED();
   return ETP_OK;

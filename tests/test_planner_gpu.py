@@ -99,3 +99,27 @@ def test_forward_c3_shape_vs_oracle_properties():
     assert torch.isfinite(nav["gmap_embeds"]).all() and torch.isfinite(pano).all()
     assert torch.equal(nav_p["global_logits"], lg[perm]), "batch permutation changed the logits"
     assert torch.equal(nav_p["gmap_embeds"], nav["gmap_embeds"][perm])
+
+
+def test_prefetcher_matches_direct_copy():
+    """HostInputPrefetcher hands out, step after step, exactly the tensors that were submitted (two slots in flight)."""
+    from etpnav_b200.pipeline import HostInputPrefetcher
+    dev = torch.device("cuda", 0)
+    pf = HostInputPrefetcher(dev)
+    g = torch.Generator().manual_seed(3)
+    hosts = [{"a": torch.randn(257, 33, generator=g).pin_memory(), "ids": torch.randint(0, 9, (64, 7), generator=g).pin_memory(),
+              "tag": i} for i in range(5)]
+    pf.submit(hosts[0])
+    for i in range(5):
+        d = pf.get()
+        if i + 1 < 5:
+            pf.submit(hosts[i + 1])
+        # a long-ish kernel on the compute stream so the next copy really overlaps a consumer of this slot
+        acc = d["a"].clone()
+        for _ in range(20):
+            acc = acc * 1.0001 + d["a"]
+        assert d["tag"] == i
+        torch.cuda.synchronize()
+        assert torch.equal(d["a"].cpu(), hosts[i]["a"]) and torch.equal(d["ids"].cpu(), hosts[i]["ids"])
+    with pytest.raises(RuntimeError):
+        pf.get()
