@@ -143,4 +143,9 @@ ETP_API int etp_sap_tail_fwd(const float* relu_out, const float* gamma, const fl
   return sap_tail_fwd(relu_out, gamma, beta, w4, b4, visited, valid, rows, H, logits, mean, rstd, S(stream));
 }
 
+ETP_API int etp_step_loss(const float* logits, const int64_t* labels, int32_t B, int32_t N, int64_t ignore_index,
+                          float grad_scale, float* loss_sum, float* dlogits, float* probs, int64_t* argmax, void* stream) {
+  return step_loss(logits, labels, B, N, ignore_index, grad_scale, loss_sum, dlogits, probs, argmax, S(stream));
+}
+
 }  // extern "C"

@@ -100,6 +100,10 @@ int embed_txt_fwd(const int64_t* ids, const float* word_emb, const float* pos_em
                   float* sum_pre, float* stats, cudaStream_t stream);
 int seq_mask(const int64_t* lens, int B, int V, uint8_t* mask, cudaStream_t stream);  // mask[b,v] = v < lens[b]
 
+// fused caller-side loss of one step (ss_trainer_ETP.py:879-900): see pack.cu:step_loss_kernel
+int step_loss(const float* logits, const int64_t* labels, int B, int N, int64_t ignore_index, float grad_scale,
+              float* loss_sum, float* dlogits, float* probs, int64_t* argmax, cudaStream_t stream);
+
 int sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, const float* w4, const float* b4,
                  const uint8_t* visited, const uint8_t* valid, int rows, int H, float* logits, float* mean,
                  float* rstd, cudaStream_t stream);

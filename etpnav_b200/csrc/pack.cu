@@ -250,4 +250,59 @@ int seq_mask(const int64_t* lens, int B, int V, uint8_t* mask, cudaStream_t stre
   return ETP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Caller-side loss of one step, fused (ss_trainer_ETP.py:879-900): softmax over the node logits (-inf entries are
+// masked nodes), cross-entropy summed over the batch with ignore_index, its gradient w.r.t. the logits, and the
+// greedy action.  One warp per episode row.
+//   loss_sum += sum_b CE(logits[b], labels[b])          (rows with labels[b] == ignore_index contribute nothing)
+//   dlogits[b, n] = grad_scale * (softmax[b, n] - [n == labels[b]])      (0 for ignored rows and -inf entries)
+//   probs[b, n] = softmax[b, n]  (optional; the trainer samples from it),  argmax[b] = first maximal logit
+__global__ void __launch_bounds__(256) step_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int B,
+                                                         int N, int64_t ignore_index, float grad_scale,
+                                                         float* __restrict__ loss_sum, float* __restrict__ dlogits,
+                                                         float* __restrict__ probs, int64_t* __restrict__ argmax) {
+  griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
+  griddep_wait();    // ... and wait for the previous one before touching memory
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* x = logits + static_cast<size_t>(b) * N;
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int n = lane; n < N; n += 32) {
+    const float v = x[n];
+    if (v > mx) { mx = v; arg = n; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  float se = 0.f;
+  for (int n = lane; n < N; n += 32) se += __expf(x[n] - mx);
+  se = warp_sum(se);
+  const float inv = 1.0f / se;
+  const int64_t lab = labels ? labels[b] : ignore_index;
+  const bool live = lab != ignore_index && lab >= 0 && lab < N;
+  for (int n = lane; n < N; n += 32) {
+    const float pr = __expf(x[n] - mx) * inv;
+    if (probs) probs[static_cast<size_t>(b) * N + n] = pr;
+    if (dlogits) dlogits[static_cast<size_t>(b) * N + n] = live ? grad_scale * (pr - (n == lab ? 1.0f : 0.0f)) : 0.0f;
+  }
+  if (lane == 0) {
+    if (argmax) argmax[b] = arg == 0x7fffffff ? 0 : arg;
+    if (live && loss_sum) atomicAdd(loss_sum, -(x[lab] - mx - __logf(se)));
+  }
+}
+
+int step_loss(const float* logits, const int64_t* labels, int B, int N, int64_t ignore_index, float grad_scale,
+              float* loss_sum, float* dlogits, float* probs, int64_t* argmax, cudaStream_t stream) {
+  ETP_REQUIRE(logits != nullptr && B > 0 && N > 0, "step_loss: bad arguments");
+  ETP_CHECK_CUDA(launch_pdl(step_loss_kernel, dim3((B + 7) / 8), dim3(256), 0, stream, logits, labels, B, N, ignore_index,
+                            grad_scale, loss_sum, dlogits, probs, argmax));
+  ETP_LAUNCHED();
+  return ETP_OK;
+}
+
 }  // namespace etp

@@ -213,6 +213,22 @@ def node_pack_fwd(**kw):
     _check(lib().etp_node_pack_fwd(C.byref(a), stream_ptr()), "etp_node_pack_fwd")
 
 
+def step_loss(logits, labels, grad_scale=1.0, ignore_index=-100, want_probs=False):
+    """Fused softmax / CE(sum, ignore_index) / dlogits / argmax over node logits [B, N] (ss_trainer_ETP.py:879-900).
+    Returns (loss_sum [1], dlogits [B,N], argmax [B], probs [B,N] or None)."""
+    B, N = logits.shape
+    lg = logits.detach().float().contiguous()
+    loss = torch.zeros(1, device=lg.device, dtype=torch.float32)
+    dl = torch.empty_like(lg)
+    am = torch.empty(B, device=lg.device, dtype=torch.int64)
+    pr = torch.empty_like(lg) if want_probs else None
+    L = lib()
+    L.etp_step_loss.argtypes = [p_void, p_void, i32, i32, C.c_int64, f32, p_void, p_void, p_void, p_void, p_void]
+    _check(L.etp_step_loss(ptr(lg), ptr(labels.contiguous().long() if labels is not None else None), B, N, ignore_index,
+                           grad_scale, ptr(loss), ptr(dl), ptr(pr), ptr(am), stream_ptr()), "etp_step_loss")
+    return loss, dl, am, pr
+
+
 def sap_tail_fwd(relu_out, gamma, beta, w4, b4, visited, valid, logits, mean=None, rstd=None):
     rows, H = relu_out.shape
     _check(lib().etp_sap_tail_fwd(ptr(relu_out), ptr(gamma), ptr(beta), ptr(w4), ptr(b4), ptr(visited), ptr(valid),

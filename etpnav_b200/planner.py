@@ -626,9 +626,12 @@ class PlannerTrainer:
         nav = m.forward_navigation(d["txt_embeds"], d["txt_masks"], None, d["gmap_step_ids"], img, d["gmap_pos_fts"],
                                    d["gmap_masks"], d["gmap_visited_masks"], d["gmap_pair_dists"])
         logits = nav["global_logits"]
-        loss = torch.nn.functional.cross_entropy(logits, d["labels"], reduction="sum", ignore_index=-100) / logits.shape[0]
-        loss.backward()
-        return logits, loss
+        # caller-side loss (ss_trainer_ETP.py:890-892: CE, sum over the batch, ignore_index=-100; :1055 divides by the
+        # number of actions) fused with its gradient and the greedy action: one kernel instead of torch's softmax /
+        # nll / nan_to_num chain; the gradient enters autograd at the logits
+        loss_sum, dlogits, self.last_action, _ = _L.step_loss(logits, d["labels"], grad_scale=1.0 / logits.shape[0])
+        logits.backward(dlogits)
+        return logits, loss_sum / logits.shape[0]
 
     def optimizer_step(self):
         m = self.m

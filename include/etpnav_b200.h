@@ -163,6 +163,12 @@ int etp_sap_tail_fwd(const float* relu_out, const float* gamma, const float* bet
                      const uint8_t* visited, const uint8_t* valid, int32_t rows, int32_t H, float* logits,
                      float* mean, float* rstd, void* stream);
 
+/* Caller-side loss of one step, fused: softmax / cross-entropy(sum, ignore_index) / its gradient / greedy action
+ * over the node logits (ss_trainer_ETP.py:879-900: F.softmax, F.cross_entropy(reduction='sum', ignore_index=-100),
+ * argmax).  loss_sum (device scalar) is ADDED to; dlogits = grad_scale * d(sum CE)/d logits; probs, argmax optional. */
+int etp_step_loss(const float* logits, const int64_t* labels, int32_t B, int32_t N, int64_t ignore_index,
+                  float grad_scale, float* loss_sum, float* dlogits, float* probs, int64_t* argmax, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * step level: one call = one reference method
  * ------------------------------------------------------------------------------------------- */

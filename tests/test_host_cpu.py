@@ -88,3 +88,57 @@ def test_flop_model_matches_survey():
     assert abs(f["txt"] / 1e9 - 1701.5) < 2.0
     f1 = step_flops(PlannerConfig(), 2, 12, 16, 80)
     assert abs(f1["step_fwd"] / 1e9 - 4.40) < 0.05
+
+
+def test_checkpoint_interop_finetune_and_pretrain_layouts():
+    """N4: the key layouts of the reference's checkpoints load unchanged.
+    (1) fine-tune ``ckpt.iter*.pth``: ``{"state_dict": policy.state_dict()}`` with keys ``net.vln_bert.<name>``
+        (``net.module.vln_bert.<name>`` when saved from DDP, ss_trainer_ETP.py:74-83,223-236) — loaded by the PARENT
+        module's ``load_state_dict``, so only our key set has to equal the reference's;
+    (2) pre-train ``model_step_*.pt``: ``bert.<name>`` for the backbone, the SAP head un-prefixed, plus heads we do not
+        own (vlnbert_init.py:20-30 prefixes the head, HF strips ``bert.``) — loaded through ``remap_checkpoint_keys``."""
+    import torch.nn as nn
+    from etpnav_b200.planner import B200Planner, remap_checkpoint_keys
+    cfg = PlannerConfig(vocab_size=256, num_l_layers=1, num_x_layers=2)
+    src = make_weights(cfg, seed=5)
+
+    class Net(nn.Module):       # stands in for ETP(Net) (Policy_ViewSelection_ETP.py:78-92)
+        def __init__(self):
+            super().__init__()
+            self.vln_bert = B200Planner(cfg, device="cpu")
+
+    class Policy(nn.Module):    # stands in for PolicyViewSelectionETP: policy.net
+        def __init__(self):
+            super().__init__()
+            self.net = Net()
+
+    pol = Policy()
+    ckpt = {"state_dict": {"net.vln_bert." + k: v.clone() for k, v in src.items()}, "iteration": 7}
+    missing, unexpected = pol.load_state_dict(ckpt["state_dict"], strict=True)
+    assert not missing and not unexpected
+    for k, v in src.items():
+        assert torch.equal(pol.net.vln_bert.state_dict()[k], v), k
+    # saving gives back the reference's key layout
+    assert sorted(pol.state_dict().keys()) == sorted("net.vln_bert." + k for k in src)
+
+    # DDP-saved variant and the pre-training layout go through the remap
+    m = B200Planner(cfg, device="cpu")
+    ddp = {"net.module.vln_bert." + k: v for k, v in src.items()}
+    out = remap_checkpoint_keys(ddp, m.state_dict().keys())
+    assert sorted(out) == sorted(src)
+    pre = {}
+    for k, v in src.items():
+        pre[(k if k.startswith("global_sap_head") else "bert." + k)] = v
+    pre["mlm_head.predictions.bias"] = torch.zeros(3)           # heads the planner does not own are ignored
+    pre["module.sap_fuse_linear.weight"] = torch.zeros(1, 3)
+    ref_style = {}
+    for k, v in pre.items():                                     # vlnbert_init.py:24-30, restated
+        if k.startswith("module"):
+            ref_style[k[7:]] = v
+        ref_style[("bert." + k) if "sap_head" in k else k] = v
+    out = remap_checkpoint_keys(ref_style, m.state_dict().keys())
+    assert sorted(out) == sorted(src)
+    res = m.load_state_dict(out, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in src.items():
+        assert torch.equal(m.state_dict()[k], v), k

@@ -248,3 +248,25 @@ def test_attention_bwd(L, impl, B, Sq, Sk, mode):
     if pair is not None:
         assert abs(dw.item() - pw.grad.item()) < 2e-2 * max(1.0, abs(pw.grad.item())), (dw.item(), pw.grad.item())
         assert abs(db.item()) < 0.05 * max(1.0, abs(pw.grad.item()))
+
+
+def test_step_loss(L):
+    """Fused softmax / CE(sum, ignore_index) / gradient / argmax vs torch (ss_trainer_ETP.py:879-900)."""
+    g = _gen(77)
+    B, N = 37, 83
+    logits = _rand((B, N), g, 3.0)
+    dead = torch.rand(B, N, generator=g, device="cuda") < 0.3
+    dead[:, 0] = False
+    logits = logits.masked_fill(dead, float("-inf"))
+    labels = torch.randint(0, N, (B,), generator=g, device="cuda")
+    labels = torch.where(dead[torch.arange(B, device="cuda"), labels], torch.zeros_like(labels), labels)
+    labels[3] = -100
+    labels[11] = -100
+    ref_in = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, labels, reduction="sum", ignore_index=-100)
+    (ref / B).backward()
+    loss, dl, am, pr = L.step_loss(logits, labels, grad_scale=1.0 / B, want_probs=True)
+    assert abs(loss.item() - ref.item()) < 1e-3 * max(1.0, abs(ref.item()))
+    assert (dl - torch.nan_to_num(ref_in.grad, nan=0.0)).abs().max() < 1e-6
+    assert torch.equal(am, logits.argmax(1))
+    assert (pr - torch.softmax(logits, 1)).abs().max() < 1e-6
