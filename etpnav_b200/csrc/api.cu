@@ -38,6 +38,11 @@ ETP_API int etp_prof_report(char* buf, size_t cap) {
 /* developer hook (not part of the ported interface): CTA-0 timeline of the next tcgen05 attention-backward launches */
 ETP_API void etp_debug_attention_bwd_timeline(void* dev_buf_128_u64) { attention_bwd_tc_set_debug(dev_buf_128_u64); }
 
+ETP_API int etp_dropout_mask(const etp_dropout* d, float p, uint32_t site, int64_t n, uint8_t* out, void* stream) {
+  ETP_REQUIRE(d != nullptr, "etp_dropout_mask: null argument");
+  return dropout_mask(make_drop_host(d->seed, p, site), n, out, S(stream));
+}
+
 ETP_API int etp_check_device(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(ETP_ERR_NO_DEVICE, "no CUDA device");
@@ -62,6 +67,7 @@ ETP_API int etp_gemm(const etp_gemm_args* g, void* stream) {
   a.out_pre = static_cast<bf16*>(g->out_pre); a.ld_pre = g->ld_pre;
   a.k_splits = g->k_splits < 1 ? 1 : g->k_splits; a.block_n = g->block_n;
   a.colsum = g->colsum; a.pre_mode = g->pre_mode;
+  a.drop_key = g->drop_key; a.drop_thr = g->drop_thr; a.drop_scale = g->drop_scale;
   return gemm(a, S(stream));
 }
 

@@ -91,6 +91,14 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnArgs a, in
       sum += e;
     }
     sum = warp_sum(sum);
+    if (a.drop_thr) {  // dropout on the normalised probabilities: the row sum above stays that of the undropped row
+      const Drop dr{a.drop_key, a.drop_thr, a.drop_scale};
+      const uint32_t e0 = static_cast<uint32_t>((static_cast<size_t>(b) * a.heads + h) * a.Sq + q) * static_cast<uint32_t>(Sk);
+      for (int t = 0; t < nk; ++t) {
+        const int j = t * 32 + lane;
+        if (j < Sk) myp[j] *= drop_mul(dr, e0 + j);
+      }
+    }
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
     for (int j = 0; j < Sk; ++j) {

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const AttnBwdArgs a, i
         float pv = 0.f;
         if (pair) { pv = pair[j]; s += pw * pv + pb; }
         const float p = __expf(s - lse);
-        const float dp = dot64(mydo, Vs + j * kStr);
+        float dp = dot64(mydo, Vs + j * kStr);  // d(dropped P); back through the dropout mask
+        if (a.drop_thr) dp *= drop_mul(Drop{a.drop_key, a.drop_thr, a.drop_scale}, static_cast<uint32_t>(((static_cast<size_t>(b) * a.heads + h) * a.Sq + q) * Sk + j));
         ds = p * (dp - Dv);
         wsum += ds * pv;
         bsum += ds;
@@ -166,8 +167,13 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const AttnBwdArgs a, 
         float s = dot64(myk, Qs + i * kStr) + kbias;
         if (a.pair) s += pw * a.pair[(static_cast<size_t>(b) * Sq + i) * Sk + j] + pb;
         p = __expf(s - lses[i]);
-        const float dp = dot64(myv, dOs + i * kStr);
-        ds = p * (dp - Ds[i]);
+        float dp = dot64(myv, dOs + i * kStr);
+        float mk = 1.0f;
+        if (a.drop_thr)
+          mk = drop_mul(Drop{a.drop_key, a.drop_thr, a.drop_scale},
+                        static_cast<uint32_t>(((static_cast<size_t>(b) * a.heads + h) * Sq + i) * Sk + j));
+        ds = p * (dp * mk - Ds[i]);
+        p *= mk;  // dV = (dropped P)^T . dO
       }
       myp[i] = p;
       myds[i] = ds;

@@ -52,6 +52,7 @@ struct BwdDev {
   bf16 *dq, *dk, *dv;
   int lddq, lddk, lddv;
   float *dpair_w, *dpair_b;
+  Drop drop;  // the forward's attention-probability dropout (thr 0 = off)
   unsigned long long* dbg;  // optional timeline of CTA 0 (globaltimer ns): [0,64) control thread, [64,128) math thread 0
 };
 
@@ -299,6 +300,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.heads, h = item % p.heads;
       const float* pair_row = kPair ? p.pair + (static_cast<size_t>(b) * p.Sq + r) * p.Sk : nullptr;
+      const uint32_t e_row = static_cast<uint32_t>(((static_cast<size_t>(b) * p.heads + h) * p.Sq + r) * p.Sk);
       float nlse2 = -INFINITY, Ds = 0.f;  // -lse (log2 domain): -inf kills padding rows
       {
         float part = 0.f;
@@ -345,9 +347,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 float sc = fmaf(__uint_as_float(vs[i + t]), sl2, kbv[t]);
                 if constexpr (kPair) sc = fmaf(pw2, pv[i + t], sc);
                 const float pr = ex2_approx(sc + nlse2);                            // P (0 on padding rows)
-                const float dss = pr * fmaf(__uint_as_float(vd[i + t]), p.scale, -Ds);  // dS * scale
+                float mk = 1.0f;  // forward dropout multiplier of this probability (0 or 1/(1-p))
+                if (p.drop.thr) mk = drop_mul(p.drop, e_row + static_cast<uint32_t>(k0 + c + i + t));
+                // dP = mask * d(dropped P);  dS = P * (dP - D)  (x scale);  dV uses the dropped P
+                const float dss = pr * fmaf(__uint_as_float(vd[i + t]) * mk, p.scale, -Ds);
                 if constexpr (kPair) { wsum = fmaf(dss, pv[i + t], wsum); bsum += dss; }
-                pe[i + t] = pr;
+                pe[i + t] = pr * mk;
                 de[i + t] = dss;
               }
             }
@@ -485,6 +490,7 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream) {
   d.pair_b_dev = a.pair_b_dev; d.out = a.out; d.ldo = a.ldo; d.dout = a.dout; d.lddo = a.lddo; d.lse = a.lse;
   d.dq = a.dq; d.dk = a.dk; d.dv = a.dv; d.lddq = a.lddq; d.lddk = a.lddk; d.lddv = a.lddv;
   d.dpair_w = a.dpair_w; d.dpair_b = a.dpair_b;
+  d.drop = Drop{a.drop_key, a.drop_thr, a.drop_scale};
   d.dbg = g_attn_bwd_dbg;
   const int items = a.B * a.heads;
   const int grid = items < num_sms() ? items : num_sms();

@@ -47,6 +47,7 @@ struct AttnDev {
   const float* pair_w_dev;
   const float* pair_b_dev;
   float* lse;
+  Drop drop;  // attention-probability dropout (thr 0 = off)
 };
 
 ETP_DEVICE float ex2_approx(float x) {
@@ -289,6 +290,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           sc[i] = ex2_approx(sc[i] - m_use);
           lsum += sc[i];
         }
+        if (p.drop.thr) {
+          // dropout acts on the normalised probabilities; the row sum keeps the undropped values, the P that
+          // multiplies V carries mask / (1 - p)
+          const uint32_t e0 = static_cast<uint32_t>(((static_cast<size_t>(b) * p.heads + h) * p.Sq + q) * p.Sk + k0 + wq * 32);
+          if ((p.Sk & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float m0, m1;
+              drop_mul2(p.drop, e0 + i, m0, m1);
+              sc[i] *= m0; sc[i + 1] *= m1;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sc[i] *= drop_mul(p.drop, e0 + i);
+          }
+        }
         {
           // 32 keys = 4 chunks of 16 B inside the 64-key panel (wq >> 1)
           uint8_t* prow = sP + (wq >> 1) * 16384 + r * 128;
@@ -374,6 +391,8 @@ int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream) {
   d.B = a.B; d.heads = a.heads; d.Sq = a.Sq; d.Sk = a.Sk; d.scale = a.scale; d.key_valid = a.key_valid;
   d.mask_value = a.mask_value; d.pair = a.pair; d.pair_w = a.pair_w; d.pair_b = a.pair_b;
   d.pair_w_dev = a.pair_w_dev; d.pair_b_dev = a.pair_b_dev; d.lse = a.lse;
+  d.drop = Drop{a.drop_key, a.drop_thr, a.drop_scale};
+  ETP_REQUIRE(!a.drop_thr || static_cast<int64_t>(a.B) * a.heads * a.Sq * a.Sk < (int64_t(1) << 32), "attention: dropout index range");
   const int items = a.B * a.heads * ((a.Sq + kBQ - 1) / kBQ);
   const int grid = items < num_sms() ? items : num_sms();
   if (a.pair)

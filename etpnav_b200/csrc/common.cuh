@@ -278,6 +278,51 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 }
 
 // ----------------------------------------------------------------------------------------------
+// dropout (train() mode).  A keep flag is a pure function of (key, element index): key = hash(seed, site) is made on
+// the host, the element index is the position in the logical tensor the reference's nn.Dropout sees (row-major).
+// One 32-bit hash (lowbias32) serves two neighbouring elements (16 bits each), thr = round(p * 65536), keep iff
+// bits >= thr; kept values are scaled by 1/(1-p).  The backward regenerates the same flags: nothing is stored.
+// ----------------------------------------------------------------------------------------------
+struct Drop {
+  uint32_t key;
+  uint32_t thr;   // 0 = dropout off
+  float scale;    // 1 / (1 - p)
+};
+ETP_DEVICE uint32_t drop_bits(uint32_t pair, uint32_t key) {
+  uint32_t x = pair * 0x9E3779B1u + key;
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+// multiplier (0 or scale) of element e
+ETP_DEVICE float drop_mul(const Drop& d, uint32_t e) {
+  const uint32_t b = drop_bits(e >> 1, d.key);
+  const uint32_t v = (e & 1u) ? (b >> 16) : (b & 0xffffu);
+  return v >= d.thr ? d.scale : 0.0f;
+}
+// multipliers of the aligned pair (e, e + 1), e even
+ETP_DEVICE void drop_mul2(const Drop& d, uint32_t e, float& m0, float& m1) {
+  const uint32_t b = drop_bits(e >> 1, d.key);
+  m0 = (b & 0xffffu) >= d.thr ? d.scale : 0.0f;
+  m1 = (b >> 16) >= d.thr ? d.scale : 0.0f;
+}
+
+// a lane's 24 values of a 768-wide row (float4 groups (i*32+lane)*4, the row-per-warp kernels' layout) times their
+// dropout multipliers; element index = row * 768 + column
+ETP_DEVICE void drop_row24(const Drop& d, int row, int lane, float (&v)[24]) {
+  if (d.thr == 0) return;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const uint32_t e = static_cast<uint32_t>(row) * 768u + static_cast<uint32_t>((i * 32 + lane) * 4);
+    float m0, m1, m2, m3;
+    drop_mul2(d, e, m0, m1);
+    drop_mul2(d, e + 2, m2, m3);
+    v[4 * i] *= m0; v[4 * i + 1] *= m1; v[4 * i + 2] *= m2; v[4 * i + 3] *= m3;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // small math helpers
 // ----------------------------------------------------------------------------------------------
 ETP_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

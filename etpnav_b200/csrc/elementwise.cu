@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                              const float* __restrict__ rstd, int rows, float* __restrict__ dx_f32,
                                                              int accumulate_dx, bf16* __restrict__ dx_bf16,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                             float* __restrict__ dxsum) {
+                                                             float* __restrict__ dxsum, const Drop drop) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
   __shared__ float red[8][kH];
@@ -119,6 +119,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       for (int i = 0; i < 24; ++i) d[i] += prev[i];
     }
     store_row(o, lane, d);
+    if (drop.thr) {
+      // the Linear whose output this LayerNorm normalised went through dropout before the residual add: ITS output
+      // gradient (the bf16 copy the dgrad / wgrad GEMMs read, and the bias gradient) carries the mask; the fp32
+      // dx written above is the residual branch and does not
+      drop_row24(drop, row, lane, d);
+    }
     if (dx_bf16) store_row_bf16(dx_bf16 + static_cast<size_t>(row) * kH, lane, d);
 #pragma unroll
     for (int i = 0; i < 24; ++i) ds[i] += d[i];
@@ -167,13 +173,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
 int layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int rows,
                   int H, float* dx_f32, int accumulate_dx, bf16* dx_bf16, float* dgamma, float* dbeta,
-                  cudaStream_t stream, float* dxsum) {
+                  cudaStream_t stream, float* dxsum, DropHost drop) {
   ETP_REQUIRE(H == kH, "layernorm: hidden size must be 768");
   if (rows <= 0) return ETP_OK;
   int grid = (rows + 7) / 8;
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
   ETP_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(grid), dim3(256), 0, stream, dy, x, gamma, mean, rstd, rows, dx_f32, accumulate_dx, dx_bf16, dgamma,
-                                                 dbeta, dxsum));
+                                                 dbeta, dxsum, Drop{drop.key, drop.thr, drop.scale}));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -281,6 +287,19 @@ int add_f32(float* dst, const float* src, int64_t n, cudaStream_t stream) {
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   ETP_CHECK_CUDA(launch_pdl(add_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, dst, src, n));
+  ETP_LAUNCHED();
+  return ETP_OK;
+}
+
+// keep flags of elements [0, n) of one dropout site, exactly as the fused kernels evaluate them (test utility)
+__global__ void dropout_mask_kernel(const Drop d, int64_t n, uint8_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (d.thr == 0 || drop_mul(d, static_cast<uint32_t>(i)) != 0.0f) ? 1 : 0;
+}
+int dropout_mask(DropHost d, int64_t n, uint8_t* out, cudaStream_t stream) {
+  ETP_REQUIRE(out != nullptr && n >= 0 && n < (int64_t(1) << 32), "dropout_mask: bad arguments");
+  if (n == 0) return ETP_OK;
+  dropout_mask_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(Drop{d.key, d.thr, d.scale}, n, out);
   ETP_LAUNCHED();
   return ETP_OK;
 }

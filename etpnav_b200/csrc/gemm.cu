@@ -327,8 +327,14 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
               float c0, e0, c1, e1;
               phi_parts(v[2 * k], c0, e0);
               phi_parts(v[2 * k + 1], c1, e1);
-              const float d0 = fmaf(v[2 * k] * 0.39894228040143267794f, e0, c0);
-              const float d1 = fmaf(v[2 * k + 1] * 0.39894228040143267794f, e1, c1);
+              float d0 = fmaf(v[2 * k] * 0.39894228040143267794f, e0, c0);
+              float d1 = fmaf(v[2 * k + 1] * 0.39894228040143267794f, e1, c1);
+              if (e.drop_thr) {  // d/dpre of dropout(gelu(pre)) = mask/(1-p) * gelu'(pre)
+                float m0, m1;
+                drop_mul2(Drop{e.drop_key, e.drop_thr, e.drop_scale},
+                          static_cast<uint32_t>(row0 + k) * static_cast<uint32_t>(e.N) + static_cast<uint32_t>(col), m0, m1);
+                d0 *= m0; d1 *= m1;
+              }
               if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * e.ld_pre) = pack_bf16x2(d0, d1);
               v[2 * k] *= c0;
               v[2 * k + 1] *= c1;
@@ -358,6 +364,16 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
             for (int k = 0; k < 16; ++k) {
               v[2 * k] *= __uint_as_float(ax[k] << 16);
               v[2 * k + 1] *= __uint_as_float(ax[k] & 0xffff0000u);
+            }
+          }
+          if (e.drop_thr) {
+            const Drop dr{e.drop_key, e.drop_thr, e.drop_scale};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              float m0, m1;
+              drop_mul2(dr, static_cast<uint32_t>(row0 + k) * static_cast<uint32_t>(e.N) + static_cast<uint32_t>(col), m0, m1);
+              v[2 * k] *= m0;
+              v[2 * k + 1] *= m1;
             }
           }
           if (e.resid) {
@@ -534,6 +550,9 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   d.resid = a.resid; d.ld_resid = a.ld_resid; d.out_f32 = a.out_f32; d.ld_f32 = a.ld_f32; d.atomic = a.atomic;
   d.out_bf16 = a.out_bf16; d.ld_bf16 = a.ld_bf16; d.out_pre = a.out_pre; d.ld_pre = a.ld_pre; d.pre_mode = a.pre_mode;
   d.colsum = a.colsum;
+  d.drop_key = a.drop_key; d.drop_thr = a.drop_thr; d.drop_scale = a.drop_scale;
+  ETP_REQUIRE(!a.drop_thr || (a.k_splits == 1 && !a.atomic && static_cast<int64_t>(a.M) * a.N < (int64_t(1) << 32)),
+              "gemm: dropout needs whole-K tiles and < 2^32 elements");
   d.k_splits = a.k_splits;
   // tile-N: 256-wide pair tiles unless N is small / not a multiple of 256, or they would leave most pairs idle
   int bn = a.block_n;

@@ -23,7 +23,9 @@ struct GemmDev {
   __nv_bfloat16* out_pre;  // pre-activation copy (bf16), for the GELU backward
   int ld_pre;
   int pre_mode;   // 0: out_pre = pre-activation; 1: out_pre = gelu'(pre-activation)
-  float* colsum;  // fp32 [N] += column sums of the final value (CTA-pair kernel only)
+  float* colsum;  // fp32 [N] += column sums of the final value
+  uint32_t drop_key, drop_thr;  // dropout of the activated value before the residual add (thr 0 = off)
+  float drop_scale;
 };
 
 }  // namespace etp

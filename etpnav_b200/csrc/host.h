@@ -75,4 +75,23 @@ int get_tmap_3d(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t
 
 int num_sms();
 
+// host side of the dropout scheme (common.cuh: Drop): key of a site from the call's seed (splitmix64), threshold and
+// scale from the probability.  p <= 0 gives thr = 0 (off).
+struct DropHost { uint32_t key, thr; float scale; };
+inline DropHost make_drop_host(uint64_t seed, float p, uint32_t site) {
+  DropHost d{0u, 0u, 1.0f};
+  if (!(p > 0.0f)) return d;
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(site) + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  d.key = static_cast<uint32_t>(z);
+  double t = static_cast<double>(p) * 65536.0 + 0.5;
+  if (t > 65535.0) t = 65535.0;
+  d.thr = static_cast<uint32_t>(t);
+  if (d.thr == 0) d.thr = 1;
+  d.scale = 1.0f / (1.0f - p);
+  return d;
+}
+
 }  // namespace etp

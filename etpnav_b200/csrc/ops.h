@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "host.h"
+
 namespace etp {
 
 typedef __nv_bfloat16 bf16;
@@ -35,6 +37,10 @@ struct GemmArgs {
   int k_splits = 1;
   int block_n = 0;  // 0 = auto, else 128 or 256
   float* colsum = nullptr;  // fp32 [N]: += column sums of the final value (bias gradient of the producing Linear)
+  // dropout applied to the activated value (and to the saved derivative) BEFORE the residual add: nn.Dropout after a
+  // dense layer (BertSelfOutput / BertOutput, vilmodel_cmt.py:150-154,189-193; transformer.py:176-181).  thr 0 = off.
+  uint32_t drop_key = 0, drop_thr = 0;
+  float drop_scale = 1.0f;
 };
 int gemm(const GemmArgs& a, cudaStream_t stream);
 // n <= 8 weight-gradient problems (a_mn = b_mn = 1, out_f32 += A^T.B, nothing else) in one persistent launch
@@ -51,11 +57,12 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
 // gradient of the Linear feeding this LayerNorm, fused here instead of a separate column-sum pass.
 int layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int rows,
                   int H, float* dx_f32, int accumulate_dx, bf16* dx_bf16, float* dgamma, float* dbeta,
-                  cudaStream_t stream, float* dxsum = nullptr);
+                  cudaStream_t stream, float* dxsum = nullptr, DropHost drop = DropHost{0u, 0u, 1.0f});
 // out[c] += sum_r x[r, c]   (bias gradients)
 int colsum_bf16(const bf16* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
 int colsum_f32(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
 int cast_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream);
+int dropout_mask(DropHost d, int64_t n, uint8_t* out, cudaStream_t stream);  // keep flags of one site (tests)
 int add_f32(float* dst, const float* src, int64_t n, cudaStream_t stream);  // dst += src
 
 // ---- token packing (pack.cu) ----------------------------------------------------------------------
@@ -75,6 +82,7 @@ struct PanoPackArgs {
   float* loc_lin = nullptr;  // [rows,768]
   float* sum_pre = nullptr;  // [rows,768] value before the final layer_norm
   float* stats = nullptr;    // [rows,8]: mean/rstd of img, dep, loc, out LayerNorms
+  DropHost drop{0u, 0u, 1.0f};  // dropout after the final LayerNorm (vilmodel_cmt.py:710-711), train mode
 };
 int pano_pack_fwd(const PanoPackArgs& a, cudaStream_t stream);
 
@@ -97,7 +105,7 @@ int node_pack_fwd(const NodePackArgs& a, cudaStream_t stream);
 // word + position + token-type-0 embedding gather and LayerNorm (BertEmbeddings.forward, vilmodel_cmt.py:62-77)
 int embed_txt_fwd(const int64_t* ids, const float* word_emb, const float* pos_emb, const float* type_emb0,
                   const float* gamma, const float* beta, float eps, int B, int L, float* x_f32, bf16* x_bf16,
-                  float* sum_pre, float* stats, cudaStream_t stream);
+                  float* sum_pre, float* stats, cudaStream_t stream, DropHost drop = DropHost{0u, 0u, 1.0f});
 int seq_mask(const int64_t* lens, int B, int V, uint8_t* mask, cudaStream_t stream);  // mask[b,v] = v < lens[b]
 
 // fused caller-side loss of one step (ss_trainer_ETP.py:879-900): see pack.cu:step_loss_kernel
@@ -106,7 +114,7 @@ int step_loss(const float* logits, const int64_t* labels, int B, int N, int64_t 
 
 int sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, const float* w4, const float* b4,
                  const uint8_t* visited, const uint8_t* valid, int rows, int H, float* logits, float* mean,
-                 float* rstd, cudaStream_t stream);
+                 float* rstd, cudaStream_t stream, DropHost drop = DropHost{0u, 0u, 1.0f});
 
 // ---- attention (attention.cu) ---------------------------------------------------------------------
 struct AttnArgs {
@@ -127,6 +135,9 @@ struct AttnArgs {
   bf16* out = nullptr;  // [B, Sq, ldo]
   int ldo = 0;
   float* lse = nullptr;  // [B, heads, Sq] log-sum-exp of the biased scores (saved for backward), may be null
+  // dropout of the attention probabilities (train mode; thr 0 = off): element index ((b*heads+h)*Sq+q)*Sk+k
+  uint32_t drop_key = 0, drop_thr = 0;
+  float drop_scale = 1.0f;
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t stream);
 
@@ -151,6 +162,8 @@ struct AttnBwdArgs {
   int lddq = 0, lddk = 0, lddv = 0;
   float* dpair_w = nullptr;  // += sum dS * pair   (sprel_linear.weight grad), device scalar or null
   float* dpair_b = nullptr;  // += sum dS          (sprel_linear.bias grad)
+  uint32_t drop_key = 0, drop_thr = 0;  // the forward's attention-probability dropout (same key)
+  float drop_scale = 1.0f;
 };
 int attention_bwd(const AttnBwdArgs& a, cudaStream_t stream);      // CUDA-core, any shape
 int attention_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t stream);
@@ -160,7 +173,8 @@ int attention_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t stream);
 // [rows,768] (ReLU mask applied), accumulates dgamma/dbeta [768], dw4 [768], db4 [1].
 int sap_tail_bwd(const float* dlogits, const float* relu_out, const float* gamma, const float* beta, const float* w4,
                  const float* mean, const float* rstd, const uint8_t* visited, const uint8_t* valid, int rows,
-                 bf16* dpre_bf16, float* dgamma, float* dbeta, float* dw4, float* db4, cudaStream_t stream);
+                 bf16* dpre_bf16, float* dgamma, float* dbeta, float* dw4, float* db4, cudaStream_t stream,
+                 DropHost drop = DropHost{0u, 0u, 1.0f});
 // node packing backward: dx [rows,768] -> dstep_emb (scatter-add), LN/Linear7 grads. d(img_fts) == dx.
 int node_pack_bwd(const float* dx, const int64_t* step_ids, const float* pos_fts, const float* pos_lin,
                   const float* stats, const float* pos_g, int rows, float* dstep_emb, float* dpos_w, float* dpos_b,
@@ -177,12 +191,13 @@ struct PanoPackBwdArgs {
         *dout_g = nullptr, *dout_b = nullptr;
   float *dloc_w = nullptr, *dloc_bias = nullptr;  // [768,4], [768]
   float *dnav_emb = nullptr, *dtok_emb1 = nullptr;
+  DropHost drop{0u, 0u, 1.0f};  // the forward's dropout after the final LayerNorm
 };
 int pano_pack_bwd(const PanoPackBwdArgs& a, cudaStream_t stream);
 // embedding + LN backward of forward_txt: dx [rows,768] -> scatter-add into word / position / type-0 tables
 int embed_txt_bwd(const float* dx, const int64_t* ids, const float* sum_pre, const float* stats, const float* gamma,
                   int B, int L, float* dword, float* dpos, float* dtype0, float* dgamma, float* dbeta,
-                  cudaStream_t stream);
+                  cudaStream_t stream, DropHost drop = DropHost{0u, 0u, 1.0f});
 
 // ---- optimizer (adamw.cu) ----------------------------------------------------------------------------
 // torch.optim.AdamW semantics (decoupled weight decay, bias correction) over flat fp32 buffers; also refreshes

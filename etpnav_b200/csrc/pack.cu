@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) pano_pack_kernel(const PanoPackArgs a) {
 #pragma unroll
   for (int i = 0; i < 24; ++i) v[i] = 0.f;
   ln_accum(acc, a.out_g, a.out_b, lane, 1e-12f, v, st[6], st[7]);
+  drop_row24(Drop{a.drop.key, a.drop.thr, a.drop.scale}, row, lane, v);  // nn.Dropout after layer_norm (train mode)
   st24(a.x_f32 + static_cast<size_t>(row) * kH, lane, v);
   if (a.stats && lane < 8) {
     float s = st[0];
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) sap_tail_kernel(const float* __restrict__
                                                         const float* __restrict__ b4, const uint8_t* __restrict__ visited,
                                                         const uint8_t* __restrict__ valid, int rows,
                                                         float* __restrict__ logits, float* __restrict__ mean_out,
-                                                        float* __restrict__ rstd_out) {
+                                                        float* __restrict__ rstd_out, const Drop drop) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
   const int lane = threadIdx.x & 31;
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(256) sap_tail_kernel(const float* __restrict__
   ld24(relu_out + static_cast<size_t>(row) * kH, lane, v);
   float mean, rstd;
   ln_accum(v, gamma, beta, lane, 1e-12f, h, mean, rstd);
+  drop_row24(drop, row, lane, h);  // NextActionPrediction's Dropout between LayerNorm and the last Linear
   ld24(w4, lane, w);
   float s = 0.f;
 #pragma unroll
@@ -185,11 +187,11 @@ __global__ void __launch_bounds__(256) sap_tail_kernel(const float* __restrict__
 
 int sap_tail_fwd(const float* relu_out, const float* gamma, const float* beta, const float* w4, const float* b4,
                  const uint8_t* visited, const uint8_t* valid, int rows, int H, float* logits, float* mean,
-                 float* rstd, cudaStream_t stream) {
+                 float* rstd, cudaStream_t stream, DropHost drop) {
   ETP_REQUIRE(H == kH, "sap_tail: hidden size must be 768");
   if (rows <= 0) return ETP_OK;
   ETP_CHECK_CUDA(launch_pdl(sap_tail_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, relu_out, gamma, beta, w4, b4, visited, valid, rows, logits, mean,
-                                                      rstd));
+                                                      rstd, Drop{drop.key, drop.thr, drop.scale}));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(256) embed_txt_kernel(const int64_t* __restric
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          float eps, int rows, int L, float* __restrict__ x_f32,
                                                          bf16* __restrict__ x_bf16, float* __restrict__ sum_pre,
-                                                         float* __restrict__ stats) {
+                                                         float* __restrict__ stats, const Drop drop) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
   const int lane = threadIdx.x & 31;
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(256) embed_txt_kernel(const int64_t* __restric
   if (sum_pre) st24(sum_pre + static_cast<size_t>(row) * kH, lane, w);
   float mean, rstd;
   ln_accum(w, gamma, beta, lane, eps, v, mean, rstd);
+  drop_row24(drop, row, lane, v);  // BertEmbeddings.dropout (train mode)
   st24(x_f32 + static_cast<size_t>(row) * kH, lane, v);
   if (x_bf16) st24_bf16(x_bf16 + static_cast<size_t>(row) * kH, lane, v);
   if (stats && lane == 0) {
@@ -228,11 +231,11 @@ __global__ void __launch_bounds__(256) embed_txt_kernel(const int64_t* __restric
 
 int embed_txt_fwd(const int64_t* ids, const float* word_emb, const float* pos_emb, const float* type_emb0,
                   const float* gamma, const float* beta, float eps, int B, int L, float* x_f32, bf16* x_bf16,
-                  float* sum_pre, float* stats, cudaStream_t stream) {
+                  float* sum_pre, float* stats, cudaStream_t stream, DropHost drop) {
   const int rows = B * L;
   if (rows <= 0) return ETP_OK;
   ETP_CHECK_CUDA(launch_pdl(embed_txt_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, ids, word_emb, pos_emb, type_emb0, gamma, beta, eps, rows, L,
-                                                       x_f32, x_bf16, sum_pre, stats));
+                                                       x_f32, x_bf16, sum_pre, stats, Drop{drop.key, drop.thr, drop.scale}));
   ETP_LAUNCHED();
   return ETP_OK;
 }

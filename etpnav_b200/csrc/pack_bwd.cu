@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) sap_tail_bwd_kernel(const float* __restri
                                                             const float* __restrict__ w4, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const uint8_t* __restrict__ visited,
                                                             const uint8_t* __restrict__ valid, int rows, bf16* __restrict__ dpre,
-                                                            float* dgamma, float* dbeta, float* dw4, float* db4) {
+                                                            float* dgamma, float* dbeta, float* dw4, float* db4, const Drop drop) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
   __shared__ float red[8][kH];
@@ -103,11 +103,15 @@ __global__ void __launch_bounds__(256) sap_tail_bwd_kernel(const float* __restri
     float r[24], dh[24], x[24], dgm[24], dbt[24];
     ld24(relu_out + static_cast<size_t>(row) * kH, lane, r);
     const float mu = mean[row], rs = rstd[row];
+    float hm[24];  // the forward's dropout multipliers of this row (all 1 when off)
+#pragma unroll
+    for (int i = 0; i < 24; ++i) hm[i] = 1.0f;
+    drop_row24(drop, row, lane, hm);
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
       x[i] = r[i];
-      dh[i] = dl * w[i];
-      aw[i] = fmaf(dl, (r[i] - mu) * rs * g[i] + bt[i], aw[i]);
+      dh[i] = dl * w[i] * hm[i];
+      aw[i] = fmaf(dl, ((r[i] - mu) * rs * g[i] + bt[i]) * hm[i], aw[i]);
     }
     ln_bwd_row(dh, x, mu, rs, g, dgm, dbt);
 #pragma unroll
@@ -127,10 +131,11 @@ __global__ void __launch_bounds__(256) sap_tail_bwd_kernel(const float* __restri
 
 int sap_tail_bwd(const float* dlogits, const float* relu_out, const float* gamma, const float* beta, const float* w4,
                  const float* mean, const float* rstd, const uint8_t* visited, const uint8_t* valid, int rows,
-                 bf16* dpre_bf16, float* dgamma, float* dbeta, float* dw4, float* db4, cudaStream_t stream) {
+                 bf16* dpre_bf16, float* dgamma, float* dbeta, float* dw4, float* db4, cudaStream_t stream, DropHost drop) {
   if (rows <= 0) return ETP_OK;
   ETP_CHECK_CUDA(launch_pdl(sap_tail_bwd_kernel, dim3(grid_for(rows)), dim3(256), 0, stream, 
-      dlogits, relu_out, gamma, beta, w4, mean, rstd, visited, valid, rows, dpre_bf16, dgamma, dbeta, dw4, db4));
+      dlogits, relu_out, gamma, beta, w4, mean, rstd, visited, valid, rows, dpre_bf16, dgamma, dbeta, dw4, db4,
+      Drop{drop.key, drop.thr, drop.scale}));
   ETP_LAUNCHED();
   return ETP_OK;
 }
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(256) pano_pack_bwd_kernel(const PanoPackBwdArg
     const float* st = a.stats + static_cast<size_t>(row) * 8;
     float d[24], x[24], dgm[24], dbt[24], g[24];
     ld24(a.dx + static_cast<size_t>(row) * kH, lane, d);
+    drop_row24(Drop{a.drop.key, a.drop.thr, a.drop.scale}, row, lane, d);  // back through the forward's dropout
     ld24(a.sum_pre + static_cast<size_t>(row) * kH, lane, x);
     ln_bwd_row(d, x, st[6], st[7], og, dgm, dbt);   // d = dsum
     gred24(a.dout_g, lane, dgm);
@@ -300,7 +306,8 @@ int pano_pack_bwd(const PanoPackBwdArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) embed_txt_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ ids,
                                                              const float* __restrict__ sum_pre, const float* __restrict__ stats,
                                                              const float* __restrict__ gamma, int rows, int L, float* dword,
-                                                             float* dpos, float* dtype0, float* dgamma, float* dbeta) {
+                                                             float* dpos, float* dtype0, float* dgamma, float* dbeta,
+                                                             const Drop drop) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
   __shared__ float red[8][kH];
@@ -313,6 +320,7 @@ __global__ void __launch_bounds__(256) embed_txt_bwd_kernel(const float* __restr
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     float d[24], x[24], dgm[24], dbt[24];
     ld24(dx + static_cast<size_t>(row) * kH, lane, d);
+    drop_row24(drop, row, lane, d);  // back through the forward's dropout
     ld24(sum_pre + static_cast<size_t>(row) * kH, lane, x);
     ln_bwd_row(d, x, stats[static_cast<size_t>(row) * 2], stats[static_cast<size_t>(row) * 2 + 1], g, dgm, dbt);
 #pragma unroll
@@ -329,11 +337,12 @@ __global__ void __launch_bounds__(256) embed_txt_bwd_kernel(const float* __restr
 
 int embed_txt_bwd(const float* dx, const int64_t* ids, const float* sum_pre, const float* stats, const float* gamma,
                   int B, int L, float* dword, float* dpos, float* dtype0, float* dgamma, float* dbeta,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, DropHost drop) {
   const int rows = B * L;
   if (rows <= 0) return ETP_OK;
   ETP_CHECK_CUDA(launch_pdl(embed_txt_bwd_kernel, dim3(grid_for(rows)), dim3(256), 0, stream, dx, ids, sum_pre, stats, gamma, rows, L,
-                                                                                 dword, dpos, dtype0, dgamma, dbeta));
+                                                                                 dword, dpos, dtype0, dgamma, dbeta,
+                                                                                 Drop{drop.key, drop.thr, drop.scale}));
   ETP_LAUNCHED();
   return ETP_OK;
 }

@@ -107,7 +107,7 @@ void TxtRecord::carve(Arena& ar, int B, int L, int NL, bool training) {
 // ---------------------------------------------------------------------------------------------------
 // out = A[rows,K] . W[N,K]^T + bias  with the usual epilogue options
 static int linear(const bf16* A, int rows, int K, const void* W, int N, const float* bias, int act, const float* resid,
-                  float* out_f32, bf16* out_bf16, bf16* out_dact, cudaStream_t s) {
+                  float* out_f32, bf16* out_bf16, bf16* out_dact, cudaStream_t s, DropHost drop = DropHost{0u, 0u, 1.0f}) {
   GemmArgs g;
   g.M = rows; g.N = N; g.K = K;
   g.A = A; g.lda = K;
@@ -117,6 +117,7 @@ static int linear(const bf16* A, int rows, int K, const void* W, int N, const fl
   g.out_f32 = out_f32; g.ld_f32 = N;
   g.out_bf16 = out_bf16; g.ld_bf16 = N;
   g.out_pre = out_dact; g.ld_pre = N; g.pre_mode = out_dact ? 1 : 0;  // saved for backward: gelu'(pre-activation)
+  g.drop_key = drop.key; g.drop_thr = drop.thr; g.drop_scale = drop.scale;
   return gemm(g, s);
 }
 
@@ -130,7 +131,8 @@ static int linear(const bf16* A, int rows, int K, const void* W, int N, const fl
 // vilmodel_cmt.py:156-193): in = (a_f32, a_bf16) -> out x (fp32 into x_out, bf16 into rec.xb)
 static int self_ffn_block(const etp_layer_weights& w, float eps, LayerRecord& rec, const float* a_f32, const bf16* a_bf16,
                           int B, int S, const uint8_t* key_valid, const float* pair, const float* pair_w,
-                          const float* pair_b, float* c_f32, float* x_out, bool training, cudaStream_t s) {
+                          const float* pair_b, float* c_f32, float* x_out, bool training, cudaStream_t s,
+                          const DropCtx& dc, uint32_t site_base, int layer) {
   const int rows = B * S;
   ETP_TRY(linear(a_bf16, rows, kH, w.sqkv_w, 3 * kH, w.sqkv_b, 0, nullptr, nullptr, rec.qkv, nullptr, s));
   AttnArgs at;
@@ -141,11 +143,17 @@ static int self_ffn_block(const etp_layer_weights& w, float eps, LayerRecord& re
   at.scale = 0.125f; at.key_valid = key_valid; at.mask_value = -10000.0f;
   at.pair = pair; at.pair_w_dev = pair_w; at.pair_b_dev = pair_b;
   at.out = rec.ctx2; at.ldo = kH; at.lse = rec.lse2;
+  {
+    const DropHost d = dc.attn(drop_site(site_base, layer, kDropSAttn));
+    at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
+  }
   ETP_TRY(attention_dispatch(at, s));
-  ETP_TRY(linear(rec.ctx2, rows, kH, w.so_w, kH, w.so_b, 0, a_f32, rec.t2, nullptr, nullptr, s));
+  ETP_TRY(linear(rec.ctx2, rows, kH, w.so_w, kH, w.so_b, 0, a_f32, rec.t2, nullptr, nullptr, s,
+                 dc.hidden(drop_site(site_base, layer, kDropSOut))));
   ETP_TRY(layernorm_fwd(rec.t2, w.sln_g, w.sln_b, eps, rows, kH, c_f32, rec.cb, rec.st2, rec.st2 + rows, s));
   ETP_TRY(linear(rec.cb, rows, kH, w.f1_w, kI, w.f1_b, 1, nullptr, nullptr, rec.h, training ? rec.pre : nullptr, s));
-  ETP_TRY(linear(rec.h, rows, kI, w.f2_w, kH, w.f2_b, 0, c_f32, rec.t3, nullptr, nullptr, s));
+  ETP_TRY(linear(rec.h, rows, kI, w.f2_w, kH, w.f2_b, 0, c_f32, rec.t3, nullptr, nullptr, s,
+                 dc.hidden(drop_site(site_base, layer, kDropFfnOut))));
   ETP_TRY(layernorm_fwd(rec.t3, w.fln_g, w.fln_b, eps, rows, kH, x_out, rec.xb, rec.st3, rec.st3 + rows, s));
   return ETP_OK;
 }
@@ -160,6 +168,8 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
   rec.carve(ar, B, N, L, X, training);
   ETP_REQUIRE(ar.off <= saved_bytes, "forward_navigation: saved buffer too small");
   const int rows = B * N;
+  DropCtx dc;
+  if (in.dropout) { dc.seed = in.dropout->seed; dc.p_hidden = in.dropout->p_hidden; dc.p_attn = in.dropout->p_attn; dc.p_head = in.dropout->p_head; }
 
   ETP_TRY(cast_f32_to_bf16(in.txt_embeds, rec.txtb, static_cast<int64_t>(B) * L * kH, s));
   NodePackArgs np;
@@ -186,20 +196,25 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
     at.v = r.kv + kH; at.ldv = r.ldkv;
     at.scale = 0.125f; at.key_valid = in.txt_masks; at.mask_value = -10000.0f;
     at.out = r.ctx1; at.ldo = kH; at.lse = r.lse1;
+    {
+      const DropHost d = dc.attn(drop_site(kSiteNav, i, kDropXAttn));
+      at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
+    }
     ETP_TRY(attention_dispatch(at, s));
-    ETP_TRY(linear(r.ctx1, rows, kH, lw.xo_w, kH, lw.xo_b, 0, x_f32, r.t1, nullptr, nullptr, s));
+    ETP_TRY(linear(r.ctx1, rows, kH, lw.xo_w, kH, lw.xo_b, 0, x_f32, r.t1, nullptr, nullptr, s,
+                   dc.hidden(drop_site(kSiteNav, i, kDropXOut))));
     ETP_TRY(layernorm_fwd(r.t1, lw.xln_g, lw.xln_b, w.ln_eps, rows, kH, rec.xa, r.ab, r.st1, r.st1 + rows, s));
     // graph-aware self-attention + FFN (vilmodel_cmt.py:391-396)
     float* x_out = (i == X - 1) ? gmap_embeds : rec.xf;
     ETP_TRY(self_ffn_block(lw, w.ln_eps, r, rec.xa, r.ab, B, N, in.gmap_masks, w.sprel_w ? in.gmap_pair_dists : nullptr,
-                           w.sprel_w, w.sprel_b, rec.xc, x_out, training, s));
+                           w.sprel_w, w.sprel_b, rec.xc, x_out, training, s, dc, kSiteNav, i));
     x_f32 = x_out;
     x_bf16 = r.xb;
   }
   // SAP head (NextActionPrediction, vilmodel_cmt.py:651-661) + masking (:743-744)
   ETP_TRY(linear(x_bf16, rows, kH, w.sap0_w, kH, w.sap0_b, 2, nullptr, rec.relu, nullptr, nullptr, s));
   ETP_TRY(sap_tail_fwd(rec.relu, w.sap_g, w.sap_bb, w.sap4_w, w.sap4_b, in.gmap_visited_masks, in.gmap_masks, rows, kH,
-                       global_logits, rec.sap_stats, rec.sap_stats + rows, s));
+                       global_logits, rec.sap_stats, rec.sap_stats + rows, s, dc.head(kSiteNav + kSiteHead)));
   return ETP_OK;
 }
 
@@ -212,6 +227,8 @@ int forward_panorama(const etp_pano_weights& w, const etp_pano_inputs& in, float
   rec.carve(ar, B, V, P, training);
   ETP_REQUIRE(ar.off <= saved_bytes, "forward_panorama: saved buffer too small");
   const int rows = B * V;
+  DropCtx dc;
+  if (in.dropout) { dc.seed = in.dropout->seed; dc.p_hidden = in.dropout->p_hidden; dc.p_attn = in.dropout->p_attn; dc.p_head = in.dropout->p_head; }
   ETP_TRY(seq_mask(in.view_lens, B, V, pano_masks, s));
   ETP_TRY(cast_f32_to_bf16(in.rgb_fts, rec.rgbb, static_cast<int64_t>(rows) * 512, s));
   ETP_TRY(linear(rec.rgbb, rows, 512, w.img_w, kH, w.img_b, 0, nullptr, rec.rgb_lin, nullptr, nullptr, s));
@@ -227,6 +244,7 @@ int forward_panorama(const etp_pano_weights& w, const etp_pano_inputs& in, float
   pp.out_g = w.out_g; pp.out_b = w.out_bb; pp.nav_emb = w.nav_emb; pp.tok_emb1 = w.tok_emb1;
   pp.x_f32 = x; pp.loc_lin = training ? rec.loc_lin : nullptr; pp.sum_pre = training ? rec.sum_pre : nullptr;
   pp.stats = rec.stats;
+  pp.drop = dc.hidden(kSitePano + kSiteEmbed);
   ETP_TRY(pano_pack_fwd(pp, s));
   // pre-norm encoder layers (TransformerEncoderLayer.forward_pre, common/transformer.py:170-182)
   for (int i = 0; i < P; ++i) {
@@ -241,11 +259,19 @@ int forward_panorama(const etp_pano_weights& w, const etp_pano_inputs& in, float
     at.q = r.qkv; at.ldq = 3 * kH; at.k = r.qkv + kH; at.ldk = 3 * kH; at.v = r.qkv + 2 * kH; at.ldv = 3 * kH;
     at.scale = 0.125f; at.key_valid = pano_masks; at.mask_value = -INFINITY;
     at.out = r.ctx; at.ldo = kH; at.lse = r.lse;
+    {
+      const DropHost d = dc.hidden(drop_site(kSitePano, i, kDropPAttn));  // MHA dropout = hidden_dropout_prob (common/ops.py:15)
+      at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
+    }
     ETP_TRY(attention_fwd(at, s));  // <= 16 views: CUDA-core kernel
-    ETP_TRY(linear(r.ctx, rows, kH, lw.out_w, kH, lw.out_b, 0, x, x_mid, nullptr, nullptr, s));
+    ETP_TRY(linear(r.ctx, rows, kH, lw.out_w, kH, lw.out_b, 0, x, x_mid, nullptr, nullptr, s,
+                   dc.hidden(drop_site(kSitePano, i, kDropPOut))));
     ETP_TRY(layernorm_fwd(x_mid, lw.n2_g, lw.n2_b, w.layer_eps, rows, kH, nullptr, r.y2b, r.st2, r.st2 + rows, s));
-    ETP_TRY(linear(r.y2b, rows, kH, lw.l1_w, kI, lw.l1_b, 1, nullptr, nullptr, r.h, training ? r.pre : nullptr, s));
-    ETP_TRY(linear(r.h, rows, kI, lw.l2_w, kH, lw.l2_b, 0, x_mid, x_out, nullptr, nullptr, s));
+    // dropout(gelu(.)) inside the FFN (transformer.py:180): the saved derivative carries the same mask
+    ETP_TRY(linear(r.y2b, rows, kH, lw.l1_w, kI, lw.l1_b, 1, nullptr, nullptr, r.h, training ? r.pre : nullptr, s,
+                   dc.hidden(drop_site(kSitePano, i, kDropPFfn))));
+    ETP_TRY(linear(r.h, rows, kI, lw.l2_w, kH, lw.l2_b, 0, x_mid, x_out, nullptr, nullptr, s,
+                   dc.hidden(drop_site(kSitePano, i, kDropPFfnOut))));
     x = x_out;
   }
   if (P > 0)
@@ -254,7 +280,9 @@ int forward_panorama(const etp_pano_weights& w, const etp_pano_inputs& in, float
 }
 
 int forward_txt(const etp_txt_weights& w, const int64_t* txt_ids, const uint8_t* txt_masks, int B, int L,
-                float* txt_embeds, void* saved, size_t saved_bytes, bool training, cudaStream_t s) {
+                float* txt_embeds, void* saved, size_t saved_bytes, bool training, cudaStream_t s, const etp_dropout* dropout) {
+  DropCtx dc;
+  if (dropout) { dc.seed = dropout->seed; dc.p_hidden = dropout->p_hidden; dc.p_attn = dropout->p_attn; dc.p_head = dropout->p_head; }
   const int NL = w.num_l_layers;
   ETP_REQUIRE(B > 0 && L > 0 && NL >= 0, "forward_txt: bad shape");
   ETP_REQUIRE(L <= 1024, "forward_txt: at most 1024 tokens");
@@ -264,14 +292,14 @@ int forward_txt(const etp_txt_weights& w, const int64_t* txt_ids, const uint8_t*
   ETP_REQUIRE(ar.off <= saved_bytes, "forward_txt: saved buffer too small");
   float* x = NL > 0 ? rec.xa : txt_embeds;
   ETP_TRY(embed_txt_fwd(txt_ids, w.word_emb, w.pos_emb, w.type_emb0, w.emb_g, w.emb_b, w.ln_eps, B, L, x, rec.x0b,
-                        training ? rec.sum_pre : nullptr, rec.emb_stats, s));
+                        training ? rec.sum_pre : nullptr, rec.emb_stats, s, dc.hidden(kSiteTxt + kSiteEmbed)));
   const bf16* xb = rec.x0b;
   for (int i = 0; i < NL; ++i) {
     float* x_out = (i == NL - 1) ? txt_embeds : rec.xa;
     // BertLayer.forward (vilmodel_cmt.py:202-208): self-attention over tokens + FFN.  In-place on xa is safe:
     // the block reads a_f32 only as the residual of the first GEMM, before x_out is written.
     ETP_TRY(self_ffn_block(w.layers[i], w.ln_eps, rec.layers[i], x, xb, B, L, txt_masks, nullptr, nullptr, nullptr,
-                           rec.xc, x_out, training, s));
+                           rec.xc, x_out, training, s, dc, kSiteTxt, i));
     x = x_out;
     xb = rec.layers[i].xb;
   }
@@ -320,9 +348,10 @@ ETP_API int etp_forward_panorama(const etp_pano_weights* w, const etp_pano_input
   return forward_panorama(*w, *in, pano_embeds, pano_masks, saved, saved_bytes, training != 0, S(stream));
 }
 ETP_API int etp_forward_txt(const etp_txt_weights* w, const int64_t* txt_ids, const uint8_t* txt_masks, int32_t B,
-                            int32_t L, float* txt_embeds, void* saved, size_t saved_bytes, int32_t training, void* stream) {
+                            int32_t L, float* txt_embeds, void* saved, size_t saved_bytes, int32_t training, void* stream,
+                            const etp_dropout* dropout) {
   ETP_REQUIRE(w && txt_ids && txt_masks && txt_embeds && saved, "etp_forward_txt: null argument");
-  return forward_txt(*w, txt_ids, txt_masks, B, L, txt_embeds, saved, saved_bytes, training != 0, S(stream));
+  return forward_txt(*w, txt_ids, txt_masks, B, L, txt_embeds, saved, saved_bytes, training != 0, S(stream), dropout);
 }
 
 }  // extern "C"

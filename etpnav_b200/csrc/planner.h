@@ -85,6 +85,25 @@ struct TxtRecord {
   void carve(Arena& ar, int B, int L, int NL, bool training);
 };
 
+// Dropout of one step-level call: seed + probabilities (include/etpnav_b200.h: etp_dropout) -> per-site kernel
+// parameters.  Sites: one id per nn.Dropout instance of the reference; forward and backward use the same ids.
+struct DropCtx {
+  uint64_t seed = 0;
+  float p_hidden = 0.f, p_attn = 0.f, p_head = 0.f;
+  DropHost hidden(uint32_t site) const { return make_drop_host(seed, p_hidden, site); }
+  DropHost attn(uint32_t site) const { return make_drop_host(seed, p_attn, site); }
+  DropHost head(uint32_t site) const { return make_drop_host(seed, p_head, site); }
+};
+// site = base + 16 * layer + k
+constexpr uint32_t kSiteNav = 1000, kSitePano = 2000, kSiteTxt = 3000;
+constexpr uint32_t kSiteEmbed = 900;  // + base: dropout after the packing / embedding LayerNorm
+constexpr uint32_t kSiteHead = 901;   // + kSiteNav: NextActionPrediction
+// post-LN blocks (x-layers, BERT layers): k =
+constexpr uint32_t kDropXAttn = 0, kDropXOut = 1, kDropSAttn = 2, kDropSOut = 3, kDropFfnOut = 4;
+// pre-LN pano layers (common/transformer.py:170-182): k =
+constexpr uint32_t kDropPAttn = 0, kDropPOut = 1, kDropPFfn = 2, kDropPFfnOut = 3;
+inline uint32_t drop_site(uint32_t base, int layer, uint32_t k) { return base + 16u * static_cast<uint32_t>(layer) + k; }
+
 // tcgen05 kernel when the shape allows it, CUDA-core kernel otherwise
 int attention_dispatch(const AttnArgs& a, cudaStream_t stream);
 

@@ -129,12 +129,13 @@ static inline float* F(const void* p) { return static_cast<float*>(const_cast<vo
 static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weights& g, const LayerRecord& rec,
                               const bf16* a_bf16, const float* dx_out, float* da, int B, int S, const uint8_t* key_valid,
                               const float* pair, const float* pair_w, const float* pair_b, float* dpair_w, float* dpair_b,
-                              BwdScratch& sc, WgradBatch& wb, cudaStream_t s) {
+                              BwdScratch& sc, WgradBatch& wb, cudaStream_t s, const DropCtx& dc, uint32_t site_base,
+                              int layer) {
   const int rows = B * S;
   // x = LN(t3)
   // (bias gradients ride along: column sums of dt3 inside the LayerNorm backward, of dpre inside the dgrad epilogue)
   ETP_TRY(layernorm_bwd(dx_out, rec.t3, w.fln_g, rec.st3, rec.st3 + rows, rows, kH, sc.g0, 0, sc.gb3, F(g.fln_g), F(g.fln_b), s,
-                        F(g.f2_b)));
+                        F(g.f2_b), dc.hidden(drop_site(site_base, layer, kDropFfnOut))));
   // t3 = h.W2^T + b2 + c
   ETP_TRY(wb.add(sc.gb3, rows, kH, kH, rec.h, kI, kI, g.f2_w, s));
   ETP_TRY(dgrad(sc.gb3, rows, kH, kH, w.f2_w, kI, nullptr, nullptr, sc.dpre, 3, rec.pre, s, g.f1_b));  // * gelu'(pre), saved by the forward
@@ -143,15 +144,18 @@ static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weight
   ETP_TRY(dgrad(sc.dpre, rows, kI, kI, w.f1_w, kH, sc.g0, sc.g1, nullptr, 0, nullptr, s));  // dc = dpre.W1 + dt3
   // c = LN(t2)
   ETP_TRY(layernorm_bwd(sc.g1, rec.t2, w.sln_g, rec.st2, rec.st2 + rows, rows, kH, sc.g0, 0, sc.gb2, F(g.sln_g), F(g.sln_b), s,
-                        F(g.so_b)));
+                        F(g.so_b), dc.hidden(drop_site(site_base, layer, kDropSOut))));
   // t2 = ctx2.Wo^T + bo + a
   ETP_TRY(wb.add(sc.gb2, rows, kH, kH, rec.ctx2, kH, kH, g.so_w, s));
   // Bias gradients of the fused q|k|v projection, without touching dK / dV:  the context is  P.(x.Wv + b_v)  and the
   // rows of P sum to one, so  d b_v = column sums of dctx  (taken in this dgrad's epilogue);  a key bias shifts all
   // scores of a query row equally, which softmax ignores, so  d b_k = 0  exactly;  only  d b_q = column sums of dQ
   // needs a pass over the attention backward's output.
+  // (with dropout on the attention probabilities the rows of the dropped P no longer sum to one: then d b_v is taken
+  // from dV below, as column sums)
+  const bool pdrop = dc.attn(0).thr != 0;
   ETP_TRY(dgrad(sc.gb2, rows, kH, kH, w.so_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s,
-                g.sqkv_b ? F(g.sqkv_b) + 2 * kH : nullptr));
+                (g.sqkv_b && !pdrop) ? F(g.sqkv_b) + 2 * kH : nullptr));
   // attention
   AttnBwdArgs at;
   at.B = B; at.heads = kHeads; at.Sq = S; at.Sk = S;
@@ -161,9 +165,14 @@ static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weight
   at.pair = pair; at.pair_w_dev = pair_w; at.pair_b_dev = pair_b; at.dpair_w = pair ? dpair_w : nullptr;
   at.dpair_b = pair ? dpair_b : nullptr;
   at.dq = sc.dqkv; at.dk = sc.dqkv + kH; at.dv = sc.dqkv + 2 * kH; at.lddq = at.lddk = at.lddv = 3 * kH;
+  {
+    const DropHost d = dc.attn(drop_site(site_base, layer, kDropSAttn));
+    at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
+  }
   ETP_TRY(attention_bwd_dispatch(at, s));
   // qkv = a.Wqkv^T + b
   ETP_TRY(bias_grad(sc.dqkv, rows, kH, 3 * kH, g.sqkv_b, s));  // query part only (see above)
+  if (pdrop && g.sqkv_b) ETP_TRY(bias_grad(sc.dqkv + 2 * kH, rows, kH, 3 * kH, F(g.sqkv_b) + 2 * kH, s));
   ETP_TRY(wb.add(sc.dqkv, rows, 3 * kH, 3 * kH, a_bf16, kH, kH, g.sqkv_w, s));
   ETP_TRY(dgrad(sc.dqkv, rows, 3 * kH, 3 * kH, w.sqkv_w, kH, sc.g0, da, nullptr, 0, nullptr, s));  // da = dqkv.Wqkv + dt2
   return ETP_OK;
@@ -185,11 +194,14 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
   float* Q = wa.take<float>(static_cast<size_t>(rows) * kH);
   ETP_REQUIRE(wa.off <= work_bytes, "backward_navigation: workspace too small");
   ETP_REQUIRE(d_gmap_embeds || d_logits, "backward_navigation: no incoming gradient");
+  DropCtx dc;
+  if (in.dropout) { dc.seed = in.dropout->seed; dc.p_hidden = in.dropout->p_hidden; dc.p_attn = in.dropout->p_attn; dc.p_head = in.dropout->p_head; }
 
   const bf16* x_last = X > 0 ? rec.layers[X - 1].xb : rec.x0b;
   if (d_logits) {
     ETP_TRY(sap_tail_bwd(d_logits, rec.relu, w.sap_g, w.sap_bb, w.sap4_w, rec.sap_stats, rec.sap_stats + rows,
-                         in.gmap_visited_masks, in.gmap_masks, rows, sc.gb, F(g.sap_g), F(g.sap_bb), F(g.sap4_w), F(g.sap4_b), s));
+                         in.gmap_visited_masks, in.gmap_masks, rows, sc.gb, F(g.sap_g), F(g.sap_bb), F(g.sap4_w), F(g.sap4_b), s,
+                         dc.head(kSiteNav + kSiteHead)));
     ETP_TRY(bias_grad(sc.gb, rows, kH, kH, g.sap0_b, s));
     ETP_TRY(wgrad(sc.gb, rows, kH, kH, x_last, kH, kH, const_cast<void*>(g.sap0_w), s));
     ETP_TRY(dgrad(sc.gb, rows, kH, kH, w.sap0_w, kH, d_gmap_embeds, P, nullptr, 0, nullptr, s));
@@ -205,14 +217,15 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     const bf16* x_in = i > 0 ? rec.layers[i - 1].xb : rec.x0b;
     WgradBatch wb;
     ETP_TRY(self_ffn_block_bwd(lw, lg, r, r.ab, P, Q, B, N, in.gmap_masks, w.sprel_w ? in.gmap_pair_dists : nullptr, w.sprel_w,
-                               w.sprel_b, F(g.sprel_w), F(g.sprel_b), sc, wb, s));
+                               w.sprel_b, F(g.sprel_w), F(g.sprel_b), sc, wb, s, dc, kSiteNav, i));
     // a = LN(t1),  t1 = ctx1.Wo^T + bo + x_in
     ETP_TRY(layernorm_bwd(Q, r.t1, lw.xln_g, r.st1, r.st1 + rows, rows, kH, sc.g0, 0, sc.gb, F(lg.xln_g), F(lg.xln_b), s,
-                          F(lg.xo_b)));
+                          F(lg.xo_b), dc.hidden(drop_site(kSiteNav, i, kDropXOut))));
     ETP_TRY(wb.add(sc.gb, rows, kH, kH, r.ctx1, kH, kH, lg.xo_w, s));
     // d b_v (text value bias of this layer) = column sums of dctx; d b_k = 0 (see self_ffn_block_bwd)
+    const bool pdrop = dc.attn(0).thr != 0;  // dropped P rows do not sum to one: d b_v from dV after the attention backward
     ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.xo_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s,
-                  lg.xkv_b ? F(lg.xkv_b) + kH : nullptr));
+                  (lg.xkv_b && !pdrop) ? F(lg.xkv_b) + kH : nullptr));
     AttnBwdArgs at;
     at.B = B; at.heads = kHeads; at.Sq = N; at.Sk = L;
     at.q = r.q; at.ldq = kH; at.k = r.kv; at.ldk = r.ldkv; at.v = r.kv + kH; at.ldv = r.ldkv;
@@ -220,8 +233,13 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     at.scale = 0.125f; at.key_valid = in.txt_masks; at.mask_value = -10000.0f;
     bf16* dkv_i = sc.dkv + static_cast<size_t>(i) * 2 * kH;  // this layer's slice of [B*L, X*1536]
     at.dq = sc.dq; at.lddq = kH; at.dk = dkv_i; at.lddk = ldkv; at.dv = dkv_i + kH; at.lddv = ldkv;
+    {
+      const DropHost d = dc.attn(drop_site(kSiteNav, i, kDropXAttn));
+      at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
+    }
     ETP_TRY(attention_bwd_dispatch(at, s));
     ETP_TRY(bias_grad(sc.dq, rows, kH, kH, lg.xq_b, s));
+    if (pdrop && lg.xkv_b) ETP_TRY(bias_grad(dkv_i + kH, kv_rows, kH, ldkv, F(lg.xkv_b) + kH, s));
     ETP_TRY(wb.add(sc.dq, rows, kH, kH, x_in, kH, kH, lg.xq_w, s));
     ETP_TRY(dgrad(sc.dq, rows, kH, kH, lw.xq_w, kH, sc.g0, P, nullptr, 0, nullptr, s));  // dx_in = dq.Wq + dt1
     ETP_TRY(wb.flush(s));  // the layer's six weight gradients, one launch
@@ -254,11 +272,14 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
   BwdScratch sc;
   sc.carve(wa, rows, 0, static_cast<size_t>(B) * kHeads * V);
   ETP_REQUIRE(wa.off <= work_bytes, "backward_panorama: workspace too small");
+  DropCtx dc;
+  if (in.dropout) { dc.seed = in.dropout->seed; dc.p_hidden = in.dropout->p_hidden; dc.p_attn = in.dropout->p_attn; dc.p_head = in.dropout->p_head; }
   float* A = sc.g0;
   float* Bf = sc.g1;
   if (Pn > 0) {
     ETP_TRY(layernorm_bwd(d_pano_embeds, rec.xs[2 * Pn], w.fin_g, rec.fin_stats, rec.fin_stats + rows, rows, kH, A, 0, sc.gb,
-                          F(g.fin_g), F(g.fin_b), s, F(g.layers[Pn - 1].l2_b)));  // dx_out of the last layer: its linear2 bias grad
+                          F(g.fin_g), F(g.fin_b), s, F(g.layers[Pn - 1].l2_b),
+                          dc.hidden(drop_site(kSitePano, Pn - 1, kDropPFfnOut))));  // bf16 copy = d linear2 output of the last layer
   } else {
     ETP_CHECK_CUDA(cudaMemcpyAsync(A, d_pano_embeds, static_cast<size_t>(rows) * kH * 4, cudaMemcpyDeviceToDevice, s));
   }
@@ -276,24 +297,31 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
     ETP_TRY(wb.add(sc.dpre, rows, kI, kI, r.y2b, kH, kH, lg.l1_w, s));
     ETP_TRY(dgrad(sc.dpre, rows, kI, kI, lw.l1_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy2
     ETP_TRY(layernorm_bwd(Bf, x_mid, lw.n2_g, r.st2, r.st2 + rows, rows, kH, A, 1, sc.gb2, F(lg.n2_g), F(lg.n2_b), s,
-                          F(lg.out_b)));  // A = dx_mid
+                          F(lg.out_b), dc.hidden(drop_site(kSitePano, i, kDropPOut))));  // A = dx_mid
     // x_mid = x + attn(LN1(x)).Wout^T + bout
     ETP_TRY(wb.add(sc.gb2, rows, kH, kH, r.ctx, kH, kH, lg.out_w, s));
+    const bool pdrop = dc.hidden(0).thr != 0;  // MHA dropout on: d b_v from dV below
     ETP_TRY(dgrad(sc.gb2, rows, kH, kH, lw.out_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s,
-                  lg.in_b ? F(lg.in_b) + 2 * kH : nullptr));  // d b_v of in_proj_bias (q|k|v); d b_k = 0
+                  (lg.in_b && !pdrop) ? F(lg.in_b) + 2 * kH : nullptr));  // d b_v of in_proj_bias (q|k|v); d b_k = 0
     AttnBwdArgs at;
     at.B = B; at.heads = kHeads; at.Sq = V; at.Sk = V;
     at.q = r.qkv; at.k = r.qkv + kH; at.v = r.qkv + 2 * kH; at.ldq = at.ldk = at.ldv = 3 * kH;
     at.out = r.ctx; at.ldo = kH; at.dout = sc.dctx; at.lddo = kH; at.lse = r.lse; at.dvec = sc.dvec;
     at.scale = 0.125f; at.key_valid = pano_masks; at.mask_value = -INFINITY;
     at.dq = sc.dqkv; at.dk = sc.dqkv + kH; at.dv = sc.dqkv + 2 * kH; at.lddq = at.lddk = at.lddv = 3 * kH;
+    {
+      const DropHost d = dc.hidden(drop_site(kSitePano, i, kDropPAttn));  // MHA dropout = hidden_dropout_prob (common/ops.py:15)
+      at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
+    }
     ETP_TRY(attention_bwd(at, s));
     ETP_TRY(bias_grad(sc.dqkv, rows, kH, 3 * kH, lg.in_b, s));  // query part
+    if (pdrop && lg.in_b) ETP_TRY(bias_grad(sc.dqkv + 2 * kH, rows, kH, 3 * kH, F(lg.in_b) + 2 * kH, s));
     ETP_TRY(wb.add(sc.dqkv, rows, 3 * kH, 3 * kH, r.y1b, kH, kH, lg.in_w, s));
     ETP_TRY(dgrad(sc.dqkv, rows, 3 * kH, 3 * kH, lw.in_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy1
     ETP_TRY(wb.flush(s));  // the layer's four weight gradients, one launch (sc.gb is rewritten just below)
     ETP_TRY(layernorm_bwd(Bf, x, lw.n1_g, r.st1, r.st1 + rows, rows, kH, A, 1, sc.gb, F(lg.n1_g), F(lg.n1_b), s,
-                          i > 0 ? F(g.layers[i - 1].l2_b) : nullptr));  // A = dx (= dx_out of layer i-1)
+                          i > 0 ? F(g.layers[i - 1].l2_b) : nullptr,
+                          i > 0 ? dc.hidden(drop_site(kSitePano, i - 1, kDropPFfnOut)) : DropHost{0u, 0u, 1.0f}));  // A = dx (= dx_out of layer i-1)
   }
   PanoPackBwdArgs pb;
   pb.rows = rows; pb.dx = A; pb.rgb_lin = rec.rgb_lin; pb.dep_lin = w.dep_w ? rec.dep_lin : nullptr; pb.loc_lin = rec.loc_lin;
@@ -303,6 +331,7 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
   pb.dimg_g = F(g.img_g); pb.dimg_b = F(g.img_bb); pb.ddep_g = F(g.dep_g); pb.ddep_b = F(g.dep_bb);
   pb.dloc_g = F(g.loc_g); pb.dloc_b = F(g.loc_bb); pb.dout_g = F(g.out_g); pb.dout_b = F(g.out_bb);
   pb.dloc_w = F(g.loc_w); pb.dloc_bias = F(g.loc_b); pb.dnav_emb = F(g.nav_emb); pb.dtok_emb1 = F(g.tok_emb1);
+  pb.drop = dc.hidden(kSitePano + kSiteEmbed);
   ETP_TRY(pano_pack_bwd(pb, s));
   ETP_TRY(bias_grad(sc.dq, rows, kH, kH, g.img_b, s));
   ETP_TRY(wgrad(sc.dq, rows, kH, kH, rec.rgbb, 512, 512, const_cast<void*>(g.img_w), s));
@@ -317,7 +346,9 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
 
 int backward_txt(const etp_txt_weights& w, const etp_txt_weights& g, const int64_t* txt_ids, const uint8_t* txt_masks, int B,
                  int L, const float* d_txt_embeds, void* saved, size_t saved_bytes, void* work, size_t work_bytes,
-                 cudaStream_t s) {
+                 cudaStream_t s, const etp_dropout* dropout) {
+  DropCtx dc;
+  if (dropout) { dc.seed = dropout->seed; dc.p_hidden = dropout->p_hidden; dc.p_attn = dropout->p_attn; dc.p_head = dropout->p_head; }
   const int NL = w.num_l_layers, rows = B * L;
   Arena ar(saved, saved_bytes);
   TxtRecord rec;
@@ -335,12 +366,12 @@ int backward_txt(const etp_txt_weights& w, const etp_txt_weights& g, const int64
     float* da = (dx == P) ? Q : P;
     WgradBatch wb;
     ETP_TRY(self_ffn_block_bwd(w.layers[i], g.layers[i], rec.layers[i], a_bf16, dx, da, B, L, txt_masks, nullptr, nullptr,
-                               nullptr, nullptr, nullptr, sc, wb, s));
+                               nullptr, nullptr, nullptr, sc, wb, s, dc, kSiteTxt, i));
     ETP_TRY(wb.flush(s));
     dx = da;
   }
   ETP_TRY(embed_txt_bwd(dx, txt_ids, rec.sum_pre, rec.emb_stats, w.emb_g, B, L, F(g.word_emb), F(g.pos_emb), F(g.type_emb0),
-                        F(g.emb_g), F(g.emb_b), s));
+                        F(g.emb_g), F(g.emb_b), s, dc.hidden(kSiteTxt + kSiteEmbed)));
   return ETP_OK;
 }
 
@@ -389,9 +420,10 @@ ETP_API int etp_backward_panorama(const etp_pano_weights* w, const etp_pano_weig
 }
 ETP_API int etp_backward_txt(const etp_txt_weights* w, const etp_txt_weights* grads, const int64_t* txt_ids,
                              const uint8_t* txt_masks, int32_t B, int32_t L, const float* d_txt_embeds, void* saved,
-                             size_t saved_bytes, void* work, size_t work_bytes, void* stream) {
+                             size_t saved_bytes, void* work, size_t work_bytes, void* stream, const etp_dropout* dropout) {
   ETP_REQUIRE(w && grads && txt_ids && txt_masks && d_txt_embeds && saved && work, "etp_backward_txt: null argument");
-  return backward_txt(*w, *grads, txt_ids, txt_masks, B, L, d_txt_embeds, saved, saved_bytes, work, work_bytes, S(stream));
+  return backward_txt(*w, *grads, txt_ids, txt_masks, B, L, d_txt_embeds, saved, saved_bytes, work, work_bytes, S(stream),
+                      dropout);
 }
 
 ETP_API int etp_adamw_step(float* param, void* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

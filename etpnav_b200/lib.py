@@ -61,7 +61,8 @@ class GemmArgs(C.Structure):
                 ("aux", p_void), ("ld_aux", i32), ("resid", p_f32), ("ld_resid", i32),
                 ("out_f32", p_f32), ("ld_f32", i32), ("atomic", i32),
                 ("out_bf16", p_void), ("ld_bf16", i32), ("out_pre", p_void), ("ld_pre", i32),
-                ("k_splits", i32), ("block_n", i32), ("colsum", p_f32), ("pre_mode", i32)]
+                ("k_splits", i32), ("block_n", i32), ("colsum", p_f32), ("pre_mode", i32),
+                ("drop_key", C.c_uint32), ("drop_thr", C.c_uint32), ("drop_scale", f32)]
 
 
 class AttnArgs(C.Structure):
@@ -113,7 +114,7 @@ def _declare(L):
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, *, a_mn=False, b_mn=False, alpha=1.0, bias=None, act=0, aux=None, aux_mode=0, resid=None,
          out_f32=None, out_bf16=None, out_pre=None, atomic=False, k_splits=1, block_n=0, M=None, N=None, K=None,
-         colsum=None, pre_mode=0):
+         colsum=None, pre_mode=0, drop=None):
     """D = epilogue(alpha * A @ B^T).  A: [M,K] (or [K,M] if a_mn), B: [N,K] (or [K,N] if b_mn), bf16, last dim contiguous."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     assert A.stride(-1) == 1 and B.stride(-1) == 1
@@ -143,6 +144,9 @@ def gemm(A, B, *, a_mn=False, b_mn=False, alpha=1.0, bias=None, act=0, aux=None,
     g.atomic, g.k_splits, g.block_n = int(atomic), k_splits, block_n
     g.colsum = ptr(colsum)
     g.pre_mode = pre_mode
+    g.drop_scale = 1.0
+    if drop is not None:  # (key, thr, scale) from dropout_site()
+        g.drop_key, g.drop_thr, g.drop_scale = drop
     _check(lib().etp_gemm(C.byref(g), stream_ptr()), "etp_gemm")
 
 

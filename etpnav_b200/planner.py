@@ -40,10 +40,15 @@ class NavWeights(C.Structure):
                               "sap0_w", "sap0_b", "sap_g", "sap_bb", "sap4_w", "sap4_b", "xkv_all_w", "xkv_all_b")]
 
 
+class Dropout(C.Structure):
+    """``etp_dropout``: seed + probabilities of one step-level call (train() mode)."""
+    _fields_ = [("seed", C.c_uint64), ("p_hidden", f32), ("p_attn", f32), ("p_head", f32)]
+
+
 class NavInputs(C.Structure):
     _fields_ = [("B", i32), ("N", i32), ("L", i32)] + [
         (n, p_void) for n in ("txt_embeds", "txt_masks", "gmap_step_ids", "gmap_img_fts", "gmap_pos_fts",
-                              "gmap_masks", "gmap_visited_masks", "gmap_pair_dists")]
+                              "gmap_masks", "gmap_visited_masks", "gmap_pair_dists")] + [("dropout", C.POINTER(Dropout))]
 
 
 class PanoLayerWeights(C.Structure):
@@ -58,7 +63,8 @@ class PanoWeights(C.Structure):
 
 
 class PanoInputs(C.Structure):
-    _fields_ = [("B", i32), ("V", i32)] + [(n, p_void) for n in ("rgb_fts", "dep_fts", "loc_fts", "nav_types", "view_lens")]
+    _fields_ = [("B", i32), ("V", i32)] + [(n, p_void) for n in ("rgb_fts", "dep_fts", "loc_fts", "nav_types", "view_lens")] + [
+        ("dropout", C.POINTER(Dropout))]
 
 
 class TxtWeights(C.Structure):
@@ -85,7 +91,7 @@ def _declare():
     L.etp_forward_panorama.argtypes = [C.POINTER(PanoWeights), C.POINTER(PanoInputs), p_void, p_void, p_void,
                                        C.c_size_t, i32, p_void]
     L.etp_forward_txt.argtypes = [C.POINTER(TxtWeights), p_void, p_void, i32, i32, p_void, p_void, C.c_size_t, i32,
-                                  p_void]
+                                  p_void, C.POINTER(Dropout)]
     for fn in ("etp_nav_bwd_work_bytes",):
         getattr(L, fn).restype = C.c_size_t
         getattr(L, fn).argtypes = [i32] * 4
@@ -97,7 +103,7 @@ def _declare():
     L.etp_backward_panorama.argtypes = [C.POINTER(PanoWeights), C.POINTER(PanoWeights), C.POINTER(PanoInputs), p_void,
                                         p_void, p_void, C.c_size_t, p_void, C.c_size_t, p_void, p_void, p_void]
     L.etp_backward_txt.argtypes = [C.POINTER(TxtWeights), C.POINTER(TxtWeights), p_void, p_void, i32, i32, p_void, p_void,
-                                   C.c_size_t, p_void, C.c_size_t, p_void]
+                                   C.c_size_t, p_void, C.c_size_t, p_void, C.POINTER(Dropout)]
     _declared = True
 
 
@@ -126,6 +132,8 @@ class B200Planner(nn.Module):
         self._grad_structs = {}
         self._direct_grad = None      # PlannerTrainer: flat fp32 gradient buffer the backward accumulates into
         self._anchor = torch.zeros(1, device=dev, requires_grad=True)
+        self._drop_base = None   # dropout seed stream: base (torch.initial_seed() unless set) + call counter
+        self._drop_calls = 0
         if config.fix_lang_embedding:  # vilmodel_cmt.py:675-679
             for n, p in self.named_parameters():
                 if n.startswith("embeddings.") or n.startswith("lang_encoder."):
@@ -356,6 +364,23 @@ class B200Planner(nn.Module):
             self._anchor = torch.zeros(1, device=self._flat.device, requires_grad=True)
         return self._anchor
 
+    # ------------------------------------------------------------------ dropout (train() mode)
+    def set_dropout_seed(self, seed: int):
+        """Restart the dropout seed stream (default: torch.initial_seed()); call k of forward_* uses seed stream[k]."""
+        self._drop_base = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._drop_calls = 0
+
+    def _next_dropout(self):
+        """``etp_dropout`` of the next forward call, or None in eval() mode (or when every probability is 0)."""
+        cfg = self.config
+        if not self.training or max(cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob, cfg.pred_head_dropout_prob) <= 0:
+            return None
+        if self._drop_base is None:
+            self._drop_base = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        seed = (self._drop_base + 0x9E3779B97F4A7C15 * (self._drop_calls + 1)) & 0xFFFFFFFFFFFFFFFF
+        self._drop_calls += 1
+        return Dropout(seed, cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob, cfg.pred_head_dropout_prob)
+
     # ------------------------------------------------------------------ the three reference methods
     @staticmethod
     def _mask_u8(m):
@@ -376,20 +401,22 @@ class B200Planner(nn.Module):
             raise ValueError("sequence longer than max_position_embeddings")
         ids = txt_ids.contiguous().long()
         mk = self._mask_u8(txt_masks)
+        drop = self._next_dropout()
         if self._wants_grad("txt") and self.config.update_lang_bert:
             params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._group_names("txt")]
-            return _TxtFn.apply(self, ids, mk, self._anchor_t(), *params)
-        return _txt_forward(self, ids, mk, 0)[0]
+            return _TxtFn.apply(self, ids, mk, drop, self._anchor_t(), *params)
+        return _txt_forward(self, ids, mk, 0, drop)[0]
 
     def forward_panorama(self, rgb_fts, dep_fts, loc_fts, nav_types, view_lens):
         """vilmodel_cmt.py:690-719 -> (pano_embeds fp32 [B,V,768], pano_masks bool [B,V])."""
         self._refresh_cache()
         nt, vl = nav_types.contiguous().long(), view_lens.contiguous().long()
         loc = _f32c(loc_fts)
+        drop = self._next_dropout()
         if self._wants_grad("pano", rgb_fts, dep_fts):
             params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._pano_param_names()]
-            return _PanoFn.apply(self, rgb_fts, dep_fts, loc, nt, vl, self._anchor_t(), *params)
-        out, masks, _, _ = _pano_forward(self, _f32c(rgb_fts), _f32c(dep_fts), loc, nt, vl, 0)
+            return _PanoFn.apply(self, rgb_fts, dep_fts, loc, nt, vl, drop, self._anchor_t(), *params)
+        out, masks, _, _ = _pano_forward(self, _f32c(rgb_fts), _f32c(dep_fts), loc, nt, vl, 0, drop)
         return out, masks.view(torch.bool)
 
     def _pano_param_names(self):
@@ -403,11 +430,12 @@ class B200Planner(nn.Module):
         self._refresh_cache()
         aux = (self._mask_u8(txt_masks), gmap_step_ids.contiguous().long(), _f32c(gmap_pos_fts),
                self._mask_u8(gmap_masks), self._mask_u8(gmap_visited_masks), _f32c(gmap_pair_dists))
+        drop = self._next_dropout()
         if self._wants_grad("nav", txt_embeds, gmap_img_fts):
             params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._group_names("nav")]
-            embeds, logits = _NavFn.apply(self, txt_embeds, gmap_img_fts, aux, self._anchor_t(), *params)
+            embeds, logits = _NavFn.apply(self, txt_embeds, gmap_img_fts, aux, drop, self._anchor_t(), *params)
         else:
-            embeds, logits, _, _ = _nav_forward(self, _f32c(txt_embeds), _f32c(gmap_img_fts), aux, 0)
+            embeds, logits, _, _ = _nav_forward(self, _f32c(txt_embeds), _f32c(gmap_img_fts), aux, 0, drop)
         return {"gmap_embeds": embeds, "global_logits": logits}
 
     # ------------------------------------------------------------------ training helper
@@ -418,31 +446,37 @@ class B200Planner(nn.Module):
 # ----------------------------------------------------------------------------------------------------
 # raw step calls (no autograd)
 # ----------------------------------------------------------------------------------------------------
-def _txt_forward(m, ids, mk, training):
+def _dptr(drop):
+    return C.byref(drop) if drop is not None else None
+
+
+def _txt_forward(m, ids, mk, training, drop=None):
     B, Lt = ids.shape
     L = _L.lib()
     out = torch.empty(B, Lt, 768, device=ids.device, dtype=torch.float32)
     nbytes = L.etp_txt_saved_bytes(B, Lt, m.config.num_l_layers, training)
     saved = torch.empty(nbytes, dtype=torch.uint8, device=ids.device)
     _L._check(L.etp_forward_txt(C.byref(m._structs["txt"]), _L.ptr(ids), _L.ptr(mk), B, Lt, _L.ptr(out), _L.ptr(saved),
-                                nbytes, training, _L.stream_ptr()), "etp_forward_txt")
+                                nbytes, training, _L.stream_ptr(), _dptr(drop)), "etp_forward_txt")
     return out, saved
 
 
-def _pano_inputs(rgb, dep, loc, nt, vl):
+def _pano_inputs(rgb, dep, loc, nt, vl, drop=None):
     pi = PanoInputs()
+    if drop is not None:
+        pi.dropout = C.pointer(drop)
     pi.B, pi.V = rgb.shape[0], rgb.shape[1]
     pi.rgb_fts, pi.dep_fts, pi.loc_fts = _L.ptr(rgb), _L.ptr(dep), _L.ptr(loc)
     pi.nav_types, pi.view_lens = _L.ptr(nt), _L.ptr(vl)
     return pi
 
 
-def _pano_forward(m, rgb, dep, loc, nt, vl, training):
+def _pano_forward(m, rgb, dep, loc, nt, vl, training, drop=None):
     B, V = rgb.shape[:2]
     L = _L.lib()
     out = torch.empty(B, V, 768, device=rgb.device, dtype=torch.float32)
     masks = torch.empty(B, V, device=rgb.device, dtype=torch.uint8)
-    pi = _pano_inputs(rgb, dep, loc, nt, vl)
+    pi = _pano_inputs(rgb, dep, loc, nt, vl, drop)
     nbytes = L.etp_pano_saved_bytes(B, V, m.config.num_pano_layers, training)
     saved = torch.empty(nbytes, dtype=torch.uint8, device=rgb.device)
     _L._check(L.etp_forward_panorama(C.byref(m._structs["pano"]), C.byref(pi), _L.ptr(out), _L.ptr(masks), _L.ptr(saved),
@@ -450,9 +484,11 @@ def _pano_forward(m, rgb, dep, loc, nt, vl, training):
     return out, masks, saved, pi
 
 
-def _nav_inputs(txt, img, aux):
+def _nav_inputs(txt, img, aux, drop=None):
     tm, ids, pos, gm, vm, pd = aux
     ni = NavInputs()
+    if drop is not None:
+        ni.dropout = C.pointer(drop)
     ni.B, ni.N, ni.L = img.shape[0], img.shape[1], txt.shape[1]
     ni.txt_embeds, ni.txt_masks, ni.gmap_step_ids = _L.ptr(txt), _L.ptr(tm), _L.ptr(ids)
     ni.gmap_img_fts, ni.gmap_pos_fts, ni.gmap_masks = _L.ptr(img), _L.ptr(pos), _L.ptr(gm)
@@ -460,11 +496,11 @@ def _nav_inputs(txt, img, aux):
     return ni
 
 
-def _nav_forward(m, txt, img, aux, training):
+def _nav_forward(m, txt, img, aux, training, drop=None):
     B, N = img.shape[:2]
     Lt = txt.shape[1]
     L = _L.lib()
-    ni = _nav_inputs(txt, img, aux)
+    ni = _nav_inputs(txt, img, aux, drop)
     embeds = torch.empty(B, N, 768, device=img.device, dtype=torch.float32)
     logits = torch.empty(B, N, device=img.device, dtype=torch.float32)
     nbytes = L.etp_nav_saved_bytes(B, N, Lt, m.config.num_x_layers, training)
@@ -485,10 +521,10 @@ def _param_grads(m, names, gbuf, gstart, per_call, nparams):
 
 class _NavFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, m, txt_embeds, gmap_img_fts, aux, anchor, *params):
+    def forward(ctx, m, txt_embeds, gmap_img_fts, aux, drop, anchor, *params):
         txt, img = _f32c(txt_embeds), _f32c(gmap_img_fts)
-        embeds, logits, saved, _ = _nav_forward(m, txt, img, aux, 1)
-        ctx.m, ctx.saved, ctx.keep, ctx.nparams = m, saved, (txt, img, aux), len(params)
+        embeds, logits, saved, _ = _nav_forward(m, txt, img, aux, 1, drop)
+        ctx.m, ctx.saved, ctx.keep, ctx.nparams, ctx.drop = m, saved, (txt, img, aux), len(params), drop
         return embeds, logits
 
     @staticmethod
@@ -499,7 +535,7 @@ class _NavFn(torch.autograd.Function):
         B, N, Lt = img.shape[0], img.shape[1], txt.shape[1]
         gbuf, gstart, per_call = m._grad_target("nav")
         gst = m._grad_structs_for(gbuf, gstart)
-        ni = _nav_inputs(txt, img, aux)
+        ni = _nav_inputs(txt, img, aux, ctx.drop)
         de = _f32c(d_embeds) if d_embeds is not None else None
         dl = _f32c(d_logits) if d_logits is not None else None
         if dl is not None:
@@ -512,15 +548,15 @@ class _NavFn(torch.autograd.Function):
                                             _L.ptr(dl), _L.ptr(ctx.saved), ctx.saved.numel(), _L.ptr(work), wbytes,
                                             _L.ptr(d_txt), _L.ptr(d_img), _L.stream_ptr()), "etp_backward_navigation")
         pg = _param_grads(m, m._group_names("nav"), gbuf, gstart, per_call, ctx.nparams)
-        return (None, d_txt, d_img, None, None, *pg)
+        return (None, d_txt, d_img, None, None, None, *pg)
 
 
 class _PanoFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, m, rgb_fts, dep_fts, loc, nt, vl, anchor, *params):
+    def forward(ctx, m, rgb_fts, dep_fts, loc, nt, vl, drop, anchor, *params):
         rgb, dep = _f32c(rgb_fts), _f32c(dep_fts)
-        out, masks, saved, _ = _pano_forward(m, rgb, dep, loc, nt, vl, 1)
-        ctx.m, ctx.saved, ctx.keep, ctx.nparams = m, saved, (rgb, dep, loc, nt, vl, masks), len(params)
+        out, masks, saved, _ = _pano_forward(m, rgb, dep, loc, nt, vl, 1, drop)
+        ctx.m, ctx.saved, ctx.keep, ctx.nparams, ctx.drop = m, saved, (rgb, dep, loc, nt, vl, masks), len(params), drop
         mb = masks.view(torch.bool)
         ctx.mark_non_differentiable(mb)
         return out, mb
@@ -543,7 +579,7 @@ class _PanoFn(torch.autograd.Function):
             gst = m._grad_structs_for(gbuf, gstart)
             tok = gbuf[ge - gs:]
             gst["pano"].tok_emb1 = C.c_void_p(tok.data_ptr())
-        pi = _pano_inputs(rgb, dep, loc, nt, vl)
+        pi = _pano_inputs(rgb, dep, loc, nt, vl, ctx.drop)
         d_rgb = torch.empty_like(rgb) if ctx.needs_input_grad[1] else None
         d_dep = torch.empty_like(dep) if (ctx.needs_input_grad[2] and m.config.use_depth_embedding) else None
         wbytes = L.etp_pano_bwd_work_bytes(B, V)
@@ -562,14 +598,14 @@ class _PanoFn(torch.autograd.Function):
             pg.append(tt)
         if d_dep is None and ctx.needs_input_grad[2]:
             d_dep = torch.zeros_like(dep)
-        return (None, d_rgb, d_dep, None, None, None, None, *pg)
+        return (None, d_rgb, d_dep, None, None, None, None, None, *pg)
 
 
 class _TxtFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, m, ids, mk, anchor, *params):
-        out, saved = _txt_forward(m, ids, mk, 1)
-        ctx.m, ctx.saved, ctx.keep, ctx.nparams = m, saved, (ids, mk), len(params)
+    def forward(ctx, m, ids, mk, drop, anchor, *params):
+        out, saved = _txt_forward(m, ids, mk, 1, drop)
+        ctx.m, ctx.saved, ctx.keep, ctx.nparams, ctx.drop = m, saved, (ids, mk), len(params), drop
         return out
 
     @staticmethod
@@ -584,9 +620,9 @@ class _TxtFn(torch.autograd.Function):
         work = torch.empty(wbytes, dtype=torch.uint8, device=ids.device)
         _L._check(L.etp_backward_txt(C.byref(m._structs["txt"]), C.byref(gst["txt"]), _L.ptr(ids), _L.ptr(mk), B, Lt,
                                      _L.ptr(_f32c(d_out)), _L.ptr(ctx.saved), ctx.saved.numel(), _L.ptr(work), wbytes,
-                                     _L.stream_ptr()), "etp_backward_txt")
+                                     _L.stream_ptr(), _dptr(ctx.drop)), "etp_backward_txt")
         pg = _param_grads(m, m._group_names("txt"), gbuf, gstart, per_call, ctx.nparams)
-        return (None, None, None, None, *pg)
+        return (None, None, None, None, None, *pg)
 
 
 class PlannerTrainer:

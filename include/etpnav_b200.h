@@ -59,6 +59,7 @@ int etp_prof_report(char* buf, size_t cap);
  * reference path (vilmodel_cmt.py:108-110,326-328,151,178,190,654; common/transformer.py:174-181).
  * a_mn/b_mn = 0: operand stored [rows, K] (K contiguous); 1: stored [K, rows] (rows contiguous).
  * epilogue: x = alpha*acc + bias[n]; out_pre = bf16(x) (or bf16(gelu'(x)) if pre_mode); x = act(x); x *= f(aux); x += resid;
+ *           x = dropout(x) (before the residual; also applied to the saved gelu');
  *           out_f32 (=, or += atomically) x; out_bf16 = bf16(x); colsum[n] += sum_m x (bias gradients). */
 typedef struct {
   int32_t M, N, K;
@@ -77,6 +78,8 @@ typedef struct {
   int32_t block_n;    /* 0 auto, 128, 256 */
   float* colsum;      /* optional fp32 [N]: += column sums of the final value x */
   int32_t pre_mode;   /* 0: out_pre = pre-activation, 1: out_pre = gelu'(pre-activation) (act must be 1) */
+  uint32_t drop_key, drop_thr;  /* dropout of the activated value before the residual add; thr = 0: off (see etp_dropout) */
+  float drop_scale;
 } etp_gemm_args;
 int etp_gemm(const etp_gemm_args* args, void* stream);
 
@@ -173,6 +176,18 @@ int etp_step_loss(const float* logits, const int64_t* labels, int32_t B, int32_t
  * step level: one call = one reference method
  * ------------------------------------------------------------------------------------------- */
 
+/* Dropout of the reference's train() mode (config.hidden_dropout_prob after every dense / embedding LayerNorm,
+ * config.attention_probs_dropout_prob on the attention probabilities, pred_head_dropout_prob in the SAP head;
+ * vilmodel_cmt.py:76,133,153,192,349,656; common/transformer.py:176-181).  A keep flag is a pure function of
+ * (seed, site, element index): pass the SAME struct to the backward call and it regenerates the forward's masks —
+ * nothing is stored.  NULL pointer or p == 0: no dropout (eval()).  Draw a fresh seed for every forward call. */
+typedef struct {
+  uint64_t seed;
+  float p_hidden, p_attn, p_head;
+} etp_dropout;
+/* keep flags (1 / 0) of elements [0, n) of `site` as the kernels compute them (tests build the matching oracle masks) */
+int etp_dropout_mask(const etp_dropout* d, float p, uint32_t site, int64_t n, uint8_t* out, void* stream);
+
 /* One post-LN BERT-style block.  Used three ways:
  *   - GraphLXRTXLayer (vilmodel_cmt.py:365-398): cross-attention (x*) + self-attention (s*) + FFN (f*)
  *   - BertLayer of the language encoder (vilmodel_cmt.py:195-208): x* pointers NULL
@@ -218,6 +233,7 @@ typedef struct {
   const uint8_t* gmap_masks;          /* [B,N] */
   const uint8_t* gmap_visited_masks;  /* [B,N] */
   const float* gmap_pair_dists;       /* [B,N,N] */
+  const etp_dropout* dropout;         /* train() mode dropout, or NULL */
 } etp_nav_inputs;
 
 /* Bytes of the activation record forward_navigation writes (and backward reads) when training != 0;
@@ -258,6 +274,7 @@ typedef struct {
   const float* loc_fts;       /* [B,V,4]   */
   const int64_t* nav_types;   /* [B,V]     */
   const int64_t* view_lens;   /* [B]       */
+  const etp_dropout* dropout; /* train() mode dropout, or NULL */
 } etp_pano_inputs;
 
 size_t etp_pano_saved_bytes(int32_t B, int32_t V, int32_t num_pano_layers, int32_t training);
@@ -279,7 +296,8 @@ size_t etp_txt_saved_bytes(int32_t B, int32_t L, int32_t num_l_layers, int32_t t
 /* GlocalTextPathNavCMT.forward_txt (vilmodel_cmt.py:684-688): txt_ids int64 [B,L], txt_masks uint8 [B,L]
  * -> txt_embeds fp32 [B,L,768]. */
 int etp_forward_txt(const etp_txt_weights* w, const int64_t* txt_ids, const uint8_t* txt_masks, int32_t B, int32_t L,
-                    float* txt_embeds, void* saved, size_t saved_bytes, int32_t training, void* stream);
+                    float* txt_embeds, void* saved, size_t saved_bytes, int32_t training, void* stream,
+                    const etp_dropout* dropout);
 
 /* ---------------------------------------------------------------------------------------------
  * step level, backward (autograd counterparts; the reference gets these from torch autograd via
@@ -302,7 +320,7 @@ int etp_backward_panorama(const etp_pano_weights* w, const etp_pano_weights* gra
                           void* work, size_t work_bytes, float* d_rgb_fts, float* d_dep_fts, void* stream);
 int etp_backward_txt(const etp_txt_weights* w, const etp_txt_weights* grads, const int64_t* txt_ids,
                      const uint8_t* txt_masks, int32_t B, int32_t L, const float* d_txt_embeds, void* saved,
-                     size_t saved_bytes, void* work, size_t work_bytes, void* stream);
+                     size_t saved_bytes, void* work, size_t work_bytes, void* stream, const etp_dropout* dropout);
 
 /* torch.optim.AdamW semantics (ss_trainer_ETP.py:213) over flat fp32 buffers; also rewrites the bf16 image of
  * the parameters.  grad_scale multiplies the gradient first (1/world_size after the gradient all-reduce). */

@@ -10,6 +10,13 @@ from etpnav_b200.synth import make_inputs, make_weights
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+def no_dropout(cfg):
+    """Parity with the fp32 oracle is defined with dropout off: zero the three probabilities so that
+    train() mode computes the p = 0 function.  tests/test_dropout_gpu.py covers the p > 0 path."""
+    cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = cfg.pred_head_dropout_prob = 0.0
+    return cfg
+
+
 def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
 

@@ -13,7 +13,7 @@ import os
 import pytest
 import torch
 
-from tests.common import golden_loss, golden_names, grad_sig, load_case, slim
+from tests.common import golden_loss, golden_names, grad_sig, load_case, no_dropout, slim
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 REL_L2_ACT = 8e-2     # activations' gradients: ||g - g_ref|| / ||g_ref||
@@ -29,6 +29,7 @@ def _rel(a, b):
 def test_backward_matches_golden(name):
     from etpnav_b200.planner import B200Planner
     gold, cfg, sd, inp = load_case(name)
+    no_dropout(cfg)
     m = B200Planner(cfg, device="cuda")
     m.load_state_dict(sd, strict=True)
     m.train()
@@ -84,7 +85,7 @@ def test_txt_backward_matches_oracle():
     from etpnav_b200.planner import B200Planner
     from etpnav_b200.synth import make_inputs, make_weights
     from oracle import planner_port as P
-    cfg = PlannerConfig(vocab_size=2048, num_l_layers=2)
+    cfg = no_dropout(PlannerConfig(vocab_size=2048, num_l_layers=2))
     sd = make_weights(cfg, seed=21)
     inp = make_inputs(cfg, 3, 12, 8, 37, seed=21, ragged=True)
     m = B200Planner(cfg, device="cuda")
@@ -111,7 +112,7 @@ def test_trainer_step_reduces_loss_and_matches_adamw():
     from etpnav_b200.config import PlannerConfig
     from etpnav_b200.planner import B200Planner
     from etpnav_b200.synth import make_inputs, make_weights
-    cfg = PlannerConfig(vocab_size=2048, num_l_layers=0, num_x_layers=2)
+    cfg = no_dropout(PlannerConfig(vocab_size=2048, num_l_layers=0, num_x_layers=2))
     sd = make_weights(cfg, seed=8)
     inp = make_inputs(cfg, 8, 12, 20, 30, seed=8, ragged=True)
     d = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
