@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--tokens", type=int, default=200)
     ap.add_argument("--x-layers", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", default="on", choices=["on", "off"],
+                    help="train mode: the reference's train() dropout (0.1 hidden / attention / head) on (default) or off")
     ap.add_argument("--gpu-eager", action="store_true",
                     help="also time the oracle port in eager PyTorch on this GPU (fp32 and bf16 autocast): the "
                          "'reference GPU eager' figure the north_star's >=10x target is stated against")
@@ -61,11 +63,24 @@ def parse():
 
 def workload_cfg(a):
     # text-side tensors are not part of the per-step path: keep the vocab small so set-up is fast
-    return PlannerConfig(vocab_size=2048, num_l_layers=0, num_x_layers=a.x_layers)
+    cfg = PlannerConfig(vocab_size=2048, num_l_layers=0, num_x_layers=a.x_layers)
+    if a.dropout == "off":
+        cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = cfg.pred_head_dropout_prob = 0.0
+    return cfg
+
+
+def torch_dropout_hook(cfg):
+    """drop(x, kind, site) for the oracle port in the baseline legs: torch's own nn.Dropout arithmetic at the
+    reference's dropout sites (train mode), or None when every probability is 0."""
+    import torch.nn.functional as F
+    ps = {"hidden": cfg.hidden_dropout_prob, "attn": cfg.attention_probs_dropout_prob, "head": cfg.pred_head_dropout_prob}
+    if max(ps.values()) <= 0:
+        return None
+    return lambda x, kind, site: F.dropout(x, ps[kind], True)
 
 
 def workload_name(a, mode):
-    what = "fwd+bwd+AdamW" if mode == "train" else "fwd"
+    what = ("fwd+bwd+AdamW, train() dropout " + a.dropout) if mode == "train" else "fwd"
     return (f"planner step {what}: forward_panorama+forward_navigation, B={a.batch}/GPU, V={a.views}, N={a.nodes}, "
             f"L={a.tokens}, {a.x_layers} cross layers")
 
@@ -145,13 +160,16 @@ def cpu_step_time(a, mode, steps, warmup, max_seconds=25.0):
         sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
         opt = torch.optim.AdamW([v for v in sd.values()], lr=1e-5)
 
+    drop = torch_dropout_hook(cfg) if mode == "train" else None
+
     def step():
         if mode == "train":
             opt.zero_grad(set_to_none=True)
-            pano, pm = P.forward_panorama(sd, cfg, inp["rgb_fts"], inp["dep_fts"], inp["loc_fts"], inp["nav_types"], inp["view_lens"])
+            pano, pm = P.forward_panorama(sd, cfg, inp["rgb_fts"], inp["dep_fts"], inp["loc_fts"], inp["nav_types"], inp["view_lens"],
+                                          drop=drop)
             nav = P.forward_navigation(sd, cfg, inp["txt_embeds"], inp["txt_masks"], None, inp["gmap_step_ids"],
                                        inp["gmap_img_fts"], inp["gmap_pos_fts"], inp["gmap_masks"],
-                                       inp["gmap_visited_masks"], inp["gmap_pair_dists"])
+                                       inp["gmap_visited_masks"], inp["gmap_pair_dists"], drop=drop)
             loss = P.step_loss(nav["global_logits"], inp["labels"]) + (pano * pm[..., None]).sum() * 1e-3
             loss.backward()
             opt.step()
@@ -192,11 +210,14 @@ def gpu_eager_time(a, mode, dev, autocast, steps=10, warmup=3):
         sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
         opt = torch.optim.AdamW(list(sd.values()), lr=1e-5)
 
+    drop = torch_dropout_hook(cfg) if mode == "train" else None
+
     def fwd():
-        pano, pm = P.forward_panorama(sd, cfg, inp["rgb_fts"], inp["dep_fts"], inp["loc_fts"], inp["nav_types"], inp["view_lens"])
+        pano, pm = P.forward_panorama(sd, cfg, inp["rgb_fts"], inp["dep_fts"], inp["loc_fts"], inp["nav_types"], inp["view_lens"],
+                                      drop=drop)
         nav = P.forward_navigation(sd, cfg, inp["txt_embeds"], inp["txt_masks"], None, inp["gmap_step_ids"],
                                    inp["gmap_img_fts"], inp["gmap_pos_fts"], inp["gmap_masks"],
-                                   inp["gmap_visited_masks"], inp["gmap_pair_dists"])
+                                   inp["gmap_visited_masks"], inp["gmap_pair_dists"], drop=drop)
         return pano, pm, nav
 
     def step():
@@ -411,7 +432,7 @@ def main():
                 "warmup": max(3, a.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload_name(a, mode), "mode": mode, "global_batch": B * world,
-                           "parallelism": f"dp{world}", "x_layers": a.x_layers,
+                           "parallelism": f"dp{world}", "x_layers": a.x_layers, "dropout": a.dropout if mode == "train" else "n/a",
                            "l2": "no flush: per-step working set (activation record + bf16/fp32 weights) exceeds the 126 MB L2"},
                 "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_ms},

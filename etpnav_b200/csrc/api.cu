@@ -25,6 +25,19 @@ ETP_API int etp_version(void) { return 100; }
 ETP_API const char* etp_last_error(void) { return last_error_cstr(); }
 
 ETP_API long long etp_launch_count(void) { return g_launches.load(); }
+ETP_API void* etp_event_create(void) {
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  return e;
+}
+ETP_API void etp_event_destroy(void* event) {
+  if (event) cudaEventDestroy(static_cast<cudaEvent_t>(event));
+}
+ETP_API int etp_stream_wait_event(void* stream, void* event) {
+  ETP_REQUIRE(event != nullptr, "etp_stream_wait_event: null event");
+  ETP_CHECK_CUDA(cudaStreamWaitEvent(S(stream), static_cast<cudaEvent_t>(event), 0));
+  return ETP_OK;
+}
 ETP_API void etp_prof_gemm_enable(int on) { prof_enable(on != 0); }
 ETP_API int etp_prof_gemm_collect(double* total_ms, double* total_flops, long long* launches) {
   ETP_REQUIRE(total_ms && total_flops && launches, "etp_prof_gemm_collect: null argument");

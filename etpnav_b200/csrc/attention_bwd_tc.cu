@@ -337,6 +337,21 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             uint32_t vs[16], vd[16];
             tmem_ld16(tS + lane_sel + c, vs);
             tmem_ld16(tDP + lane_sel + c, vd);
+            // dropout multipliers of these 16 probabilities: one hash per aligned pair when the key count is even
+            float dm[16];
+            if (p.drop.thr) {
+              const uint32_t e0 = e_row + static_cast<uint32_t>(k0 + c);
+              if ((p.Sk & 1) == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) drop_mul2(p.drop, e0 + i, dm[i], dm[i + 1]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dm[i] = drop_mul(p.drop, e0 + i);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) dm[i] = 1.0f;
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -347,8 +362,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 float sc = fmaf(__uint_as_float(vs[i + t]), sl2, kbv[t]);
                 if constexpr (kPair) sc = fmaf(pw2, pv[i + t], sc);
                 const float pr = ex2_approx(sc + nlse2);                            // P (0 on padding rows)
-                float mk = 1.0f;  // forward dropout multiplier of this probability (0 or 1/(1-p))
-                if (p.drop.thr) mk = drop_mul(p.drop, e_row + static_cast<uint32_t>(k0 + c + i + t));
+                const float mk = dm[i + t];  // forward dropout multiplier of this probability (1, or 0 / 1/(1-p))
                 // dP = mask * d(dropped P);  dS = P * (dP - D)  (x scale);  dV uses the dropped P
                 const float dss = pr * fmaf(__uint_as_float(vd[i + t]) * mk, p.scale, -Ds);
                 if constexpr (kPair) { wsum = fmaf(dss, pv[i + t], wsum); bsum += dss; }

@@ -243,6 +243,8 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     ETP_TRY(wb.add(sc.dq, rows, kH, kH, x_in, kH, kH, lg.xq_w, s));
     ETP_TRY(dgrad(sc.dq, rows, kH, kH, lw.xq_w, kH, sc.g0, P, nullptr, 0, nullptr, s));  // dx_in = dq.Wq + dt1
     ETP_TRY(wb.flush(s));  // the layer's six weight gradients, one launch
+    if (in.layer_done_events && in.layer_done_events[i])
+      ETP_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(in.layer_done_events[i]), s));
   }
   // text side, all layers at once: kv_all = txt . Wkv_all^T + b  ->  one wgrad, one dgrad (bias grads: above)
   if (X > 0) {

@@ -23,3 +23,41 @@ def allreduce_flat_(flat_grad: torch.Tensor, world: int) -> float:
         import torch.distributed as dist
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
     return 1.0 / world
+
+
+def gradient_buckets(layout, cfg, lo, hi):
+    """Slices [start, end) of the flat gradient buffer in the order the backward completes them, covering [lo, hi):
+    x-layer X-1 (with the SAP head that follows it in the layout), X-2, ..., 0, then the rest (panorama group,
+    node-packing parameters and the stacked text key|value projections, all finished last).  Each x-layer's own
+    parameters are one contiguous run of the layout (etpnav_b200/layout.py)."""
+    X = cfg.num_x_layers
+    buckets = []
+    if X == 0:
+        return [("rest", lo, hi)]
+    starts = [layout.offset(f"global_encoder.encoder.x_layers.{i}.visual_attention.att.query.weight") for i in range(X)]
+    ends = starts[1:] + [hi]     # the last layer's run extends over the SAP head to the end of the nav group
+    for i in range(X - 1, -1, -1):
+        buckets.append((f"x_layer_{i}", starts[i], ends[i]))
+    if starts[0] > lo:
+        buckets.append(("rest", lo, starts[0]))
+    return buckets
+
+
+def allreduce_buckets_(flat_grad, buckets, world, side_stream=None, wait_fns=None):
+    """SUM all-reduce of ``flat_grad`` bucket by bucket.  With a CUDA ``side_stream``, bucket i is enqueued on it
+    after ``wait_fns[i](side_stream)`` (e.g. a cudaStreamWaitEvent on the event the backward records when that
+    bucket is final), so the collectives overlap the rest of the backward; the caller joins the streams afterwards.
+    Without a side stream (CPU / gloo tests) the buckets are reduced in order on the current stream."""
+    if world <= 1:
+        return 1.0
+    import torch.distributed as dist
+    if side_stream is None:
+        for _, a, b in buckets:
+            dist.all_reduce(flat_grad[a:b], op=dist.ReduceOp.SUM)
+        return 1.0 / world
+    for i, (_, a, b) in enumerate(buckets):
+        if wait_fns is not None and wait_fns[i] is not None:
+            wait_fns[i](side_stream)
+        with torch.cuda.stream(side_stream):
+            dist.all_reduce(flat_grad[a:b], op=dist.ReduceOp.SUM)
+    return 1.0 / world

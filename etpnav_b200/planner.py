@@ -48,7 +48,8 @@ class Dropout(C.Structure):
 class NavInputs(C.Structure):
     _fields_ = [("B", i32), ("N", i32), ("L", i32)] + [
         (n, p_void) for n in ("txt_embeds", "txt_masks", "gmap_step_ids", "gmap_img_fts", "gmap_pos_fts",
-                              "gmap_masks", "gmap_visited_masks", "gmap_pair_dists")] + [("dropout", C.POINTER(Dropout))]
+                              "gmap_masks", "gmap_visited_masks", "gmap_pair_dists")] + [
+        ("dropout", C.POINTER(Dropout)), ("layer_done_events", C.POINTER(p_void))]
 
 
 class PanoLayerWeights(C.Structure):
@@ -132,6 +133,7 @@ class B200Planner(nn.Module):
         self._grad_structs = {}
         self._direct_grad = None      # PlannerTrainer: flat fp32 gradient buffer the backward accumulates into
         self._anchor = torch.zeros(1, device=dev, requires_grad=True)
+        self._layer_events = None  # PlannerTrainer (world > 1): cudaEvent_t per x-layer, recorded by the nav backward
         self._drop_base = None   # dropout seed stream: base (torch.initial_seed() unless set) + call counter
         self._drop_calls = 0
         if config.fix_lang_embedding:  # vilmodel_cmt.py:675-679
@@ -536,6 +538,8 @@ class _NavFn(torch.autograd.Function):
         gbuf, gstart, per_call = m._grad_target("nav")
         gst = m._grad_structs_for(gbuf, gstart)
         ni = _nav_inputs(txt, img, aux, ctx.drop)
+        if m._layer_events is not None:
+            ni.layer_done_events = m._layer_events
         de = _f32c(d_embeds) if d_embeds is not None else None
         dl = _f32c(d_logits) if d_logits is not None else None
         if dl is not None:
@@ -643,6 +647,21 @@ class PlannerTrainer:
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.t = 0
+        # data parallel: the gradient slice is reduced in buckets, in the order the backward completes them, on a side
+        # stream: x-layer i's bucket starts as soon as the event the nav backward records for it fires
+        self.buckets, self.side, self._events = None, None, []
+        if world_size > 1:
+            from .dist import gradient_buckets
+            self.buckets = [(nm, a - self.lo, b - self.lo) for nm, a, b in
+                            gradient_buckets(model.layout, model.config, self.lo, self.hi)]
+            self.side = torch.cuda.Stream(dev)
+            L0 = _L.lib()
+            L0.etp_event_create.restype = p_void
+            L0.etp_event_destroy.argtypes = [p_void]
+            L0.etp_stream_wait_event.argtypes = [p_void, p_void]
+            X = model.config.num_x_layers
+            self._events = [L0.etp_event_create() for _ in range(X)]
+            model._layer_events = (p_void * max(X, 1))(*self._events)
         L = _L.lib()
         L.etp_adamw_step.argtypes = [p_void, p_void, p_void, p_void, p_void, C.c_int64, f32, f32, f32, f32, f32, i32, f32,
                                      p_void]
@@ -671,9 +690,26 @@ class PlannerTrainer:
 
     def optimizer_step(self):
         m = self.m
-        from .dist import allreduce_flat_
         g = m._direct_grad[self.lo:self.hi]
-        scale = allreduce_flat_(g, self.world)  # SUM over ranks; DDP's 1/world is folded into AdamW's grad_scale
+        scale = 1.0
+        if self.world > 1:
+            # SUM over ranks (DDP's 1/world is folded into AdamW's grad_scale).  Everything below is only ENQUEUED here:
+            # the backward kernels are still running; each layer bucket waits for its own event, the last bucket for
+            # the end of the backward.
+            from .dist import allreduce_buckets_
+            L0 = _L.lib()
+            main = torch.cuda.current_stream()
+            X = m.config.num_x_layers
+            waits = []
+            for nm, _, _ in self.buckets:
+                if nm.startswith("x_layer_"):
+                    ev = self._events[int(nm.split("_")[-1])]
+                    waits.append(lambda s, ev=ev: _L._check(L0.etp_stream_wait_event(C.c_void_p(s.cuda_stream), C.c_void_p(ev)),
+                                                            "etp_stream_wait_event"))
+                else:
+                    waits.append(lambda s: s.wait_stream(main))
+            scale = allreduce_buckets_(g, self.buckets, self.world, self.side, waits)
+            main.wait_stream(self.side)
         self.t += 1
         _L._check(_L.lib().etp_adamw_step(
             C.c_void_p(m._flat.data_ptr() + 4 * self.lo), C.c_void_p(m._flat_bf16.data_ptr() + 2 * self.lo), _L.ptr(g),

@@ -41,6 +41,10 @@ int etp_version(void);                /* 100 * major + minor */
 const char* etp_last_error(void);     /* text of the last error on this thread */
 /* 0 if the current CUDA device is sm_100 (B200); ETP_ERR_NO_DEVICE otherwise. */
 int etp_check_device(void);
+/* thin CUDA event helpers for hosts without their own bindings (used for the gradient-bucket overlap) */
+void* etp_event_create(void);                       /* cudaEventCreateWithFlags(disable timing); NULL on error */
+void etp_event_destroy(void* event);
+int etp_stream_wait_event(void* stream, void* event);   /* cudaStreamWaitEvent */
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long etp_launch_count(void);
 /* CUDA-event timing of every tcgen05 GEMM launch (for the roofline line of bench.py): enable, run steps,
@@ -234,6 +238,10 @@ typedef struct {
   const uint8_t* gmap_visited_masks;  /* [B,N] */
   const float* gmap_pair_dists;       /* [B,N,N] */
   const etp_dropout* dropout;         /* train() mode dropout, or NULL */
+  /* backward only, optional: HOST array of num_x_layers cudaEvent_t; event i is recorded on the stream when every
+   * parameter gradient of x-layer i is complete (layers finish in the order X-1 ... 0), so the caller can start the
+   * all-reduce of that layer's gradient slice on another stream while the rest of the backward runs */
+  void* const* layer_done_events;
 } etp_nav_inputs;
 
 /* Bytes of the activation record forward_navigation writes (and backward reads) when training != 0;
