@@ -215,14 +215,19 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             const uint64_t dom = make_smem_desc(aDO, 8192, 1024), dqm = make_smem_desc(aQ, 8192, 1024);     // MN-major B
             const uint64_t dsk = make_smem_desc(aDS, 16, 1024);                                             // K-major A
             const uint64_t dkm = make_smem_desc(aK, 8192, 1024);                                            // MN-major B
+            // reductions only over the query / key groups that exist (the rest of the tiles is zero padding)
+            const int qgroups = (min(kBQ, p.Sq) + 15) >> 4;
+            const int kgroups = (min(kBK, p.Sk - j * kBK) + 15) >> 4;
 #pragma unroll
             for (int k = 0; k < kBQ / 16; ++k) {
+              if (k >= qgroups) break;
               umma_bf16_lh(tDV, desc_lo(dpm) + 128 * k, desc_hi(dpm), desc_lo(dom) + 128 * k, desc_hi(dom), id_kv, k > 0 ? 1u : 0u);
               umma_bf16_lh(tDK, desc_lo(dsm) + 128 * k, desc_hi(dsm), desc_lo(dqm) + 128 * k, desc_hi(dqm), id_kv, k > 0 ? 1u : 0u);
             }
             // dQ += dS.K : reduction over the 128 keys of this block
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
+              if (k < kgroups)
               umma_bf16_lh(tDQ, desc_lo(dsk) + (k >> 2) * 1024 + (k & 3) * 2, desc_hi(dsk), desc_lo(dkm) + 128 * k, desc_hi(dkm),
                            id_q, (j > 0 || k > 0) ? 1u : 0u);
           }

@@ -169,8 +169,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait(p_ready, s & 1);
           tc_fence_after();
           const uint64_t dv0 = make_smem_desc(smem_u32(sV + (s & 1) * kTile), 8192, 1024);
+          // only the key groups that hold real keys (P is 0 beyond them): every MMA costs ~75 ns of issue latency
+          const int kgroups = (min(kBK, p.Sk - j * kBK) + 15) >> 4;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
+            if (k < kgroups)
             umma_bf16_lh(tO, desc_lo(dp0) + (k >> 2) * 1024 + (k & 3) * 2, desc_hi(dp0), desc_lo(dv0) + 128 * k, desc_hi(dv0),
                          idesc_o, k > 0 ? 1u : 0u);
           umma_commit(o_ready);

@@ -28,6 +28,7 @@
 // Replaces the cuBLAS calls behind torch.nn.Linear / torch.matmul on the reference path
 // (vilmodel_cmt.py:108-110,326-328,151,178,190,654; common/transformer.py:174-181).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -41,17 +42,20 @@ namespace {
 
 constexpr int BM = 128;  // accumulator rows per CTA (pair tile: 256)
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + kEpiWarps * 32;
+// Epilogue warps per CTA (template parameter EW): 8 = 4 TMEM lane quadrants x 2 column halves (one more pipeline
+// stage, 168 registers: next-chunk residual prefetch); 16 = 4 x 4 column quarters (four warps per scheduler hide the
+// latency chains of the epilogue: TMEM load -> transpose -> math -> stores), 96 registers.
+constexpr int kThreadsOf(int ew) { return 64 + ew * 32; }
 constexpr int kTS = 36;  // staging pitch (floats): 16-byte aligned rows, conflict-free for STS.128 rows / LDS.32 columns
-constexpr int kScratchBytes = kEpiWarps * 32 * kTS * 4;
+constexpr int kScratchBytesOf(int ew) { return ew * 32 * kTS * 4; }
 
-template <int BN>
+template <int BN, int EW>
 struct PairCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / 2) * BK * 2;  // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 5 : 7;
+  static constexpr int kStages = (EW == 8) ? ((BN == 256) ? 5 : 7) : ((BN == 256) ? 4 : 6);
+  static constexpr int kScratchBytes = kScratchBytesOf(EW);
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -79,9 +83,11 @@ struct TileRef {
   int m_blk, n_blk, kb0, kb1, g;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool kGrouped>
+template <int BN, bool A_MN, bool B_MN, bool kGrouped, int EW>
 ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, const GroupParams* gp) {
-  using Cfg = PairCfg<BN>;
+  using Cfg = PairCfg<BN, EW>;
+  constexpr int kEpiWarps = EW;
+  constexpr int kScratchBytes = Cfg::kScratchBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -228,8 +234,9 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     // ===================== epilogue warps (both CTAs) =====================
     const int ew = warp - 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;   // which half of the BN columns
-    constexpr int kChunks = BN / 2 / 32;
+    const int half = ew >> 2;   // which slice (half / quarter) of the BN columns
+    constexpr int kSlice = BN / (EW / 4);
+    constexpr int kChunks = kSlice / 32;
     const uint32_t scr = smem_u32(scratch + ew * 32 * kTS);
     const uint32_t empty_leader = mapa_shared(smem_u32(&tmem_empty[0]), 0);
     // after the transpose a lane owns two adjacent columns (cp) of 16 rows (rh): every global access of a warp
@@ -249,7 +256,7 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
         e.resid = pr.out; e.ld_resid = pr.ld;  // dW += acc
       }
       const int row0 = m_blk * (2 * BM) + static_cast<int>(rank) * BM + quad * 32 + rh * 16;  // first row of this lane
-      const int colbase = n_blk * BN + half * (BN / 2) + 2 * cp;
+      const int colbase = n_blk * BN + half * kSlice + 2 * cp;
       const int nrows = min(16, e.M - row0);  // <= 0: nothing of this lane's rows is inside the matrix
 
       // residual of chunk `c` in the transposed layout: 16 independent row segments in flight per lane
@@ -267,7 +274,7 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + acc * BN + half * (BN / 2) + (static_cast<uint32_t>(quad * 32) << 16);
+      const uint32_t taddr0 = tmem_base + acc * BN + half * kSlice + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int col = colbase + c * 32;
@@ -275,7 +282,11 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
         uint32_t r[32];
         tmem_ld32(taddr0 + c * 32, r);
         float2 Rn[16];
-        if (e.resid && c + 1 < kChunks) load_resid(c + 1, Rn);
+        if constexpr (EW == 8) {
+          if (e.resid && c + 1 < kChunks) load_resid(c + 1, Rn);  // next chunk's residual while this one is processed
+        } else {
+          if (e.resid && c > 0) load_resid(c, R);  // (chunk 0 was requested before the accumulator was ready)
+        }
         uint32_t ax[16];
         if (e.aux_mode) {
           const __nv_bfloat16* ap = e.aux + static_cast<size_t>(row0) * e.ld_aux + col;
@@ -402,6 +413,12 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
               if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * e.ld_bf16) = pack_bf16x2(v[2 * k], v[2 * k + 1]);
           }
         }
+        if constexpr (EW == 8) {
+          if (e.resid && c + 1 < kChunks) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) R[k] = Rn[k];
+          }
+        }
         if (e.colsum) {
           // bias gradient: column sums of the final values (rows outside the matrix contribute 0)
           float s0 = 0.0f, s1 = 0.0f;
@@ -414,10 +431,6 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
           s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
           if (rh == 0 && colok)
             asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(e.colsum + col), "f"(s0), "f"(s1) : "memory");
-        }
-        if (e.resid && c + 1 < kChunks) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) R[k] = Rn[k];
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -435,21 +448,21 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int BN, bool A_MN, bool B_MN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsOf(EW), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  gemm_body<BN, A_MN, B_MN, false>(tmA, tmB, p, nullptr);
+  gemm_body<BN, A_MN, B_MN, false, EW>(tmA, tmB, p, nullptr);
 }
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsOf(8), 1)
 gemm_tcgen05_grouped_kernel(const __grid_constant__ GroupParams gp, const GemmDev p) {
-  gemm_body<BN, A_MN, B_MN, true>(gp.prob[0].tmA, gp.prob[0].tmB, p, &gp);
+  gemm_body<BN, A_MN, B_MN, true, 8>(gp.prob[0].tmA, gp.prob[0].tmB, p, &gp);
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch_pair(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
-  using Cfg = PairCfg<BN>;
+template <int BN, bool A_MN, bool B_MN, int EW>
+int launch_pair_ew(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
+  using Cfg = PairCfg<BN, EW>;
   CUtensorMap tmA, tmB;
   int rc;
   // K-major: global [rows, K] (K contiguous), box [rows_per_cta, 64].  MN-major: global [K, rows], box [64 k, 64 rows].
@@ -459,7 +472,7 @@ int launch_pair(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
   if (!B_MN) rc = get_tmap_2d(a.B, a.N, a.K, a.ldb, BN / 2, BK, &tmB);
   else       rc = get_tmap_2d(a.B, a.K, a.N, a.ldb, BK, 64, &tmB);
   if (rc) return rc;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     ETP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -470,20 +483,32 @@ int launch_pair(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   if (g_prof_on) {
     char tag[160];
-    snprintf(tag, sizeof(tag), "M%d N%d K%d bn%d %s%s ks%d%s%s%s%s%s%s", a.M, a.N, a.K, BN, A_MN ? "T" : "N",
+    snprintf(tag, sizeof(tag), "M%d N%d K%d bn%d ew%d %s%s ks%d%s%s%s%s%s%s", a.M, a.N, a.K, BN, EW, A_MN ? "T" : "N",
              B_MN ? "T" : "N", dev.k_splits, a.bias ? " bias" : "", a.act ? (a.act == 1 ? " gelu" : " relu") : "",
              a.aux_mode ? " aux" : "", a.resid ? " resid" : "", a.out_f32 ? (a.atomic ? " red32" : " f32") : "",
              (a.out_bf16 ? " bf16" : ""));
     prof_tag(tag, 2.0 * a.M * a.N * a.K);
   }
-  ETP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tmA, tmB, dev));
+  ETP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreadsOf(EW)), Cfg::kSmemBytes, stream, tmA, tmB, dev));
   ETP_LAUNCHED();
   return ETP_OK;
 }
 
+template <int BN, bool A_MN, bool B_MN>
+int launch_pair(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
+  // 16 epilogue warps for every single-problem launch: measured on one box (tests/run_gpu_ab.sh) the c3 training step
+  // runs 5.67 ms with 16 everywhere, 5.85 ms with 16 only for GELU / derivative / dropout epilogues, 5.96 ms with 8.
+  // The grouped weight-gradient launch (main-loop bound, 80 k-blocks per tile) keeps 8 warps and 5 stages.
+  // ETP_GEMM_EW=8 forces the 8-warp variant (A/B measurements).
+  bool heavy = true;
+  static const int forced = [] { const char* e = getenv("ETP_GEMM_EW"); return e ? atoi(e) : 0; }();
+  if (forced == 8) heavy = false;
+  return heavy ? launch_pair_ew<BN, A_MN, B_MN, 16>(a, dev, stream) : launch_pair_ew<BN, A_MN, B_MN, 8>(a, dev, stream);
+}
+
 template <int BN>
 int launch_grouped_tt(const GemmArgs* a, int n, cudaStream_t stream) {
-  using Cfg = PairCfg<BN>;
+  using Cfg = PairCfg<BN, 8>;
   GroupParams gp;
   memset(&gp, 0, sizeof(gp));
   gp.n = n;
@@ -520,7 +545,7 @@ int launch_grouped_tt(const GemmArgs* a, int n, cudaStream_t stream) {
     snprintf(tag, sizeof(tag), "grouped wgrad x%d bn%d TT K%d tiles%d", n, BN, a[0].K, tiles);
     prof_tag(tag, flops);
   }
-  ETP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, gp, d));
+  ETP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreadsOf(8)), Cfg::kSmemBytes, stream, gp, d));
   ETP_LAUNCHED();
   return ETP_OK;
 }

@@ -258,6 +258,9 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
                         F(g.pos_w), F(g.pos_b), F(g.pos_g), F(g.pos_bb), s));
   if (d_gmap_img_fts)
     ETP_CHECK_CUDA(cudaMemcpyAsync(d_gmap_img_fts, P, static_cast<size_t>(rows) * kH * 4, cudaMemcpyDeviceToDevice, s));
+  // entry X of the optional event array: every gradient of the navigation group is complete
+  if (in.layer_done_events && in.layer_done_events[X])
+    ETP_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(in.layer_done_events[X]), s));
   return ETP_OK;
 }
 

@@ -29,7 +29,8 @@ def gradient_buckets(layout, cfg, lo, hi):
     """Slices [start, end) of the flat gradient buffer in the order the backward completes them, covering [lo, hi):
     x-layer X-1 (with the SAP head that follows it in the layout), X-2, ..., 0, then the rest (panorama group,
     node-packing parameters and the stacked text key|value projections, all finished last).  Each x-layer's own
-    parameters are one contiguous run of the layout (etpnav_b200/layout.py)."""
+    parameters are one contiguous run of the layout (etpnav_b200/layout.py).  When the slice also holds the panorama
+    group, the remainder is split into ``nav_head`` (final at the end of the navigation backward) and ``rest``."""
     X = cfg.num_x_layers
     buckets = []
     if X == 0:
@@ -38,7 +39,11 @@ def gradient_buckets(layout, cfg, lo, hi):
     ends = starts[1:] + [hi]     # the last layer's run extends over the SAP head to the end of the nav group
     for i in range(X - 1, -1, -1):
         buckets.append((f"x_layer_{i}", starts[i], ends[i]))
-    if starts[0] > lo:
+    nav_lo = layout.group_ranges["nav"][0]
+    if lo < nav_lo < starts[0]:
+        buckets.append(("nav_head", nav_lo, starts[0]))   # node packing + stacked text K|V: done when the nav backward is
+        buckets.append(("rest", lo, nav_lo))              # panorama group: done last
+    elif starts[0] > lo:
         buckets.append(("rest", lo, starts[0]))
     return buckets
 

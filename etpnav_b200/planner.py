@@ -660,8 +660,8 @@ class PlannerTrainer:
             L0.etp_event_destroy.argtypes = [p_void]
             L0.etp_stream_wait_event.argtypes = [p_void, p_void]
             X = model.config.num_x_layers
-            self._events = [L0.etp_event_create() for _ in range(X)]
-            model._layer_events = (p_void * max(X, 1))(*self._events)
+            self._events = [L0.etp_event_create() for _ in range(X + 1)]   # one per x-layer + "nav group complete"
+            model._layer_events = (p_void * (X + 1))(*self._events)
         L = _L.lib()
         L.etp_adamw_step.argtypes = [p_void, p_void, p_void, p_void, p_void, C.c_int64, f32, f32, f32, f32, f32, i32, f32,
                                      p_void]
@@ -702,8 +702,8 @@ class PlannerTrainer:
             X = m.config.num_x_layers
             waits = []
             for nm, _, _ in self.buckets:
-                if nm.startswith("x_layer_"):
-                    ev = self._events[int(nm.split("_")[-1])]
+                if nm.startswith("x_layer_") or nm == "nav_head":
+                    ev = self._events[X if nm == "nav_head" else int(nm.split("_")[-1])]
                     waits.append(lambda s, ev=ev: _L._check(L0.etp_stream_wait_event(C.c_void_p(s.cuda_stream), C.c_void_p(ev)),
                                                             "etp_stream_wait_event"))
                 else:

@@ -238,9 +238,10 @@ typedef struct {
   const uint8_t* gmap_visited_masks;  /* [B,N] */
   const float* gmap_pair_dists;       /* [B,N,N] */
   const etp_dropout* dropout;         /* train() mode dropout, or NULL */
-  /* backward only, optional: HOST array of num_x_layers cudaEvent_t; event i is recorded on the stream when every
-   * parameter gradient of x-layer i is complete (layers finish in the order X-1 ... 0), so the caller can start the
-   * all-reduce of that layer's gradient slice on another stream while the rest of the backward runs */
+  /* backward only, optional: HOST array of num_x_layers + 1 cudaEvent_t (entries may be NULL); event i < X is recorded
+   * on the stream when every parameter gradient of x-layer i is complete (layers finish in the order X-1 ... 0),
+   * event X when the whole navigation group is, so the caller can start the all-reduce of those gradient slices on
+   * another stream while the rest of the backward runs */
   void* const* layer_done_events;
 } etp_nav_inputs;
 
