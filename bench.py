@@ -348,8 +348,9 @@ def main():
     lib = L.lib()
     lib.etp_launch_count.restype = __import__("ctypes").c_longlong
     n0 = lib.etp_launch_count()
-    with Clocks(local) as clk:
-        total_ms = timed(lambda: step(resident), a.steps)
+    clk = Clocks(local)
+    clk.__enter__()   # sampled across the timed regions below (value, e2e) and the profiled pass: all under load
+    total_ms = timed(lambda: step(resident), a.steps)
     launches = lib.etp_launch_count() - n0
     ms_per_step = total_ms / a.steps
     value = world / (ms_per_step * 1e-3)
@@ -385,6 +386,7 @@ def main():
     lib.etp_prof_report.argtypes = [C.c_char_p, C.c_size_t]
     L._check(lib.etp_prof_report(buf, len(buf)), "etp_prof_report")
     lib.etp_prof_gemm_enable(0)
+    clk.__exit__()
     g_ms, g_fl, g_n = C.c_double(0.0), C.c_double(0.0), C.c_longlong(0)
     rows = []
     for ln in buf.value.decode().splitlines():
@@ -411,7 +413,10 @@ def main():
     achieved = (g_fl.value / (g_ms.value * 1e-3)) / 1e12 if g_ms.value > 0 else 0.0
     fl = step_flops(cfg, B, V, N, Lt)
     roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": None,
+            "traffic_note": "per-launch dram__bytes of 12 captured launches: profiles/r01_gemm_ncu_full_summary.tsv "
+                            "(grouped wgrad: 198 MB read + 20 MB written for 189 MB of operands)",
+            "peak_source": peak_src,
             "gemm_launches_per_step": g_n.value / prof_steps, "gemm_ms_per_step": g_ms.value / prof_steps,
             "gemm_share_of_step": (g_ms.value / prof_steps) / ms_per_step,
             "step_model_tflops": (fl["step_fwd"] * (3 if mode == "train" else 1)) / (ms_per_step * 1e-3) / 1e12}
