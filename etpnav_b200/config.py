@@ -36,6 +36,11 @@ class PlannerConfig:
     pred_head_dropout_prob: float = 0.1
     # pano encoder layers use nn.LayerNorm's default eps (common/transformer.py:144-145)
     pano_layer_norm_eps: float = 1e-5
+    # pre-training twin (pretrain_src/run_pt/r2r_model_config_dep.json): extra lang_self_att / lang_inter / lang_output
+    # parameters in every x-layer (pretrain_src/pretrain_src/model/vilmodel.py:370-374) and the MLM head
+    # (pretrain_cmt.py:56-57; decoder tied to the word embeddings, :79-82).  Both off for the navigation model.
+    use_lang2visn_attn: bool = False
+    mlm_head: bool = False
 
     @property
     def head_dim(self) -> int:

@@ -58,6 +58,27 @@ void NavRecord::carve(Arena& ar, int B, int N, int L, int X, bool training) {
   }
 }
 
+void L2VRecord::carve(Arena& ar, int B, int N, int L, int X, bool training) {
+  const size_t rows = static_cast<size_t>(B) * L, nrows = static_cast<size_t>(B) * N;
+  nodeb = ar.take<bf16>(nrows * kH);
+  pos_lin = ar.take<float>(nrows * kH);
+  pos_stats = ar.take<float>(nrows * 2);
+  nodef = ar.take<float>(nrows * kH);
+  kv_all = ar.take<bf16>(nrows * 2 * kH * (X > 0 ? X : 1));
+  txtb = ar.take<bf16>(rows * kH);
+  xa = ar.take<float>(rows * kH);
+  xc = ar.take<float>(rows * kH);
+  xf = ar.take<float>(rows * kH);
+  layers.resize(X);
+  const size_t mark = ar.off;
+  for (int i = 0; i < X; ++i) {
+    if (!training) ar.off = mark;
+    layers[i].carve(ar, static_cast<int>(rows), 0, B, L, true);
+    layers[i].kv = kv_all + static_cast<size_t>(i) * 2 * kH;
+    layers[i].ldkv = X * 2 * kH;
+  }
+}
+
 void PanoRecord::carve(Arena& ar, int B, int V, int P, bool training) {
   const size_t rows = static_cast<size_t>(B) * V;
   rgbb = ar.take<bf16>(rows * 512);
@@ -306,6 +327,61 @@ int forward_txt(const etp_txt_weights& w, const int64_t* txt_ids, const uint8_t*
   return ETP_OK;
 }
 
+// GlocalTextPathCMT.forward_mlm's cross-modal part (pretrain_src/pretrain_src/model/vilmodel.py:733-741): node packing
+// (gmap_input_embedding, :621-632) then, per x-layer, GraphLXRTXLayer.forward_lang2visn (:400-411): tokens query the
+// nodes through visual_attention, lang_self_att over the tokens, lang_inter / lang_output.  The node K|V of every
+// layer depend only on the packed nodes, so they come out of one GEMM, like the text K|V of forward_navigation.
+int forward_lang2visn(const etp_nav_weights& w, const etp_nav_inputs& in, float* lang_embeds, void* saved,
+                      size_t saved_bytes, bool training, cudaStream_t s) {
+  const int B = in.B, N = in.N, L = in.L, X = w.num_x_layers;
+  ETP_REQUIRE(B > 0 && N > 0 && L > 0 && X >= 1, "forward_lang2visn: bad shape");
+  ETP_REQUIRE(N <= 1024 && L <= 1024, "forward_lang2visn: at most 1024 nodes / tokens");
+  Arena ar(saved, saved_bytes);
+  L2VRecord rec;
+  rec.carve(ar, B, N, L, X, training);
+  ETP_REQUIRE(ar.off <= saved_bytes, "forward_lang2visn: saved buffer too small");
+  const int rows = B * L, nrows = B * N;
+  DropCtx dc;
+  if (in.dropout) { dc.seed = in.dropout->seed; dc.p_hidden = in.dropout->p_hidden; dc.p_attn = in.dropout->p_attn; dc.p_head = in.dropout->p_head; }
+
+  NodePackArgs np;
+  np.rows = nrows; np.img_fts = in.gmap_img_fts; np.step_ids = in.gmap_step_ids; np.pos_fts = in.gmap_pos_fts;
+  np.pos_w = w.pos_w; np.pos_b = w.pos_b; np.pos_g = w.pos_g; np.pos_bb = w.pos_bb; np.step_emb = w.step_emb;
+  np.x_f32 = rec.nodef; np.x_bf16 = rec.nodeb;
+  np.pos_lin = training ? rec.pos_lin : nullptr; np.stats = rec.pos_stats;
+  ETP_TRY(node_pack_fwd(np, s));
+  ETP_TRY(cast_f32_to_bf16(in.txt_embeds, rec.txtb, static_cast<int64_t>(rows) * kH, s));
+  ETP_TRY(linear(rec.nodeb, nrows, kH, w.xkv_all_w, X * 2 * kH, w.xkv_all_b, 0, nullptr, nullptr, rec.kv_all, nullptr, s));
+  const float* x_f32 = in.txt_embeds;
+  const bf16* x_bf16 = rec.txtb;
+  for (int i = 0; i < X; ++i) {
+    const etp_layer_weights& lw = w.layers[i];
+    LayerRecord& r = rec.layers[i];
+    ETP_TRY(linear(x_bf16, rows, kH, lw.xq_w, kH, lw.xq_b, 0, nullptr, nullptr, r.q, nullptr, s));
+    AttnArgs at;
+    at.B = B; at.heads = kHeads; at.Sq = L; at.Sk = N;
+    at.q = r.q; at.ldq = kH;
+    at.k = r.kv; at.ldk = r.ldkv;
+    at.v = r.kv + kH; at.ldv = r.ldkv;
+    at.scale = 0.125f; at.key_valid = in.gmap_masks; at.mask_value = -10000.0f;
+    at.out = r.ctx1; at.ldo = kH; at.lse = r.lse1;
+    {
+      const DropHost d = dc.attn(drop_site(kSiteL2V, i, kDropXAttn));
+      at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
+    }
+    ETP_TRY(attention_dispatch(at, s));
+    ETP_TRY(linear(r.ctx1, rows, kH, lw.xo_w, kH, lw.xo_b, 0, x_f32, r.t1, nullptr, nullptr, s,
+                   dc.hidden(drop_site(kSiteL2V, i, kDropXOut))));
+    ETP_TRY(layernorm_fwd(r.t1, lw.xln_g, lw.xln_b, w.ln_eps, rows, kH, rec.xa, r.ab, r.st1, r.st1 + rows, s));
+    float* x_out = (i == X - 1) ? lang_embeds : rec.xf;
+    ETP_TRY(self_ffn_block(lw, w.ln_eps, r, rec.xa, r.ab, B, L, in.txt_masks, nullptr, nullptr, nullptr, rec.xc, x_out,
+                           training, s, dc, kSiteL2V, i));
+    x_f32 = x_out;
+    x_bf16 = r.xb;
+  }
+  return ETP_OK;
+}
+
 static size_t record_bytes_nav(int B, int N, int L, int X, bool training) {
   Arena ar(nullptr, ~size_t(0));
   NavRecord r;
@@ -335,6 +411,18 @@ ETP_API size_t etp_txt_saved_bytes(int32_t B, int32_t L, int32_t NL, int32_t tra
   TxtRecord r;
   r.carve(ar, B, L, NL, training != 0);
   return ar.off;
+}
+
+ETP_API size_t etp_l2v_saved_bytes(int32_t B, int32_t N, int32_t L, int32_t X, int32_t training) {
+  Arena ar(nullptr, ~size_t(0));
+  L2VRecord r;
+  r.carve(ar, B, N, L, X, training != 0);
+  return ar.off;
+}
+ETP_API int etp_forward_lang2visn(const etp_nav_weights* w, const etp_nav_inputs* in, float* lang_embeds, void* saved,
+                                  size_t saved_bytes, int32_t training, void* stream) {
+  ETP_REQUIRE(w && in && lang_embeds && saved, "etp_forward_lang2visn: null argument");
+  return forward_lang2visn(*w, *in, lang_embeds, saved, saved_bytes, training != 0, S(stream));
 }
 
 ETP_API int etp_forward_navigation(const etp_nav_weights* w, const etp_nav_inputs* in, float* gmap_embeds,

@@ -59,6 +59,18 @@ struct NavRecord {
   void carve(Arena& ar, int B, int N, int L, int X, bool training);
 };
 
+// forward_lang2visn (pre-training twin, forward_mlm): the instruction tokens are the query stream, the packed map
+// nodes the (layer-invariant) context
+struct L2VRecord {
+  bf16* nodeb = nullptr;    // packed nodes gmap_input_embeds (bf16) [B*N,768]
+  float *pos_lin = nullptr, *pos_stats = nullptr;
+  bf16* kv_all = nullptr;   // node K|V of all layers, [B*N, X*1536]
+  bf16* txtb = nullptr;     // bf16 copy of the incoming txt_embeds [B*L,768]
+  float *xa = nullptr, *xc = nullptr, *xf = nullptr, *nodef = nullptr;
+  std::vector<LayerRecord> layers;
+  void carve(Arena& ar, int B, int N, int L, int X, bool training);
+};
+
 struct PanoLayerRecord {
   bf16* y1b = nullptr;
   float* st1 = nullptr;
@@ -95,7 +107,7 @@ struct DropCtx {
   DropHost head(uint32_t site) const { return make_drop_host(seed, p_head, site); }
 };
 // site = base + 16 * layer + k
-constexpr uint32_t kSiteNav = 1000, kSitePano = 2000, kSiteTxt = 3000;
+constexpr uint32_t kSiteNav = 1000, kSitePano = 2000, kSiteTxt = 3000, kSiteL2V = 4000;
 constexpr uint32_t kSiteEmbed = 900;  // + base: dropout after the packing / embedding LayerNorm
 constexpr uint32_t kSiteHead = 901;   // + kSiteNav: NextActionPrediction
 // post-LN blocks (x-layers, BERT layers): k =

@@ -264,6 +264,75 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
   return ETP_OK;
 }
 
+// Backward of forward_lang2visn (planner.cu).  Same skeleton as backward_navigation with the roles swapped: the token
+// stream carries the residual gradient (P), the node side receives dK|dV of all layers, which become one wgrad and one
+// dgrad of the stacked key|value projection, and then flow into the node-packing backward.
+int backward_lang2visn(const etp_nav_weights& w, const etp_nav_weights& g, const etp_nav_inputs& in,
+                       const float* d_lang_embeds, void* saved, size_t saved_bytes, void* work, size_t work_bytes,
+                       float* d_txt_embeds, float* d_gmap_img_fts, cudaStream_t s) {
+  const int B = in.B, N = in.N, L = in.L, X = w.num_x_layers;
+  ETP_REQUIRE(X >= 1, "backward_lang2visn: needs at least one x-layer");
+  const int rows = B * L, kv_rows = B * N;
+  Arena ar(saved, saved_bytes);
+  L2VRecord rec;
+  rec.carve(ar, B, N, L, X, true);
+  ETP_REQUIRE(ar.off <= saved_bytes, "backward_lang2visn: saved buffer too small");
+  Arena wa(work, work_bytes);
+  BwdScratch sc;
+  sc.carve(wa, rows, kv_rows, static_cast<size_t>(B) * kHeads * (N > L ? N : L), X);
+  float* P = wa.take<float>(static_cast<size_t>(rows) * kH);
+  float* Q = wa.take<float>(static_cast<size_t>(rows) * kH);
+  ETP_REQUIRE(wa.off <= work_bytes, "backward_lang2visn: workspace too small");
+  DropCtx dc;
+  if (in.dropout) { dc.seed = in.dropout->seed; dc.p_hidden = in.dropout->p_hidden; dc.p_attn = in.dropout->p_attn; dc.p_head = in.dropout->p_head; }
+
+  const float* dx = d_lang_embeds;
+  const int ldkv = X * 2 * kH;
+  for (int i = X - 1; i >= 0; --i) {
+    const etp_layer_weights& lw = w.layers[i];
+    const etp_layer_weights& lg = g.layers[i];
+    const LayerRecord& r = rec.layers[i];
+    const bf16* x_in = i > 0 ? rec.layers[i - 1].xb : rec.txtb;
+    WgradBatch wb;
+    ETP_TRY(self_ffn_block_bwd(lw, lg, r, r.ab, dx, Q, B, L, in.txt_masks, nullptr, nullptr, nullptr, nullptr, nullptr, sc, wb,
+                               s, dc, kSiteL2V, i));
+    ETP_TRY(layernorm_bwd(Q, r.t1, lw.xln_g, r.st1, r.st1 + rows, rows, kH, sc.g0, 0, sc.gb, F(lg.xln_g), F(lg.xln_b), s,
+                          F(lg.xo_b), dc.hidden(drop_site(kSiteL2V, i, kDropXOut))));
+    ETP_TRY(wb.add(sc.gb, rows, kH, kH, r.ctx1, kH, kH, lg.xo_w, s));
+    const bool pdrop = dc.attn(0).thr != 0;
+    ETP_TRY(dgrad(sc.gb, rows, kH, kH, lw.xo_w, kH, nullptr, nullptr, sc.dctx, 0, nullptr, s,
+                  (lg.xkv_b && !pdrop) ? F(lg.xkv_b) + kH : nullptr));
+    AttnBwdArgs at;
+    at.B = B; at.heads = kHeads; at.Sq = L; at.Sk = N;
+    at.q = r.q; at.ldq = kH; at.k = r.kv; at.ldk = r.ldkv; at.v = r.kv + kH; at.ldv = r.ldkv;
+    at.out = r.ctx1; at.ldo = kH; at.dout = sc.dctx; at.lddo = kH; at.lse = r.lse1; at.dvec = sc.dvec;
+    at.scale = 0.125f; at.key_valid = in.gmap_masks; at.mask_value = -10000.0f;
+    bf16* dkv_i = sc.dkv + static_cast<size_t>(i) * 2 * kH;
+    at.dq = sc.dq; at.lddq = kH; at.dk = dkv_i; at.lddk = ldkv; at.dv = dkv_i + kH; at.lddv = ldkv;
+    {
+      const DropHost d = dc.attn(drop_site(kSiteL2V, i, kDropXAttn));
+      at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
+    }
+    ETP_TRY(attention_bwd_dispatch(at, s));
+    ETP_TRY(bias_grad(sc.dq, rows, kH, kH, lg.xq_b, s));
+    if (pdrop && lg.xkv_b) ETP_TRY(bias_grad(dkv_i + kH, kv_rows, kH, ldkv, F(lg.xkv_b) + kH, s));
+    ETP_TRY(wb.add(sc.dq, rows, kH, kH, x_in, kH, kH, lg.xq_w, s));
+    // dx_in = dq.Wq + dt1; the first layer's input is the caller's txt_embeds
+    float* dst = (i == 0 && d_txt_embeds) ? d_txt_embeds : P;
+    ETP_TRY(dgrad(sc.dq, rows, kH, kH, lw.xq_w, kH, sc.g0, dst, nullptr, 0, nullptr, s));
+    ETP_TRY(wb.flush(s));
+    dx = P;
+  }
+  // node side, all layers at once: kv_all = nodes . Wkv_all^T + b
+  ETP_TRY(wgrad(sc.dkv, kv_rows, ldkv, ldkv, rec.nodeb, kH, kH, const_cast<void*>(g.xkv_all_w), s));
+  ETP_TRY(dgrad(sc.dkv, kv_rows, ldkv, ldkv, w.xkv_all_w, kH, nullptr, sc.dtxt, nullptr, 0, nullptr, s));  // d(packed nodes)
+  ETP_TRY(node_pack_bwd(sc.dtxt, in.gmap_step_ids, in.gmap_pos_fts, rec.pos_lin, rec.pos_stats, w.pos_g, kv_rows, F(g.step_emb),
+                        F(g.pos_w), F(g.pos_b), F(g.pos_g), F(g.pos_bb), s));
+  if (d_gmap_img_fts)
+    ETP_CHECK_CUDA(cudaMemcpyAsync(d_gmap_img_fts, sc.dtxt, static_cast<size_t>(kv_rows) * kH * 4, cudaMemcpyDeviceToDevice, s));
+  return ETP_OK;
+}
+
 int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, const etp_pano_inputs& in,
                       const uint8_t* pano_masks, const float* d_pano_embeds, void* saved, size_t saved_bytes, void* work,
                       size_t work_bytes, float* d_rgb_fts, float* d_dep_fts, cudaStream_t s) {
@@ -406,6 +475,18 @@ ETP_API size_t etp_pano_bwd_work_bytes(int32_t B, int32_t V) {
 }
 ETP_API size_t etp_txt_bwd_work_bytes(int32_t B, int32_t L) {
   return work_bytes_for(static_cast<size_t>(B) * L, 0, static_cast<size_t>(B) * kHeads * L);
+}
+
+ETP_API size_t etp_l2v_bwd_work_bytes(int32_t B, int32_t N, int32_t L, int32_t num_x_layers) {
+  return work_bytes_for(static_cast<size_t>(B) * L, static_cast<size_t>(B) * N, static_cast<size_t>(B) * kHeads * (N > L ? N : L),
+                        num_x_layers > 0 ? num_x_layers : 1);
+}
+ETP_API int etp_backward_lang2visn(const etp_nav_weights* w, const etp_nav_weights* grads, const etp_nav_inputs* in,
+                                   const float* d_lang_embeds, void* saved, size_t saved_bytes, void* work,
+                                   size_t work_bytes, float* d_txt_embeds, float* d_gmap_img_fts, void* stream) {
+  ETP_REQUIRE(w && grads && in && d_lang_embeds && saved && work, "etp_backward_lang2visn: null argument");
+  return backward_lang2visn(*w, *grads, *in, d_lang_embeds, saved, saved_bytes, work, work_bytes, d_txt_embeds,
+                            d_gmap_img_fts, S(stream));
 }
 
 ETP_API int etp_backward_navigation(const etp_nav_weights* w, const etp_nav_weights* grads, const etp_nav_inputs* in,

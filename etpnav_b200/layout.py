@@ -19,7 +19,7 @@ from .spec import param_shapes
 
 def ordered_names(cfg: PlannerConfig):
     """Returns OrderedDict group -> [param names] with fused operands adjacent."""
-    g = OrderedDict(txt=[], pano=[], nav=[])
+    g = OrderedDict(txt=[], pano=[], nav=[], pre=[])
     t = g["txt"]
     # token_type_embeddings first: forward_panorama reads row 1 of it (vilmodel_cmt.py:709)
     t += ["embeddings.token_type_embeddings.weight", "embeddings.word_embeddings.weight",
@@ -80,6 +80,22 @@ def ordered_names(cfg: PlannerConfig):
     nv += ["global_sap_head.net.0.weight", "global_sap_head.net.0.bias",
            "global_sap_head.net.2.weight", "global_sap_head.net.2.bias",
            "global_sap_head.net.4.weight", "global_sap_head.net.4.bias"]
+    # pre-training twin only: appended as a fourth group so the offsets of the three navigation groups never move
+    pr = g["pre"]
+    if cfg.use_lang2visn_attn:
+        for i in range(cfg.num_x_layers):
+            p = f"global_encoder.encoder.x_layers.{i}."
+            pr += [p + f"lang_self_att.self.{n}.weight" for n in ("query", "key", "value")]
+            pr += [p + f"lang_self_att.self.{n}.bias" for n in ("query", "key", "value")]
+            pr += [p + "lang_self_att.output.dense.weight", p + "lang_self_att.output.dense.bias",
+                   p + "lang_self_att.output.LayerNorm.weight", p + "lang_self_att.output.LayerNorm.bias",
+                   p + "lang_inter.dense.weight", p + "lang_inter.dense.bias",
+                   p + "lang_output.dense.weight", p + "lang_output.dense.bias",
+                   p + "lang_output.LayerNorm.weight", p + "lang_output.LayerNorm.bias"]
+    if cfg.mlm_head:
+        pr += ["mlm_head.predictions.transform.dense.weight", "mlm_head.predictions.transform.dense.bias",
+               "mlm_head.predictions.transform.LayerNorm.weight", "mlm_head.predictions.transform.LayerNorm.bias",
+               "mlm_head.predictions.bias"]
     return g
 
 

@@ -82,4 +82,19 @@ def param_shapes(cfg: PlannerConfig) -> "OrderedDict[str, tuple]":
     _lin(d, "global_sap_head.net.0", H, H)
     _ln(d, "global_sap_head.net.2", H)
     _lin(d, "global_sap_head.net.4", 1, H)
+    # pre-training twin only (pretrain_src/pretrain_src/model/vilmodel.py:370-374; BertOnlyMLMHead :258-299)
+    if cfg.use_lang2visn_attn:
+        for i in range(cfg.num_x_layers):
+            p = f"global_encoder.encoder.x_layers.{i}."
+            for n in ("query", "key", "value"):
+                _lin(d, p + "lang_self_att.self." + n, H, H)
+            _lin(d, p + "lang_self_att.output.dense", H, H)
+            _ln(d, p + "lang_self_att.output.LayerNorm", H)
+            _lin(d, p + "lang_inter.dense", I, H)
+            _lin(d, p + "lang_output.dense", H, I)
+            _ln(d, p + "lang_output.LayerNorm", H)
+    if cfg.mlm_head:
+        _lin(d, "mlm_head.predictions.transform.dense", H, H)
+        _ln(d, "mlm_head.predictions.transform.LayerNorm", H)
+        d["mlm_head.predictions.bias"] = (cfg.vocab_size,)
     return d

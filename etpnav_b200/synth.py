@@ -141,3 +141,98 @@ def step_flops(cfg: PlannerConfig, B: int, V: int, N: int, L: int) -> dict:
     txt = cfg.num_l_layers * (8 * L * H * H + 4 * L * L * H + 4 * L * H * I)
     return dict(pano=B * pano, nav=B * nav, step_fwd=B * (pano + nav), txt=B * txt,
                 txt_kv=B * X * 4 * L * H * H)
+
+
+def make_traj_batch(cfg: PlannerConfig, B: int, T: int, V: int, L: int, seed: int = 0, mlm_prob: float = 0.15,
+                    ghosts: int = 3) -> dict:
+    """One PRE-TRAINING batch (CPU tensors / Python lists) with the keys ``mlm_collate`` / ``sap_collate`` produce
+    (pretrain_src/pretrain_src/data/tasks.py:98-138): a text, a trajectory of 1..T visited viewpoints per episode with up
+    to V views each (the first ones are the navigable candidates, as ``_aggregate_gmap_features`` assumes, vilmodel.py:600)
+    and the topological map built from it.  Viewpoint ids are strings; some episodes revisit their first viewpoint (the
+    reference keeps the LAST visit's feature), unvisited candidates are shared between steps (their features average),
+    and a candidate may be visited later (then it is a visited node)."""
+    g = torch.Generator().manual_seed(5000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    steps = [ri(1, T) for _ in range(B)]
+    steps[0] = T
+    traj_vpids, traj_cand_vpids, gmap_vpids, view_lens = [], [], [], []
+    for i in range(B):
+        path = [f"v{i}_{t}" for t in range(steps[i])]
+        if steps[i] >= 3 and i % 2 == 0:
+            path[2] = path[0]                      # revisit
+        ghost_ids = [f"u{i}_{k}" for k in range(ghosts)]
+        cands, visited_order, unvisited_order = [], [], []
+        for t in range(steps[i]):
+            vl = V if (i == 0 and t == 0) else ri(max(4, V // 2), V)
+            view_lens.append(vl)
+            c = []
+            if t + 1 < steps[i]:
+                c.append(path[t + 1])              # the next viewpoint is a candidate now, visited later
+            if t > 0:
+                c.append(path[t - 1])              # already visited: skipped by the aggregation
+            for k in range(ri(1, max(2, ghosts // 2))):
+                c.append(ghost_ids[ri(0, ghosts - 1)])
+            c = list(dict.fromkeys(c))[:vl]
+            cands.append(c)
+            if path[t] not in visited_order:
+                visited_order.append(path[t])
+        for c in cands:
+            for vp in c:
+                if vp not in visited_order and vp not in unvisited_order:
+                    unvisited_order.append(vp)
+        traj_vpids.append(path)
+        traj_cand_vpids.append(cands)
+        gmap_vpids.append([None] + visited_order + unvisited_order)
+    S = sum(steps)
+    vlens = torch.tensor(view_lens, dtype=torch.long)
+    vm = (torch.arange(V)[None] < vlens[:, None])
+    img = torch.randn(S, V, cfg.image_feat_size, generator=g) * vm[..., None]
+    dep = torch.randn(S, V, cfg.depth_feat_size, generator=g) * vm[..., None]
+    th = torch.rand(S, V, generator=g) * (2 * math.pi)
+    loc = torch.stack([th.sin(), th.cos(), torch.zeros_like(th), torch.ones_like(th)], -1) * vm[..., None]
+    nav_types = torch.zeros(S, V, dtype=torch.long)
+    k = 0
+    for i in range(B):
+        for t in range(steps[i]):
+            nav_types[k, :len(traj_cand_vpids[i][t])] = 1
+            k += 1
+    gmap_lens = torch.tensor([len(x) for x in gmap_vpids], dtype=torch.long)
+    N = int(gmap_lens.max())
+    gm = torch.arange(N)[None] < gmap_lens[:, None]
+    step_ids = torch.zeros(B, N, dtype=torch.long)
+    visited = torch.zeros(B, N, dtype=torch.bool)
+    labels = torch.zeros(B, dtype=torch.long)
+    for i in range(B):
+        nv = len(dict.fromkeys(traj_vpids[i]))
+        for n in range(1, 1 + nv):
+            step_ids[i, n] = max(t for t in range(steps[i]) if traj_vpids[i][t] == gmap_vpids[i][n]) + 1
+        visited[i, 1:1 + nv] = True
+        glen = int(gmap_lens[i])
+        labels[i] = ri(1 + nv, glen - 1) if (glen > 1 + nv and i % 3 != 2) else 0
+    a1 = torch.rand(B, N, generator=g) * (2 * math.pi)
+    a2 = torch.rand(B, N, generator=g) * (2 * math.pi)
+    pos = torch.stack([a1.sin(), a1.cos(), a2.sin(), a2.cos(), torch.rand(B, N, generator=g), torch.rand(B, N, generator=g),
+                       torch.randint(0, 10, (B, N), generator=g).float() / 10.0], -1) * gm[..., None]
+    pos[:, 0] = 0
+    pd = torch.rand(B, N, N, generator=g)
+    pd = 0.5 * (pd + pd.transpose(1, 2)) * gm[:, :, None] * gm[:, None, :] * (1 - torch.eye(N))[None]
+    pd[:, 0, :] = 0
+    pd[:, :, 0] = 0
+    txt_lens = _lens(g, B, max(4, L // 2), L)
+    tm = torch.arange(L)[None] < txt_lens[:, None]
+    ids = torch.randint(1000, cfg.vocab_size, (B, L), generator=g)
+    ids[:, 0] = 101
+    sel = (torch.rand(B, L, generator=g) < mlm_prob) & tm
+    sel[:, 0] = False
+    sel[0, 1] = True                                # at least one masked token
+    txt_labels = torch.where(sel, ids, torch.full_like(ids, -1))
+    ids = torch.where(sel, torch.full_like(ids, 103), ids)
+    ids = torch.where(tm, ids, torch.zeros_like(ids))
+    return dict(
+        txt_ids=ids, txt_lens=txt_lens, txt_labels=txt_labels,
+        traj_view_img_fts=img.contiguous(), traj_view_dep_fts=dep.contiguous(), traj_obj_img_fts=None,
+        traj_loc_fts=loc.contiguous(), traj_nav_types=nav_types, traj_step_lens=steps, traj_vp_view_lens=vlens,
+        traj_vp_obj_lens=None, traj_vpids=traj_vpids, traj_cand_vpids=traj_cand_vpids,
+        gmap_lens=gmap_lens, gmap_step_ids=step_ids, gmap_pos_fts=pos.contiguous(), gmap_pair_dists=pd.contiguous(),
+        gmap_vpids=gmap_vpids, gmap_visited_masks=visited, global_act_labels=labels, local_act_labels=None,
+    )

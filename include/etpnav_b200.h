@@ -337,6 +337,35 @@ int etp_adamw_step(float* param, void* param_bf16, const float* grad, float* exp
                    float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                    void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * pre-training twin: GlocalTextPathCMT of pretrain_src/pretrain_src/model/vilmodel.py:656-754.
+ * Its `forward` is the composition etp_forward_txt -> etp_forward_panorama over the (sum of steps) x views
+ * trajectory batch (ImageEmbeddings.forward, :488-534) -> etp_segment_gather (_aggregate_gmap_features, :585-619)
+ * -> etp_forward_navigation; `forward_mlm` (:713-754) replaces the last call by etp_forward_lang2visn.
+ * ------------------------------------------------------------------------------------------- */
+/* out[s, :] = sum_{k in [seg_ptr[s], seg_ptr[s+1])} weight[k] * src[index[k], :]   (rows of `width` floats, width % 4 == 0;
+ * an empty segment writes zeros).  Forward of _aggregate_gmap_features with the host-built CSR of the reference's
+ * visited / unvisited dictionaries (weight = 1/len), its backward with the transposed structure, and the
+ * masked-token gather of _compute_masked_hidden (pretrain_cmt.py:160-164) with unit weights. */
+int etp_segment_gather(const float* src, const int32_t* seg_ptr, const int32_t* index, const float* weight,
+                       int32_t num_segments, int32_t width, float* out, void* stream);
+
+/* GraphLXRTXLayer.forward_lang2visn stacked over the x-layers as GlocalTextPathCMT.forward_mlm drives it
+ * (vilmodel.py:400-411,733-741): the instruction tokens query the packed map nodes (visual_attention weights,
+ * key mask = gmap_masks), then lang_self_att / lang_inter / lang_output over the tokens.
+ * `w` is an etp_nav_weights whose layers[i].{sqkv,so,sln,f1,f2,fln}* point at the lang_* parameters of x-layer i
+ * (x* members: visual_attention, as for navigation); sap* / sprel* are ignored.  `in` is the navigation input
+ * struct (gmap_visited_masks / gmap_pair_dists ignored).  Output: lang_embeds fp32 [B,L,768]. */
+size_t etp_l2v_saved_bytes(int32_t B, int32_t N, int32_t L, int32_t num_x_layers, int32_t training);
+int etp_forward_lang2visn(const etp_nav_weights* w, const etp_nav_inputs* in, float* lang_embeds, void* saved,
+                          size_t saved_bytes, int32_t training, void* stream);
+size_t etp_l2v_bwd_work_bytes(int32_t B, int32_t N, int32_t L, int32_t num_x_layers);
+/* d_lang_embeds [B,L,768] -> d_txt_embeds [B,L,768], d_gmap_img_fts [B,N,768] (overwritten; either may be NULL)
+ * + parameter gradients accumulated through `grads`. */
+int etp_backward_lang2visn(const etp_nav_weights* w, const etp_nav_weights* grads, const etp_nav_inputs* in,
+                           const float* d_lang_embeds, void* saved, size_t saved_bytes, void* work, size_t work_bytes,
+                           float* d_txt_embeds, float* d_gmap_img_fts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

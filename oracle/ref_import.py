@@ -62,3 +62,60 @@ def build_reference(cfg, state_dict=None):
         assert not unexpected, unexpected
         assert all("position_ids" in m for m in missing), missing
     return model
+
+
+# ----------------------------------------------------------------------------------------------------
+# pre-training twin (pretrain_src/pretrain_src/model): SURVEY.md §8c, second half of the import recipe
+# ----------------------------------------------------------------------------------------------------
+def load_pretrain():
+    """Import ``model.vilmodel`` / ``model.pretrain_cmt`` of the reference's pre-training tree with two class-attribute
+    shims for transformers 5.x: the ``init_weights`` idiom (as above) and ``tie_weights`` (pretrain_cmt.py:79-82 calls
+    the removed ``_tie_or_clone_weights``; the shim shares the Parameter, which is what that helper did)."""
+    root = REF + "/pretrain_src/pretrain_src"
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    sys.dont_write_bytecode = True
+    from transformers import PreTrainedModel
+    from model import vilmodel, pretrain_cmt
+    _orig = PreTrainedModel.init_weights
+
+    def _init_weights_compat(self):
+        return self.post_init() if not hasattr(self, "all_tied_weights_keys") else _orig(self)
+
+    def _tie(self, *a, **k):
+        if "mlm" in self.config.pretrain_tasks:
+            self.mlm_head.predictions.decoder.weight = self.bert.embeddings.word_embeddings.weight
+
+    vilmodel.GlocalTextPathCMT.init_weights = _init_weights_compat
+    pretrain_cmt.GlocalTextPathCMTPreTraining.init_weights = _init_weights_compat
+    pretrain_cmt.GlocalTextPathCMTPreTraining.tie_weights = _tie
+    return vilmodel, pretrain_cmt
+
+
+def ref_key(k):
+    """planner-namespace key -> key of ``GlocalTextPathCMTPreTraining.state_dict()``."""
+    return k if k.startswith(("mlm_head.", "global_sap_head.")) else "bert." + k
+
+
+def build_pretrain_reference(cfg, state_dict=None):
+    """Instantiate the reference ``GlocalTextPathCMTPreTraining`` (pretrain_cmt.py:50) for a PlannerConfig with
+    ``use_lang2visn_attn`` / ``mlm_head`` set, tasks mlm + sap (run_pt/r2r_pretrain_habitat.json)."""
+    from transformers import PretrainedConfig
+    _, pretrain_cmt = load_pretrain()
+    hf = PretrainedConfig.from_json_file(REF + "/pretrain_src/run_pt/r2r_model_config_dep.json")
+    hf.pretrain_tasks = ["mlm", "sap"]
+    for k in ("vocab_size", "max_position_embeddings", "type_vocab_size", "layer_norm_eps", "hidden_dropout_prob",
+              "attention_probs_dropout_prob", "pred_head_dropout_prob", "max_action_steps", "image_feat_size",
+              "depth_feat_size", "angle_feat_size", "num_l_layers", "num_pano_layers", "num_x_layers", "graph_sprels",
+              "update_lang_bert", "use_lang2visn_attn"):
+        setattr(hf, k, getattr(cfg, k))
+    if not cfg.use_depth_embedding:
+        hf.depth_feat_size = 0
+    model = pretrain_cmt.GlocalTextPathCMTPreTraining(hf)
+    if state_dict is not None:
+        sd = {ref_key(k): v for k, v in state_dict.items()}
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected, unexpected
+        assert all("position_ids" in m or m == "mlm_head.predictions.decoder.weight" for m in missing), missing
+        model.tie_weights()
+    return model
