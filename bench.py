@@ -58,6 +58,9 @@ def parse():
                     help="also time the oracle port in eager PyTorch on this GPU (fp32 and bf16 autocast): the "
                          "'reference GPU eager' figure the north_star's >=10x target is stated against")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel CUDA-event table of the profiled pass here")
+    ap.add_argument("--workload", default="planner", choices=["planner", "pretrain", "packing"],
+                    help="planner (default, BASELINE.json's metric) | pretrain (SURVEY.md 8f N2: one pre-training iteration "
+                         "of the twin, mlm and sap alternating) | packing (8f N3: the per-step map / view packing)")
     return ap.parse_args()
 
 
@@ -263,10 +266,160 @@ def run_reference_arm(a, mode, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+# secondary workloads: same timing rules, their own metric names, single GPU
+# ------------------------------------------------------------------------------------------------
+def _timed_events(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_pretrain_workload(a):
+    """One pre-training iteration = one task batch (mlm, then sap, alternating as mix_ratio 1:1 of
+    run_pt/r2r_pretrain_habitat.json) forward + backward + AdamW at train_batch_size 32, <= 7 viewpoints x 36 views per
+    episode, <= 100 tokens, 9 language / 2 panorama / 4 cross-modal layers, train() dropout on."""
+    from etpnav_b200 import lib as L
+    from etpnav_b200.pretrain import B200PreTraining, PretrainTrainer
+    from etpnav_b200.synth import make_traj_batch
+    torch.cuda.set_device(0)
+    L.require_device()
+    cfg = PlannerConfig(vocab_size=30522, num_l_layers=9, num_x_layers=4, use_lang2visn_attn=True, mlm_head=True)
+    model = B200PreTraining(cfg, device="cuda").train()
+    sd = make_weights(cfg, seed=0)
+    model.bert.load_state_dict(sd, strict=True)
+    host = make_traj_batch(cfg, 32, 7, 36, 100, seed=3, ghosts=20)
+    dev_batch = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+    tr = PretrainTrainer(model, world_size=1)
+    lib = L.lib()
+    lib.etp_launch_count.restype = __import__("ctypes").c_longlong
+    state = {"i": 0}
+
+    def it(batch=dev_batch):
+        tr.step(batch, "mlm" if state["i"] % 2 == 0 else "sap")
+        state["i"] += 1
+
+    ms = _timed_events(it, max(2, a.steps // 2 * 2), max(4, a.warmup))
+    n0 = lib.etp_launch_count()
+    it(); it()
+    launches = (lib.etp_launch_count() - n0) / 2
+
+    pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+
+    def e2e_it():   # host batch: every tensor crosses PCIe inside the timed region, the loss comes back
+        d = {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in pinned.items()}
+        tr.step(d, "mlm" if state["i"] % 2 == 0 else "sap").item()
+        state["i"] += 1
+    e2e_ms = _timed_events(e2e_it, max(2, a.steps // 2 * 2), 2)
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if isinstance(v, torch.Tensor))
+    cpu = None
+    if not a.no_cpu_baseline:
+        from oracle import pretrain_port as PP  # test infrastructure, used here only as the timed CPU baseline
+        cores = min(_host_cores(), 32)
+        torch.set_num_threads(cores)
+        sdc = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        opt = torch.optim.AdamW(list(sdc.values()), lr=5e-5, betas=(0.9, 0.98), weight_decay=0.01)
+        ts = []
+        for task in ("mlm", "sap", "mlm", "sap"):
+            t0 = time.perf_counter()
+            opt.zero_grad(set_to_none=True)
+            (PP.task_mlm(sdc, cfg, host) if task == "mlm" else PP.task_sap(sdc, cfg, host)).mean().backward()
+            opt.step()
+            ts.append(time.perf_counter() - t0)
+        med = (ts[2] + ts[3]) / 2
+        cpu = {"value": 1.0 / med, "unit": "iterations/s", "cores": cores, "kind": "port",
+               "sample": "one mlm + one sap iteration after one warm-up pair; oracle/pretrain_port.py fp32 autograd + torch AdamW"}
+    line = {"metric": "pre-training iterations/sec (B=32, <=7 viewpoints x 36 views, <=100 tokens; mlm/sap alternating)",
+            "value": 1e3 / ms, "unit": "iterations/s", "n_gpus": 1, "steps": max(2, a.steps // 2 * 2), "warmup": max(4, a.warmup),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "GlocalTextPathCMTPreTraining iteration: fwd+bwd+AdamW, tasks mlm and sap alternating, "
+                                   "train() dropout on, 9/2/4 layers, vocab 30522",
+                       "view_tokens": int(host["traj_view_img_fts"].shape[0] * 36), "nodes": int(host["gmap_step_ids"].shape[1]),
+                       "masked_tokens": int((host["txt_labels"] != -1).sum())},
+            "e2e": {"value": 1e3 / e2e_ms, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def run_packing_workload(a):
+    """One packing step = ETPTrainer._nav_gmap_variable for B=64 environments whose maps hold about 80 nodes
+    (15 visited + 64 ghosts + [stop]): host flattening + H2D + etp_gmap_pack + the image-feature gather, against the
+    oracle port of the reference's Python loops on the host."""
+    import types
+    import numpy as np
+    from etpnav_b200 import lib as L
+    from etpnav_b200 import packing
+    torch.cuda.set_device(0)
+    L.require_device()
+    rng = np.random.default_rng(0)
+    B, n, g = a.batch, 15, 64
+    gms, cur_vp, cur_pos, cur_ori = [], [], [], []
+    for e in range(B):
+        nid, gid = [str(k) for k in range(n)], [f"g{k}" for k in range(g)]
+        P = rng.normal(0, 5, (n, 3))
+        D = np.linalg.norm(P[:, None] - P[None], axis=-1)
+        gms.append(types.SimpleNamespace(
+            node_pos={v: P[k] for k, v in enumerate(nid)}, ghost_pos={v: None for v in gid},
+            ghost_aug_pos={v: rng.normal(0, 5, 3) for v in gid}, node_stepId={v: k + 1 for k, v in enumerate(nid)},
+            ghost_fronts={v: [nid[int(f)] for f in rng.integers(0, n, 2)] for v in gid},
+            shortest_dist={x: {y: float(D[i, j]) for j, y in enumerate(nid)} for i, x in enumerate(nid)},
+            shortest_path={x: {y: [0] * (1 + abs(i - j)) for j, y in enumerate(nid)} for i, x in enumerate(nid)},
+            node_embeds={v: torch.randn(768, device="cuda") for v in nid},
+            ghost_embeds={v: [torch.randn(768, device="cuda"), 2] for v in gid}))
+        cur_vp.append(nid[-1]); cur_pos.append(P[-1]); cur_ori.append(np.array([0.0, 0.6, 0.0, 0.8]))
+    meta, f64, i32b, _, n_max, max_g = packing.flatten_gmaps(gms, cur_vp, cur_pos, cur_ori)
+    kern_ms = _timed_events(lambda: packing.pack_gmap_geometry(meta, f64, i32b, n_max, max_g, "cuda"), a.steps, max(3, a.warmup))
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        out = packing.pack_gmap(gms, cur_vp, cur_pos, cur_ori, "cuda")
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    from oracle import packing_port as PK  # test infrastructure: the reference's loops restated, timed as the CPU baseline
+    sts = [PK.MapState.from_graph_map(gm) for gm in gms]
+    ne = [[gm.node_embeds[v].cpu() for v in gm.node_pos] for gm in gms]
+    ge = [[(gm.ghost_embeds[v][0].cpu(), 2) for v in gm.ghost_pos] for gm in gms]
+    t0 = time.perf_counter()
+    PK.nav_gmap_variable(sts, [n - 1] * B, cur_pos, cur_ori, ne, ge)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    out_bytes = B * n_max * (n_max + 7) * 4 + B * n_max * 10
+    line = {"metric": f"map packs/sec (B={B} environments, {n_max} nodes each)", "value": 1e3 / e2e_ms, "unit": "packs/s",
+            "n_gpus": 1, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": e2e_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64->f32", "data": "synthetic",
+            "config": {"workload": "ETPTrainer._nav_gmap_variable replacement: flatten + H2D + etp_gmap_pack + image-feature gather",
+                       "host_flatten_plus_kernel_ms": e2e_ms, "h2d_plus_kernel_ms": kern_ms},
+            "e2e": {"value": 1e3 / e2e_ms, "unit": "packs/s", "h2d_bytes_per_step": int(meta.nbytes + f64.nbytes + i32b.nbytes),
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 3,
+            "roofline": {"bound": "hbm", "kernel": "gmap_pack_kernel", "achieved": None, "peak": None, "unit": "GB/s", "frac": None,
+                         "traffic": None, "note": f"{out_bytes} output bytes per launch: latency-bound at this size (one CTA per environment)"},
+            "cpu_baseline": {"value": 1e3 / cpu_ms, "unit": "packs/s", "cores": 1, "kind": "port",
+                             "sample": "one full-size call of oracle/packing_port.py:nav_gmap_variable (the reference's Python loops)"}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def main():
     a = parse()
+    if a.workload == "pretrain":
+        return run_pretrain_workload(a)
+    if a.workload == "packing":
+        return run_packing_workload(a)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -362,26 +362,36 @@ class _MlmHeadFn(torch.autograd.Function):
         V = m.config.vocab_size
         dev = xb.device
         ldp = _pad64(V)
+        direct = m._direct_grad is not None   # PretrainTrainer: accumulate straight into the flat gradient buffer
+
+        def target(name, shape):
+            if direct:
+                off, numel, shp = m.layout.entries[name]
+                return m._direct_grad[off:off + numel].view(shp)
+            return torch.zeros(shape, device=dev, dtype=torch.float32)
+
         dl = d_logits.contiguous().float()
         dlb = torch.zeros(M, ldp, device=dev, dtype=torch.bfloat16)
         dlb[:, :V].copy_(dl)
-        d_bias = torch.zeros(V, device=dev, dtype=torch.float32)
-        _L.colsum(dl, d_bias)
-        d_emb = torch.empty(V, H, device=dev, dtype=torch.float32)
-        _L.gemm(dlb, hb, a_mn=True, b_mn=True, out_f32=d_emb, M=V, N=H, K=M)              # dW_dec = dlogits^T . h
+        d_bias = target("mlm_head.predictions.bias", (V,))
+        _L.colsum(dl, d_bias)                                                               # += column sums
+        d_emb = target("embeddings.word_embeddings.weight", (V, H))
+        _L.gemm(dlb, hb, a_mn=True, b_mn=True, out_f32=d_emb, resid=d_emb, M=V, N=H, K=M)  # dW_dec += dlogits^T . h
         dh = torch.empty(M, H, device=dev, dtype=torch.float32)
         _L.gemm(dlb, Wemb, b_mn=True, out_f32=dh, M=M, N=H, K=V)                           # dh = dlogits . W_dec
         dg = torch.empty(M, H, device=dev, dtype=torch.float32)
-        d_gamma = torch.zeros(H, device=dev, dtype=torch.float32)
-        d_beta = torch.zeros(H, device=dev, dtype=torch.float32)
+        d_gamma = target("mlm_head.predictions.transform.LayerNorm.weight", (H,))
+        d_beta = target("mlm_head.predictions.transform.LayerNorm.bias", (H,))
         _L.layernorm_bwd(dh, g, ln_g, mean, rstd, dg, dgamma=d_gamma, dbeta=d_beta)
         dtb = (dg * gp.float()).to(torch.bfloat16)                                           # * gelu'(pre): [M,768] glue
-        d_db = torch.zeros(H, device=dev, dtype=torch.float32)
+        d_db = target("mlm_head.predictions.transform.dense.bias", (H,))
         _L.colsum(dtb, d_db)
-        d_dw = torch.empty(H, H, device=dev, dtype=torch.float32)
-        _L.gemm(dtb, xb, a_mn=True, b_mn=True, out_f32=d_dw, M=H, N=H, K=M)
+        d_dw = target("mlm_head.predictions.transform.dense.weight", (H, H))
+        _L.gemm(dtb, xb, a_mn=True, b_mn=True, out_f32=d_dw, resid=d_dw, M=H, N=H, K=M)
         dx = torch.empty(M, H, device=dev, dtype=torch.float32)
         _L.gemm(dtb, Wd, b_mn=True, out_f32=dx, M=M, N=H, K=H)
+        if direct:
+            return None, dx, None, None, None, None, None, None
         return None, dx, d_dw, d_db, d_gamma, d_beta, d_bias, d_emb
 
 
@@ -480,3 +490,43 @@ class B200PreTraining(nn.Module):
         if compute_loss:
             return F.cross_entropy(global_logits, labels, reduction="none")
         return global_logits, labels
+
+
+class PretrainTrainer:
+    """Fused pre-training iteration (pretrain_src/pretrain_src/train_r2r.py:231-297): one task batch forward + backward
+    through the step-level C calls with every parameter gradient accumulated straight into ONE flat fp32 buffer, one NCCL
+    all-reduce of that buffer when data-parallel (the reference wraps the model in DDP, train_r2r.py:113-116), and the
+    fused AdamW of the navigation trainer over the whole flat parameter buffer (betas (0.9, 0.98), weight decay 0.01 as
+    run_pt/r2r_pretrain_habitat.json; the reference's no-decay list for biases / LayerNorm and its grad-norm clipping are
+    not reproduced)."""
+
+    def __init__(self, model: "B200PreTraining", lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, world_size=1):
+        self.model, self.m = model, model.bert
+        self.lr, self.betas, self.eps, self.wd, self.world = lr, betas, eps, weight_decay, world_size
+        m = self.m
+        m._refresh_cache()
+        dev = m._flat.device
+        n = m.layout.total
+        m._direct_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.t = 0
+        _L.lib().etp_adamw_step.argtypes = [p_void, p_void, p_void, p_void, p_void, C.c_int64, C.c_float, C.c_float,
+                                            C.c_float, C.c_float, C.c_float, i32, C.c_float, p_void]
+
+    def step(self, batch, task):
+        m = self.m
+        m._direct_grad.zero_()
+        loss = self.model(batch, task, compute_loss=True).mean()
+        loss.backward()
+        scale = 1.0
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(m._direct_grad, op=dist.ReduceOp.SUM)
+            scale = 1.0 / self.world
+        self.t += 1
+        _L._check(_L.lib().etp_adamw_step(_L.ptr(m._flat), _L.ptr(m._flat_bf16), _L.ptr(m._direct_grad), _L.ptr(self.exp_avg),
+                                          _L.ptr(self.exp_avg_sq), m.layout.total, self.lr, self.betas[0], self.betas[1],
+                                          self.eps, self.wd, self.t, scale, _L.stream_ptr()), "etp_adamw_step")
+        m._bf16_fresh = True
+        return loss

@@ -366,6 +366,23 @@ int etp_backward_lang2visn(const etp_nav_weights* w, const etp_nav_weights* grad
                            const float* d_lang_embeds, void* saved, size_t saved_bytes, void* work, size_t work_bytes,
                            float* d_txt_embeds, float* d_gmap_img_fts, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * caller-side packing: the numeric half of ETPTrainer._nav_gmap_variable
+ * (vlnce_baselines/ss_trainer_ETP.py:344-417) with GraphMap.get_pos_fts / front_to_ghost_dist
+ * (vlnce_baselines/models/graph_utils.py:258-322), one launch for the whole batch of environments.
+ * The host flattens each GraphMap into two blobs (etpnav_b200/packing.py shows the layout a binding produces):
+ *   meta[env]  = {n_nodes, n_ghosts, cur_node, off_f64, off_i32, nnz_fronts, 0, 0}          (int32, device)
+ *   f64 @off   = cur_pos[3], base_heading, node_pos[3n], ghost_aug_pos[3g], shortest_dist[n*n]
+ *   i32 @off   = node_stepId[n], front_ptr[g+1], front_idx[nnz], len(shortest_path)[n*n]
+ * Outputs are the padded tensors of the reference, [B, n_max] / [B, n_max, 7] / [B, n_max, n_max], rows
+ * [stop], nodes, ghosts, zero padding: gmap_step_ids int64, gmap_visited_masks / gmap_masks uint8 (bool storage),
+ * gmap_pos_fts and gmap_pair_dists fp32.  Distances are bit-identical to the reference's numpy (double arithmetic in
+ * the same operation order, rounded once to fp32); sin / cos of the float32-rounded angles are within 1 ulp.
+ * The image-feature half (stack / pad of node and ghost embeddings, :362-366,399) is etp_segment_gather. */
+int etp_gmap_pack(const int32_t* meta, const double* f64_blob, const int32_t* i32_blob, int32_t B, int32_t n_max,
+                  int32_t max_ghosts, int64_t* gmap_step_ids, uint8_t* gmap_visited_masks, uint8_t* gmap_masks,
+                  float* gmap_pos_fts, float* gmap_pair_dists, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,3 +119,66 @@ def build_pretrain_reference(cfg, state_dict=None):
         assert all("position_ids" in m or m == "mlm_head.predictions.decoder.weight" for m in missing), missing
         model.tie_weights()
     return model
+
+
+# ----------------------------------------------------------------------------------------------------
+# caller-side packing: graph_utils.GraphMap and two ETPTrainer methods
+# ----------------------------------------------------------------------------------------------------
+def load_graph_utils():
+    """Import ``vlnce_baselines/models/graph_utils.py`` unmodified.  Its module-level imports of matplotlib (unused) and
+    habitat-lab 0.1.7 (three small geometry helpers used by ``heading_from_quaternion``) are absent here and are
+    provided as stub modules restating the published helpers (oracle/packing_port.py)."""
+    from . import packing_port as PK
+    import numpy as np
+    load_vilmodel()  # registers the namespace packages
+
+    def mod(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(sys.modules[name], k, v)
+
+    class _Quat:  # the slice of numpy-quaternion the reference touches: inverse() and being passed back to the helpers
+        def __init__(self, q):
+            self.q = np.asarray(q, dtype=np.float64)  # (w, x, y, z)
+
+        def inverse(self):
+            return _Quat(PK.quat_inverse(self.q))
+
+    mod("matplotlib")
+    mod("matplotlib.pyplot")
+    mod("habitat")
+    mod("habitat.tasks")
+    mod("habitat.utils")
+    mod("habitat.tasks.utils", cartesian_to_polar=lambda x, y: (np.sqrt(x ** 2 + y ** 2), np.arctan2(y, x)))
+    mod("habitat.utils.geometry_utils",
+        quaternion_from_coeff=lambda c: _Quat([c[3], c[0], c[1], c[2]]),
+        quaternion_rotate_vector=lambda quat, v: PK.quaternion_rotate_vector(quat.q, v))
+    from vlnce_baselines.models import graph_utils
+    return graph_utils
+
+
+def load_trainer_packers():
+    """The UNMODIFIED bodies of ``ETPTrainer._vp_feature_variable`` / ``_nav_gmap_variable``
+    (vlnce_baselines/ss_trainer_ETP.py:308-417), compiled from the reference source (the module itself imports Habitat
+    and cannot be imported).  Returned as plain functions taking ``self`` first."""
+    import ast
+    import numpy as np
+    import torch
+    from torch.nn.utils.rnn import pad_sequence
+    gu = load_graph_utils()
+    from vlnce_baselines.common.ops import gen_seq_masks, pad_tensors_wgrad
+    path = REF + "/vlnce_baselines/ss_trainer_ETP.py"
+    tree = ast.parse(open(path).read())
+    ns = dict(torch=torch, np=np, pad_sequence=pad_sequence, pad_tensors_wgrad=pad_tensors_wgrad,
+              gen_seq_masks=gen_seq_masks, MAX_DIST=gu.MAX_DIST)
+    out = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in ("_vp_feature_variable", "_nav_gmap_variable"):
+            m = ast.Module(body=[node], type_ignores=[])
+            exec(compile(m, path, "exec"), ns)
+            out[node.name] = ns[node.name]
+    assert len(out) == 2
+    return out

@@ -88,3 +88,16 @@ def test_mlm_and_sap_graph_wiring(stub):
                                       "gmap_pos_fts", "gmap_pair_dists", "gmap_vpids")])
     assert scores.shape == (n_masked, cfg.vocab_size) and logits.shape == b["gmap_step_ids"].shape
     assert emb.shape == (*b["gmap_step_ids"].shape, 768)
+
+
+def test_trainer_wiring(stub):
+    from etpnav_b200.pretrain import B200PreTraining, PretrainTrainer
+    cfg = PlannerConfig(vocab_size=2048, num_l_layers=1, num_x_layers=2)
+    model = B200PreTraining(cfg, device="cpu").train()
+    b = make_traj_batch(cfg, 2, 3, 6, 12, seed=1)
+    tr = PretrainTrainer(model, world_size=1)
+    for task in ("mlm", "sap"):
+        loss = tr.step(b, task)
+        assert loss.dim() == 0
+    assert tr.t == 2 and "etp_adamw_step" in stub.calls
+    assert all(p.grad is None for p in model.bert._pmap.values())   # gradients live in the flat buffer only

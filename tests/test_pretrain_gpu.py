@@ -148,3 +148,36 @@ def test_twin_backward_matches_reference_fixture(name):
     _report(**rep)
     assert rep["d_view_img"] < REL_L2_ACT, rep
     assert not rep["fails"], rep["fails"][:8]
+
+
+def test_pretrain_trainer_matches_autograd_and_learns():
+    """PretrainTrainer accumulates every gradient straight into the flat buffer: it must equal what autograd collects
+    parameter by parameter for the same batch (dropout off), and a few iterations on one batch must reduce both losses."""
+    from etpnav_b200.pretrain import PretrainTrainer
+    gold, cfg, sd, b = load("pt_small")
+    no_dropout(cfg)
+    d = _cuda(b)
+    m = _model(cfg, sd, train=True)
+    m(d, "mlm").mean().backward()
+    ref = {k: p.grad.clone() for k, p in m.bert._pmap.items() if p.grad is not None}
+    m2 = _model(cfg, sd, train=True)
+    tr = PretrainTrainer(m2, lr=0.0, weight_decay=0.0)
+    first = {t: tr.step(d, t).item() for t in ("mlm", "sap")}
+    tr.m._direct_grad.zero_()
+    m2(d, "mlm").mean().backward()
+    torch.cuda.synchronize()
+    lay = m2.bert.layout
+    for k, g in ref.items():
+        off, numel, shape = lay.entries[k]
+        got = tr.m._direct_grad[off:off + numel].view(shape)
+        denom = g.norm().clamp_min(1e-12)
+        assert ((got - g).norm() / denom).item() < 1e-3, k     # same kernels, same order: fp32 atomics noise only
+    tr.lr = 1e-4
+    for _ in range(8):
+        for t in ("mlm", "sap"):
+            last_t = tr.step(d, t).item()
+            first.setdefault("last_" + t, 0.0)
+            first["last_" + t] = last_t
+    torch.cuda.synchronize()
+    _report(kind="pretrain_trainer", **first)
+    assert first["last_mlm"] < first["mlm"] and first["last_sap"] < first["sap"], first
