@@ -28,6 +28,7 @@ def _declare():
     if not _declared:
         _L.lib().etp_gmap_pack.argtypes = [p_void, p_void, p_void, i32, i32, i32, p_void, p_void, p_void, p_void, p_void,
                                            p_void]
+        _L.lib().etp_segment_gather_rows.argtypes = [p_void, p_void, p_void, p_void, i32, i32, p_void, p_void]
         _declared = True
 
 
@@ -121,8 +122,20 @@ def pack_gmap_img_fts(gmaps, n_max, device):
             idx.append(len(rows)); wt.append(1.0 / gm.ghost_embeds[vp][1]); rows.append(gm.ghost_embeds[vp][0])
             ptr.append(len(idx)); k += 1
         ptr.extend([len(idx)] * (n_max - k))
-    pool = torch.stack(rows, 0).to(device)
     csr = Csr(np.asarray(ptr, dtype=np.int32), np.asarray(idx, dtype=np.int32), np.asarray(wt, dtype=np.float32), len(rows))
+    device = torch.device(device)
+    no_grad = not torch.is_grad_enabled() or not any(r.requires_grad for r in rows)
+    if no_grad and device.type == "cuda" and all(r.is_cuda and r.dtype == torch.float32 and r.is_contiguous() for r in rows):
+        # inference: read every node / ghost tensor where it lives (table of row pointers), no stacking copy
+        _declare()
+        table = _to_device(np.fromiter((r.data_ptr() for r in rows), dtype=np.int64, count=len(rows)), torch.int64, device)
+        d_ptr, d_idx, d_wt = csr.to(device)
+        out = torch.empty(csr.num_segments, rows[0].shape[0], device=device, dtype=torch.float32)
+        _L._check(_L.lib().etp_segment_gather_rows(_L.ptr(table), _L.ptr(d_ptr), _L.ptr(d_idx), _L.ptr(d_wt),
+                                                   csr.num_segments, rows[0].shape[0], _L.ptr(out), _L.stream_ptr()),
+                  "etp_segment_gather_rows")
+        return out.view(len(gmaps), n_max, rows[0].shape[0])
+    pool = torch.stack(rows, 0).to(device)
     return segment_gather(pool, csr).view(len(gmaps), n_max, pool.shape[1])
 
 

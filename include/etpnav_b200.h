@@ -350,6 +350,11 @@ int etp_adamw_step(float* param, void* param_bf16, const float* grad, float* exp
 int etp_segment_gather(const float* src, const int32_t* seg_ptr, const int32_t* index, const float* weight,
                        int32_t num_segments, int32_t width, float* out, void* stream);
 
+/* The same gather with one device pointer per source row (`rows[index[k]]`, each `width` floats, 16-byte aligned): reads
+ * the per-node tensors of a GraphMap where they live (inference path of the map image features, no stacking copy). */
+int etp_segment_gather_rows(const float* const* rows, const int32_t* seg_ptr, const int32_t* index, const float* weight,
+                            int32_t num_segments, int32_t width, float* out, void* stream);
+
 /* GraphLXRTXLayer.forward_lang2visn stacked over the x-layers as GlocalTextPathCMT.forward_mlm drives it
  * (vilmodel.py:400-411,733-741): the instruction tokens query the packed map nodes (visual_attention weights,
  * key mask = gmap_masks), then lang_self_att / lang_inter / lang_output over the tokens.

@@ -2,7 +2,7 @@
 # gpurun payload: new-row tests, secondary bench workloads, the main bench line, ncu launch list + GEMM full capture.
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_report.jsonl
-timeout 600 python -m pytest tests/test_pretrain_gpu.py tests/test_packing_gpu.py -q -m gpu --timeout 300 --timeout-method=thread > gpurun_out/pytest_new.txt 2>&1
+timeout 600 python -m pytest tests/test_pretrain_gpu.py tests/test_packing_gpu.py tests/test_shapes_gpu.py -q -m gpu --timeout 300 --timeout-method=thread > gpurun_out/pytest_new.txt 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_new.txt
 tail -40 gpurun_out/pytest_new.txt
 timeout 400 python bench.py --workload pretrain --steps 10 --warmup 4 > gpurun_out/bench_pretrain.json 2> gpurun_out/bench_pretrain.err

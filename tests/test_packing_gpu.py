@@ -30,6 +30,10 @@ def test_pack_gmap_matches_reference(name):
     assert torch.equal(pos[..., 4:], rp[..., 4:])
     assert (pos[..., :4] - rp[..., :4]).abs().max().item() <= 2.4e-7
     torch.testing.assert_close(out["gmap_img_fts"].cpu(), ref["gmap_img_fts"], rtol=1e-6, atol=1e-6)
+    # inference path: no tensor requires grad -> the per-node tensors are read in place through a pointer table
+    with torch.no_grad():
+        img_ng = packing.pack_gmap_img_fts(gms, ref["gmap_img_fts"].shape[1], "cuda")
+    assert torch.equal(img_ng, out["gmap_img_fts"].detach())
     # the gather is differentiable: the gradient of a node row lands on that node's embedding
     out["gmap_img_fts"].sum().backward()
     first = next(iter(gms[0].node_embeds.values()))
