@@ -565,10 +565,17 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
     achieved = (g_fl.value / (g_ms.value * 1e-3)) / 1e12 if g_ms.value > 0 else 0.0
     fl = step_flops(cfg, B, V, N, Lt)
+    traffic, traffic_note = None, "no ncu summary found under profiles/"
+    try:   # mean dram__bytes_read + dram__bytes_write per GEMM launch over one captured step (profiles/summarize_ncu.py)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+        traffic = tj["mean_dram_bytes_per_launch"]
+        traffic_note = (f"mean over {tj['launches']} GEMM launches of one train step captured with ncu "
+                        f"(profiles/r01_step_metrics_summary.tsv); tensor pipe active {tj['tensor_pipe_active_pct_time_weighted']:.1f} % "
+                        "time-weighted over those launches")
+    except Exception:
+        pass
     roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None,
-            "traffic_note": "per-launch dram__bytes of 12 captured launches: profiles/r01_gemm_ncu_full_summary.tsv "
-                            "(grouped wgrad: 198 MB read + 20 MB written for 189 MB of operands)",
+            "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
             "peak_source": peak_src,
             "gemm_launches_per_step": g_n.value / prof_steps, "gemm_ms_per_step": g_ms.value / prof_steps,
             "gemm_share_of_step": (g_ms.value / prof_steps) / ms_per_step,
