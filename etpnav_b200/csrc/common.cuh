@@ -363,6 +363,17 @@ ETP_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// predicated global stores (one @p STG, no branch / reconvergence pair around it)
+ETP_DEVICE void st_global_b32_if(void* p, uint32_t v, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.b32 [%0], %1;\n\t}" ::"l"(p), "r"(v),
+               "r"(static_cast<uint32_t>(pred))
+               : "memory");
+}
+ETP_DEVICE void st_global_v2f32_if(void* p, float a, float b, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(a),
+               "f"(b), "r"(static_cast<uint32_t>(pred))
+               : "memory");
+}
 ETP_DEVICE float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -263,12 +263,15 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
       float2 R[16];
       auto load_resid = [&](int c, float2 (&dst)[16]) {
         const int col = colbase + c * 32;
-        const float* rp = e.resid + static_cast<size_t>(row0) * e.ld_resid + col;
+        // row pointers advance by the pitch (two adds per row) instead of being rebuilt from (row, col) per access
+        const char* rp = reinterpret_cast<const char*>(e.resid + static_cast<size_t>(row0) * e.ld_resid + col);
+        const int64_t pitch = static_cast<int64_t>(e.ld_resid) * 4;
         const bool ok = col < e.N;
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          dst[k] = (ok && k < nrows) ? __ldg(reinterpret_cast<const float2*>(rp + static_cast<size_t>(k) * e.ld_resid))
-                                     : make_float2(0.f, 0.f);
+        for (int k = 0; k < 16; ++k) {
+          dst[k] = (ok && k < nrows) ? __ldg(reinterpret_cast<const float2*>(rp)) : make_float2(0.f, 0.f);
+          rp += pitch;
+        }
       };
       if (e.resid) load_resid(0, R);  // lands while the main loop of this tile is still running
 
@@ -289,10 +292,13 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
         }
         uint32_t ax[16];
         if (e.aux_mode) {
-          const __nv_bfloat16* ap = e.aux + static_cast<size_t>(row0) * e.ld_aux + col;
+          const char* ap = reinterpret_cast<const char*>(e.aux + static_cast<size_t>(row0) * e.ld_aux + col);
+          const int64_t pitch = static_cast<int64_t>(e.ld_aux) * 2;
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            ax[k] = (colok && k < nrows) ? __ldg(reinterpret_cast<const unsigned int*>(ap + static_cast<size_t>(k) * e.ld_aux)) : 0u;
+          for (int k = 0; k < 16; ++k) {
+            ax[k] = (colok && k < nrows) ? __ldg(reinterpret_cast<const unsigned int*>(ap)) : 0u;
+            ap += pitch;
+          }
         }
         tmem_ld_wait();
         if (c == kChunks - 1) {
@@ -325,14 +331,18 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
             v[2 * k + 1] = fmaf(v[2 * k + 1], e.alpha, bias.y);
           }
           if (e.out_pre && !e.pre_mode) {
-            __nv_bfloat16* o = e.out_pre + static_cast<size_t>(row0) * e.ld_pre + col;
+            char* o = reinterpret_cast<char*>(e.out_pre + static_cast<size_t>(row0) * e.ld_pre + col);
+            const int64_t pitch = static_cast<int64_t>(e.ld_pre) * 2;
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-              if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * e.ld_pre) = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+            for (int k = 0; k < 16; ++k) {
+              st_global_b32_if(o, pack_bf16x2(v[2 * k], v[2 * k + 1]), k < nrows);
+              o += pitch;
+            }
           }
           if (e.act == 1 && e.pre_mode) {
             // GELU and its derivative from one Phi / exp evaluation; the derivative is what the backward multiplies by
-            __nv_bfloat16* o = e.out_pre + static_cast<size_t>(row0) * e.ld_pre + col;
+            char* o = reinterpret_cast<char*>(e.out_pre + static_cast<size_t>(row0) * e.ld_pre + col);
+            const int64_t pitch = static_cast<int64_t>(e.ld_pre) * 2;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               float c0, e0, c1, e1;
@@ -346,7 +356,8 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                           static_cast<uint32_t>(row0 + k) * static_cast<uint32_t>(e.N) + static_cast<uint32_t>(col), m0, m1);
                 d0 *= m0; d1 *= m1;
               }
-              if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * e.ld_pre) = pack_bf16x2(d0, d1);
+              st_global_b32_if(o, pack_bf16x2(d0, d1), k < nrows);
+              o += pitch;
               v[2 * k] *= c0;
               v[2 * k + 1] *= c1;
             }
@@ -401,16 +412,23 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                                "f"(v[2 * k + 1])
                                : "memory");
             } else {
+              char* ob = reinterpret_cast<char*>(o);
+              const int64_t pitch = static_cast<int64_t>(e.ld_f32) * 4;
 #pragma unroll
-              for (int k = 0; k < 16; ++k)
-                if (k < nrows) *reinterpret_cast<float2*>(o + static_cast<size_t>(k) * e.ld_f32) = make_float2(v[2 * k], v[2 * k + 1]);
+              for (int k = 0; k < 16; ++k) {
+                st_global_v2f32_if(ob, v[2 * k], v[2 * k + 1], k < nrows);
+                ob += pitch;
+              }
             }
           }
           if (e.out_bf16) {
-            __nv_bfloat16* o = e.out_bf16 + static_cast<size_t>(row0) * e.ld_bf16 + col;
+            char* o = reinterpret_cast<char*>(e.out_bf16 + static_cast<size_t>(row0) * e.ld_bf16 + col);
+            const int64_t pitch = static_cast<int64_t>(e.ld_bf16) * 2;
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-              if (k < nrows) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(k) * e.ld_bf16) = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+            for (int k = 0; k < 16; ++k) {
+              st_global_b32_if(o, pack_bf16x2(v[2 * k], v[2 * k + 1]), k < nrows);
+              o += pitch;
+            }
           }
         }
         if constexpr (EW == 8) {
