@@ -19,6 +19,10 @@ CASES = {
     "c4": (dict(vocab_size=2048, num_l_layers=0, num_x_layers=4), 64, 12, 60, 80, True, 4),
     "c5": (dict(vocab_size=2048, num_l_layers=0, num_x_layers=4, max_position_embeddings=514, layer_norm_eps=1e-5), 32, 12, 120,
            512, True, 2),
+    # edges: the smallest map the trainer can produce ([stop] + the current node, a three-token instruction, one episode)
+    # and a map wider than one 128-row query tile (attention backward falls back to the CUDA-core kernels)
+    "tiny": (dict(vocab_size=2048, num_l_layers=0, num_x_layers=2), 1, 12, 2, 3, False, 1),
+    "wide": (dict(vocab_size=2048, num_l_layers=0, num_x_layers=2), 2, 16, 200, 300, True, 2),
 }
 
 
@@ -70,8 +74,9 @@ def test_config_shape_forward_backward_vs_oracle(name):
     assert torch.equal(pm[:S].cpu(), pm_o)
     assert ((pano[:S].detach().cpu() - pano_o.detach()) * pm_o[..., None]).abs().max().item() < 6e-2
     rel = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
-    assert rel(txt.grad[:S].cpu(), txt_o.grad) < 8e-2
-    assert rel(img.grad[:S].cpu(), img_o.grad) < 8e-2
+    tol_g = 0.15 if name == "tiny" else 8e-2   # a 2-node, 3-token problem averages nothing
+    assert rel(txt.grad[:S].cpu(), txt_o.grad) < tol_g
+    assert rel(img.grad[:S].cpu(), img_o.grad) < tol_g
     # the full batch equals the slice run alone (independent episodes; the GEMM tile width may differ between the two
     # batch sizes, so this is asserted to fp32 round-off rather than bit for bit)
     with torch.no_grad():
