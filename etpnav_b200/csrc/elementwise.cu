@@ -76,22 +76,38 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
 }
 
 // Backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd.
-// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy: per-lane register partials over a grid-stride loop
-// of rows, reduced across the CTA's 8 warps in shared memory, one atomicAdd per column per CTA.
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, int rows, float* __restrict__ dx_f32,
-                                                             int accumulate_dx, bf16* __restrict__ dx_bf16,
-                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                             float* __restrict__ dxsum, const Drop drop) {
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy, dxsum += sum_rows dx: per-lane partials over a grid-stride loop of
+// rows.  The three partial rows live in SHARED memory (each lane owns its own float4 slots, so no synchronisation is
+// needed inside the loop): keeping them in registers cost 72 registers per thread and limited the kernel to ONE 8-warp CTA
+// per SM (178 registers), i.e. 8 warps of loads in flight; with them in shared memory two CTAs fit and the 2 x 148 CTA grid
+// is a single wave.  At the end the 8 warps' partials are summed and leave as one vector reduction per 4 columns per CTA.
+constexpr int kLnBwdSmem = (3 * 8 + 1) * (kH / 4) * 16;  // [dgamma | dbeta | dxsum][warp][192] float4 + gamma = 76,800 B
+ETP_DEVICE void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, int rows, float* __restrict__ dx_f32,
+                                                                int accumulate_dx, bf16* __restrict__ dx_bf16,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                float* __restrict__ dxsum, const Drop drop) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
-  __shared__ float red[8][kH];
+  extern __shared__ float4 ln_acc[];
+  constexpr int kQ = kH / 4;  // float4 slots per row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float g[24], dg[24], db[24], ds[24];
-  load_row(gamma, lane, g);
+  float4* adg = ln_acc + (0 * 8 + warp) * kQ;
+  float4* adb = ln_acc + (1 * 8 + warp) * kQ;
+  float4* ads = ln_acc + (2 * 8 + warp) * kQ;
+  float4* sgam = ln_acc + 3 * 8 * kQ;  // gamma, read per chunk (kept out of the registers)
 #pragma unroll
-  for (int i = 0; i < 24; ++i) { dg[i] = 0.f; db[i] = 0.f; ds[i] = 0.f; }
+  for (int i = 0; i < kVec; ++i) {
+    adg[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    adb[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ads[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int c = threadIdx.x; c < kQ; c += 256) sgam[c] = reinterpret_cast<const float4*>(gamma)[c];
+  __syncthreads();
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     float d[24], v[24];
     load_row(dy + static_cast<size_t>(row) * kH, lane, d);
@@ -99,86 +115,103 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     const float mu = mean[row], rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
-      v[i] = (v[i] - mu) * rs;       // xhat
-      dg[i] += d[i] * v[i];
-      db[i] += d[i];
-      d[i] *= g[i];                  // g
-      s1 += d[i];
-      s2 += d[i] * v[i];
+    for (int i = 0; i < kVec; ++i) {
+      float4 tg = adg[i * 32 + lane], tb = adb[i * 32 + lane];
+      const float4 gi = sgam[i * 32 + lane];
+      const float gg[4] = {gi.x, gi.y, gi.z, gi.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[4 * i + j] = (v[4 * i + j] - mu) * rs;  // xhat
+      tg.x += d[4 * i] * v[4 * i]; tg.y += d[4 * i + 1] * v[4 * i + 1];
+      tg.z += d[4 * i + 2] * v[4 * i + 2]; tg.w += d[4 * i + 3] * v[4 * i + 3];
+      tb.x += d[4 * i]; tb.y += d[4 * i + 1]; tb.z += d[4 * i + 2]; tb.w += d[4 * i + 3];
+      adg[i * 32 + lane] = tg;
+      adb[i * 32 + lane] = tb;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        d[4 * i + j] *= gg[j];  // g
+        s1 += d[4 * i + j];
+        s2 += d[4 * i + j] * v[4 * i + j];
+      }
     }
     s1 = warp_sum(s1) * (1.0f / kH);
     s2 = warp_sum(s2) * (1.0f / kH);
-#pragma unroll
-    for (int i = 0; i < 24; ++i) d[i] = rs * (d[i] - s1 - v[i] * s2);
     float* o = dx_f32 + static_cast<size_t>(row) * kH;
-    if (accumulate_dx) {
-      float prev[24];
-      load_row(o, lane, prev);
 #pragma unroll
-      for (int i = 0; i < 24; ++i) d[i] += prev[i];
+    for (int i = 0; i < kVec; ++i) {
+      float4 t;
+      t.x = rs * (d[4 * i] - s1 - v[4 * i] * s2);
+      t.y = rs * (d[4 * i + 1] - s1 - v[4 * i + 1] * s2);
+      t.z = rs * (d[4 * i + 2] - s1 - v[4 * i + 2] * s2);
+      t.w = rs * (d[4 * i + 3] - s1 - v[4 * i + 3] * s2);
+      float4* o4 = reinterpret_cast<float4*>(o + (i * 32 + lane) * 4);
+      if (accumulate_dx) {
+        const float4 prev = *o4;
+        t.x += prev.x; t.y += prev.y; t.z += prev.z; t.w += prev.w;
+      }
+      *o4 = t;
+      if (drop.thr) {
+        // the Linear whose output this LayerNorm normalised went through dropout before the residual add: ITS output
+        // gradient (the bf16 copy the dgrad / wgrad GEMMs read, and the bias gradient) carries the mask; the fp32
+        // dx written above is the residual branch and does not.  Element index = row * 768 + column (drop_row24).
+        const uint32_t e = static_cast<uint32_t>(row) * 768u + static_cast<uint32_t>((i * 32 + lane) * 4);
+        float m0, m1, m2, m3;
+        drop_mul2(drop, e, m0, m1);
+        drop_mul2(drop, e + 2, m2, m3);
+        t.x *= m0; t.y *= m1; t.z *= m2; t.w *= m3;
+      }
+      if (dx_bf16)
+        *reinterpret_cast<uint2*>(dx_bf16 + static_cast<size_t>(row) * kH + (i * 32 + lane) * 4) =
+            make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+      if (dxsum != nullptr) {
+        float4 ts = ads[i * 32 + lane];
+        ts.x += t.x; ts.y += t.y; ts.z += t.z; ts.w += t.w;
+        ads[i * 32 + lane] = ts;
+      }
     }
-    store_row(o, lane, d);
-    if (drop.thr) {
-      // the Linear whose output this LayerNorm normalised went through dropout before the residual add: ITS output
-      // gradient (the bf16 copy the dgrad / wgrad GEMMs read, and the bias gradient) carries the mask; the fp32
-      // dx written above is the residual branch and does not
-      drop_row24(drop, row, lane, d);
-    }
-    if (dx_bf16) store_row_bf16(dx_bf16 + static_cast<size_t>(row) * kH, lane, d);
-#pragma unroll
-    for (int i = 0; i < 24; ++i) ds[i] += d[i];
-  }
-  if (dxsum != nullptr) {
-    // column sums of dx: the bias gradient of the Linear whose output (+ residual) this LayerNorm normalised
-#pragma unroll
-    for (int i = 0; i < kVec; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) red[warp][(i * 32 + lane) * 4 + j] = ds[4 * i + j];
-    __syncthreads();
-    for (int c = threadIdx.x; c < kH; c += 256) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w][c];
-      atomicAdd(dxsum + c, s);
-    }
-    __syncthreads();
-  }
-  if (dgamma == nullptr) return;
-  // CTA reduction of the per-warp partials
-#pragma unroll
-  for (int i = 0; i < kVec; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) red[warp][(i * 32 + lane) * 4 + j] = dg[4 * i + j];
-  __syncthreads();
-  for (int c = threadIdx.x; c < kH; c += 256) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][c];
-    atomicAdd(dgamma + c, s);
   }
   __syncthreads();
+  // CTA reduction of the 8 warps' partial rows; one vector reduction per 4 columns per CTA and quantity
+  for (int c = threadIdx.x; c < kQ; c += 256) {
+    if (dgamma != nullptr) {
+      float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sb = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < kVec; ++i)
+      for (int w = 0; w < 8; ++w) {
+        const float4 a = ln_acc[(0 * 8 + w) * kQ + c], b2 = ln_acc[(1 * 8 + w) * kQ + c];
+        sg.x += a.x; sg.y += a.y; sg.z += a.z; sg.w += a.w;
+        sb.x += b2.x; sb.y += b2.y; sb.z += b2.z; sb.w += b2.w;
+      }
+      red_add_v4(dgamma + 4 * c, sg);
+      red_add_v4(dbeta + 4 * c, sb);
+    }
+    if (dxsum != nullptr) {
+      float4 ss = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[warp][(i * 32 + lane) * 4 + j] = db[4 * i + j];
-  __syncthreads();
-  for (int c = threadIdx.x; c < kH; c += 256) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][c];
-    atomicAdd(dbeta + c, s);
+      for (int w = 0; w < 8; ++w) {
+        const float4 a = ln_acc[(2 * 8 + w) * kQ + c];
+        ss.x += a.x; ss.y += a.y; ss.z += a.z; ss.w += a.w;
+      }
+      red_add_v4(dxsum + 4 * c, ss);
+    }
   }
 }
 
 int layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int rows,
                   int H, float* dx_f32, int accumulate_dx, bf16* dx_bf16, float* dgamma, float* dbeta,
                   cudaStream_t stream, float* dxsum, DropHost drop) {
+
   ETP_REQUIRE(H == kH, "layernorm: hidden size must be 768");
   if (rows <= 0) return ETP_OK;
+  ETP_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta come together");
+  ETP_REQUIRE(((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta) | reinterpret_cast<uintptr_t>(dxsum)) & 15) == 0,
+              "layernorm_bwd: dgamma / dbeta / dxsum must be 16-byte aligned");
+  static bool attr = false;
+  if (!attr) {
+    ETP_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnBwdSmem));
+    attr = true;
+  }
   int grid = (rows + 7) / 8;
-  if (grid > 2 * num_sms()) grid = 2 * num_sms();
-  ETP_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(grid), dim3(256), 0, stream, dy, x, gamma, mean, rstd, rows, dx_f32, accumulate_dx, dx_bf16, dgamma,
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();  // two resident CTAs per SM: one wave
+  ETP_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(grid), dim3(256), kLnBwdSmem, stream, dy, x, gamma, mean, rstd, rows, dx_f32, accumulate_dx, dx_bf16, dgamma,
                                                  dbeta, dxsum, Drop{drop.key, drop.thr, drop.scale}));
   ETP_LAUNCHED();
   return ETP_OK;
