@@ -66,3 +66,73 @@ def test_shard_batch_covers_global_batch():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+# ----------------------------------------------------------------------------------------------------
+# pre-training trainer: the one exchange of its data-parallel path is the SUM all-reduce of the flat
+# gradient buffer followed by AdamW with grad_scale = 1 / world.  Two gloo ranks drive PretrainTrainer.step with the C
+# library stubbed (tests/test_pretrain_dryrun_cpu.py), each filling the flat gradient with a rank-dependent pattern where
+# the backward would: after the step both ranks must hold the same reduced buffer and have passed 1 / world to AdamW.
+# ----------------------------------------------------------------------------------------------------
+def _pretrain_worker(rank, world, port, out):
+    import ctypes as C
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from etpnav_b200 import lib as L
+    from etpnav_b200 import planner, pretrain
+    from etpnav_b200.synth import make_traj_batch
+    from tests.test_pretrain_dryrun_cpu import _StubLib, _fake_refresh
+    stub = _StubLib()
+    seen = {}
+
+    class Adam:
+        restype = None
+        argtypes = None
+
+        def __call__(self, *a):
+            seen["grad_scale"] = a[12].value if hasattr(a[12], "value") else a[12]
+            return 0
+    stub.etp_adamw_step = Adam()
+    L.lib = lambda: stub
+    L.require_device = lambda: None
+    L.stream_ptr = lambda: C.c_void_p(0)
+    L.ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    planner._declared = pretrain._declared = True
+    planner.B200Planner._refresh_cache = _fake_refresh
+    cfg = PlannerConfig(vocab_size=2048, num_l_layers=1, num_x_layers=2, hidden_dropout_prob=0.0,
+                        attention_probs_dropout_prob=0.0, pred_head_dropout_prob=0.0)
+    model = pretrain.B200PreTraining(cfg, device="cpu").train()
+    tr = pretrain.PretrainTrainer(model, world_size=world)
+    # stand-in for the backward kernels: a deterministic rank-dependent gradient, written when the loss is formed
+    orig = model.forward
+
+    def fwd(batch, task, compute_loss=True):
+        loss = orig(batch, task, compute_loss)
+        tr.m._direct_grad.copy_(torch.arange(tr.m._direct_grad.numel(), dtype=torch.float32) % 97 * (rank + 1))
+        return torch.nan_to_num(loss, nan=0.0, posinf=0.0, neginf=0.0)
+    model.forward = fwd
+    model.__call__ = fwd
+    b = make_traj_batch(cfg, 2, 2, 6, 10, seed=rank_seed(7, rank))
+
+    class M:   # PretrainTrainer calls self.model(batch, task, compute_loss=True)
+        bert = model.bert
+
+        def __call__(self, batch, task, compute_loss=True):
+            return fwd(batch, task, compute_loss)
+    tr.model = M()
+    tr.step(b, "sap")
+    torch.save({"g": tr.m._direct_grad.clone(), "scale": seen.get("grad_scale")}, f"{out}/p{rank}.pt")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_pretrain_trainer_allreduce(tmp_path):
+    world = 2
+    mp.spawn(_pretrain_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "p0.pt"), torch.load(tmp_path / "p1.pt")
+    assert torch.equal(r0["g"], r1["g"])
+    n = r0["g"].numel()
+    want = torch.arange(n, dtype=torch.float32) % 97 * 3.0       # SUM of the rank patterns (x1 + x2)
+    # the stubbed backward kernels add nothing; the loss.backward() of the stub graph may not touch the buffer either
+    assert torch.equal(r0["g"], want)
+    assert abs(float(r0["scale"]) - 0.5) < 1e-7 and abs(float(r1["scale"]) - 0.5) < 1e-7
