@@ -12,6 +12,7 @@ the policy already holds on the device (differentiable, so the averaged panorama
 No CPU / PyTorch fallback: without the library or a B200 the calls raise.
 """
 import ctypes as C
+from operator import itemgetter
 
 import numpy as np
 import torch
@@ -58,27 +59,33 @@ def flatten_gmaps(gmaps, cur_vp, cur_pos, cur_ori):
         ix = {vp: k for k, vp in enumerate(nid)}
         n, g = len(nid), len(gid)
         fronts = [[ix[f] for f in gm.ghost_fronts[v]] for v in gid]
-        fptr = np.zeros(g + 1, dtype=np.int32)
-        if g:
-            np.cumsum([len(f) for f in fronts], out=fptr[1:])
+        nfront = [len(f) for f in fronts]
         sd, sp = gm.shortest_dist, gm.shortest_path
-        fe = np.concatenate([
-            np.asarray(cur_pos[e], dtype=np.float64).reshape(3), [heading_from_quaternion(cur_ori[e])],
-            np.asarray([gm.node_pos[v] for v in nid], dtype=np.float64).reshape(-1),
-            np.asarray([gm.ghost_aug_pos[v] for v in gid], dtype=np.float64).reshape(-1),
-            np.asarray([[sd[a][b] for b in nid] for a in nid], dtype=np.float64).reshape(-1)])
-        ie = np.concatenate([
-            np.asarray([gm.node_stepId[v] for v in nid], dtype=np.int32).reshape(-1), fptr,
-            np.asarray([k for f in fronts for k in f], dtype=np.int32).reshape(-1),
-            np.asarray([[len(sp[a][b]) for b in nid] for a in nid], dtype=np.int32).reshape(-1)])
-        meta[e, :6] = (n, g, ix[cur_vp[e]], off_f, off_i, int(fptr[-1]))
+        # row getters run the per-row dictionary reads in C (itemgetter with one key returns a scalar: wrap it)
+        row = itemgetter(*nid) if n > 1 else (lambda d, k=nid[0]: (d[k],))
+        fe = np.empty(4 + 3 * n + 3 * g + n * n, dtype=np.float64)
+        fe[0:3] = np.asarray(cur_pos[e], dtype=np.float64).reshape(3)
+        fe[3] = heading_from_quaternion(cur_ori[e])
+        fe[4:4 + 3 * n] = np.asarray(row(gm.node_pos), dtype=np.float64).reshape(-1)
+        if g:
+            fe[4 + 3 * n:4 + 3 * n + 3 * g] = np.asarray([gm.ghost_aug_pos[v] for v in gid], dtype=np.float64).reshape(-1)
+        fe[4 + 3 * n + 3 * g:] = np.asarray([row(sd[a]) for a in nid], dtype=np.float64).reshape(-1)
+        nnz = sum(nfront)
+        ie = np.empty(n + g + 1 + nnz + n * n, dtype=np.int32)
+        ie[0:n] = row(gm.node_stepId)
+        ie[n] = 0
+        if g:
+            np.cumsum(nfront, out=ie[n + 1:n + g + 1])
+            ie[n + g + 1:n + g + 1 + nnz] = [k for f in fronts for k in f]
+        ie[n + g + 1 + nnz:] = np.asarray([list(map(len, row(sp[a]))) for a in nid], dtype=np.int32).reshape(-1)
+        meta[e, :6] = (n, g, ix[cur_vp[e]], off_f, off_i, nnz)
         f64.append(fe)
         i32b.append(ie)
         off_f += len(fe)
         off_i += len(ie)
         n_max, max_g = max(n_max, 1 + n + g), max(max_g, g)
         vp_ids.append([None] + nid + gid)
-    return meta, np.concatenate(f64), np.concatenate(i32b).astype(np.int32), vp_ids, n_max, max_g
+    return meta, np.concatenate(f64), np.concatenate(i32b), vp_ids, n_max, max_g
 
 
 def _to_device(arr, dtype, device):
