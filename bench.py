@@ -58,6 +58,9 @@ def parse():
                     help="also time the oracle port in eager PyTorch on this GPU (fp32 and bf16 autocast): the "
                          "'reference GPU eager' figure the north_star's >=10x target is stated against")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel CUDA-event table of the profiled pass here")
+    ap.add_argument("--text-law", default=None, choices=["r2r"],
+                    help="ragged instruction lengths: 'r2r' = normal(32, 12) clipped to [8, 80] BERT tokens (BASELINE.json "
+                         "configs[3]; etpnav_b200/synth.py:r2r_text_lengths), padded to --tokens")
     ap.add_argument("--workload", default="planner", choices=["planner", "pretrain", "packing"],
                     help="planner (default, BASELINE.json's metric) | pretrain (SURVEY.md 8f N2: one pre-training iteration "
                          "of the twin, mlm and sap alternating) | packing (8f N3: the per-step map / view packing)")
@@ -84,8 +87,9 @@ def torch_dropout_hook(cfg):
 
 def workload_name(a, mode):
     what = ("fwd+bwd+AdamW, train() dropout " + a.dropout) if mode == "train" else "fwd"
+    law = ", R2R-CE-like text lengths (normal(32,12) in [8,80], padded)" if a.text_law else ""
     return (f"planner step {what}: forward_panorama+forward_navigation, B={a.batch}/GPU, V={a.views}, N={a.nodes}, "
-            f"L={a.tokens}, {a.x_layers} cross layers")
+            f"L={a.tokens}{law}, {a.x_layers} cross layers")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -158,7 +162,7 @@ def cpu_step_time(a, mode, steps, warmup, max_seconds=25.0):
                 best = (c, min(ts[1:]))
         cores = best[0]
     torch.set_num_threads(cores)
-    inp = make_inputs(cfg, a.batch, a.views, a.nodes, a.tokens, seed=1, ragged=False)
+    inp = make_inputs(cfg, a.batch, a.views, a.nodes, a.tokens, seed=1, ragged=False, txt_law=a.text_law)
     if mode == "train":
         sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
         opt = torch.optim.AdamW([v for v in sd.values()], lr=1e-5)
@@ -208,7 +212,7 @@ def gpu_eager_time(a, mode, dev, autocast, steps=10, warmup=3):
     cfg = workload_cfg(a)
     sd = {k: v.to(dev) for k, v in make_weights(cfg, seed=0, skip_text=False).items()}
     inp = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v)
-           for k, v in make_inputs(cfg, a.batch, a.views, a.nodes, a.tokens, seed=1, ragged=False).items()}
+           for k, v in make_inputs(cfg, a.batch, a.views, a.nodes, a.tokens, seed=1, ragged=False, txt_law=a.text_law).items()}
     if mode == "train":
         sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
         opt = torch.optim.AdamW(list(sd.values()), lr=1e-5)
@@ -452,7 +456,7 @@ def main():
     model = PL.B200Planner(cfg, device=dev)
     model.load_state_dict(make_weights(cfg, seed=0), strict=True)
     B, V, N, Lt = a.batch, a.views, a.nodes, a.tokens
-    host = make_inputs(cfg, B, V, N, Lt, seed=100 + rank, ragged=False)
+    host = make_inputs(cfg, B, V, N, Lt, seed=100 + rank, ragged=False, txt_law=a.text_law)
     keys_pano = ["rgb_fts", "dep_fts", "loc_fts", "nav_types", "view_lens"]
     keys_nav = ["txt_embeds", "txt_masks", "gmap_step_ids", "gmap_img_fts", "gmap_pos_fts", "gmap_masks",
                 "gmap_visited_masks", "gmap_pair_dists"]

@@ -58,8 +58,18 @@ def _lens(g, B, lo, hi):
     return lens
 
 
+def r2r_text_lengths(g, B: int, L: int):
+    """R2R-CE-like instruction lengths in BERT tokens (BASELINE.json configs[3]): the dataset is not in the
+    reference repository, so the law is synthetic and stated here — normal(mean 32, sd 12) clipped to [8, min(80, L)]
+    (``IL.max_text_len`` = 80, run_r2r/iter_train.yaml:42); one row takes the maximum so the padded width is reached."""
+    hi = min(80, L)
+    lens = (torch.randn(B, generator=g) * 12.0 + 32.0).round().long().clamp_(8, hi)
+    lens[0] = hi
+    return lens
+
+
 def make_inputs(cfg: PlannerConfig, B: int, V: int, N: int, L: int, seed: int = 0,
-                ragged: bool = True, txt_from: str = "normal", pad_id: int = 0) -> dict:
+                ragged: bool = True, txt_from: str = "normal", pad_id: int = 0, txt_law: str = None) -> dict:
     """One planner step's inputs (CPU tensors).
 
     ``ragged=False`` gives fixed V/N/L (peak-throughput shape); ``ragged=True`` draws
@@ -76,6 +86,8 @@ def make_inputs(cfg: PlannerConfig, B: int, V: int, N: int, L: int, seed: int = 
         view_lens = torch.full((B,), V, dtype=torch.long)
         gmap_lens = torch.full((B,), N, dtype=torch.long)
         txt_lens = torch.full((B,), L, dtype=torch.long)
+    if txt_law == "r2r":
+        txt_lens = r2r_text_lengths(g, B, L)
     ar = torch.arange
     rgb_fts = torch.randn(B, V, cfg.image_feat_size, generator=g)
     dep_fts = torch.randn(B, V, cfg.depth_feat_size, generator=g)
