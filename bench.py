@@ -262,7 +262,9 @@ def run_reference_arm(a, mode, rank):
     line = {"metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": a.gpus, "steps": n, "warmup": 1,
             "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(a, mode), "mode": mode},
+            "config": {"workload": workload_name(a, mode), "mode": mode, "global_batch": a.batch * max(1, a.gpus),
+                       "parallelism": f"dp{max(1, a.gpus)}", "x_layers": a.x_layers,
+                       "dropout": a.dropout if mode == "train" else "n/a", "l2": "n/a (host arm)"},
             "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
