@@ -50,14 +50,22 @@ def simulate(gu, rng, g, steps, H, merge_ghost=True, loc_noise=0.5):
     return gm, last
 
 
-def case_gmap(name, seed, B, max_steps, H=768):
+def case_gmap(name, seed, B, max_steps, H=768, edge=False):
     gu = ref_import.load_graph_utils()
     fns = ref_import.load_trainer_packers()
     rng = np.random.default_rng(seed)
     g = torch.Generator().manual_seed(seed)
     gms, cur = [], []
     for i in range(B):
-        gm, last = simulate(gu, rng, g, int(rng.integers(1, max_steps + 1)) if i else max_steps, H)
+        if edge:
+            # 0: ghosts never merged (MODEL.merge_ghost False); 1: every ghost explored away (no_vp_left); 2: a single step
+            gm, last = simulate(gu, rng, g, [max_steps, max_steps, 1][i % 3], H, merge_ghost=(i % 3 != 0))
+            if i % 3 == 1:
+                for gvp in list(gm.ghost_pos.keys()):
+                    gm.delete_ghost(gvp)
+                    gm.ghost_aug_pos.pop(gvp, None)
+        else:
+            gm, last = simulate(gu, rng, g, int(rng.integers(1, max_steps + 1)) if i else max_steps, H)
         gms.append(gm)
         cur.append(last)
     fake = types.SimpleNamespace(gmaps=gms, envs=types.SimpleNamespace(num_envs=B))
@@ -101,3 +109,4 @@ if __name__ == "__main__":
     case_gmap("gmap_small", 0, 3, 4)
     case_gmap("gmap_mid", 1, 6, 9)
     case_vp("vp_small", 2, 5)
+    case_gmap("edge_gmap", 3, 3, 5, edge=True)   # CPU-only fixture (name outside the gmap_* glob of the GPU tests)

@@ -27,7 +27,13 @@ def gmap_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLD, "gmap_*.pt")))
 
 
-@pytest.mark.parametrize("name", gmap_names())
+def cpu_gmap_names():
+    """gmap_* fixtures (also used by the GPU tests) + the CPU-only edge fixture: ghosts never merged, a map whose ghosts
+    have all been explored (no_vp_left), a single-step map."""
+    return gmap_names() + ["edge_gmap"]
+
+
+@pytest.mark.parametrize("name", cpu_gmap_names())
 def test_nav_gmap_variable_port_is_bit_exact(name):
     gold = load(name)
     sts, raw = states_of(gold)

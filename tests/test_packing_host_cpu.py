@@ -14,7 +14,7 @@ import torch
 
 from etpnav_b200 import packing
 from oracle import packing_port as PK
-from tests.test_packing_cpu import gmap_names, load
+from tests.test_packing_cpu import cpu_gmap_names, gmap_names, load
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -66,7 +66,7 @@ def run_host(L, meta, f64, i32b, n_max):
     return step, vis, msk, pos, pd
 
 
-@pytest.mark.parametrize("name", gmap_names())
+@pytest.mark.parametrize("name", cpu_gmap_names())
 def test_flatten_and_device_geometry_match_reference(harness, name):
     gold = load(name)
     gms, cur_vp, cur_pos, cur_ori = fake_gmaps(gold)
@@ -108,11 +108,12 @@ def test_img_fts_and_vp_index_construction_cpu():
         return out
     packing.segment_gather = dense
     try:
-        gold = load("gmap_mid")
-        gms, *_ = fake_gmaps(gold)
-        n_max = gold["out"]["gmap_step_ids"].shape[1]
-        img = packing.pack_gmap_img_fts(gms, n_max, "cpu")
-        torch.testing.assert_close(img, gold["out"]["gmap_img_fts"], rtol=1e-6, atol=1e-6)  # x * (1/c) vs x / c
+        for name in ("gmap_mid", "edge_gmap"):
+            gold = load(name)
+            gms, *_ = fake_gmaps(gold)
+            n_max = gold["out"]["gmap_step_ids"].shape[1]
+            img = packing.pack_gmap_img_fts(gms, n_max, "cpu")
+            torch.testing.assert_close(img, gold["out"]["gmap_img_fts"], rtol=1e-6, atol=1e-6)  # x * (1/c) vs x / c
         vp = load("vp_small")
         out = packing.pack_vp_features(vp["obs"], "cpu")
         for k, v in vp["out"].items():
