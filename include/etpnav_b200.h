@@ -18,6 +18,10 @@
  *   (2) operator level — the fused kernels the step level is made of (GEMM+epilogue, attention,
  *       LayerNorm, token packing, SAP head, AdamW); exported for the parity tests and for hosts that
  *       want to compose them differently.
+ * Two further groups at the end of the file cover the rows SURVEY.md §8f calls "next":
+ *   (3) the pre-training twin GlocalTextPathCMT (pretrain_src/pretrain_src/model/vilmodel.py:656-754):
+ *       etp_segment_gather(_rows), etp_forward_lang2visn / etp_backward_lang2visn;
+ *   (4) the trainer's per-step map packing (vlnce_baselines/ss_trainer_ETP.py:344-417): etp_gmap_pack.
  */
 #ifndef ETPNAV_B200_H_
 #define ETPNAV_B200_H_
