@@ -408,6 +408,25 @@ class B200PreTraining(nn.Module):
         self.config = config
         self.bert = B200TextPathCMT(config, device=device)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path=None, config=None, state_dict=None, device="cuda"):
+        """The constructor call of the reference's driver (pretrain_src/pretrain_src/train_r2r.py:146-148:
+        ``model_class.from_pretrained(pretrained_model_name_or_path=None, config=model_config, state_dict=checkpoint)``).
+        ``config`` is the reference's model config object (attributes of run_pt/r2r_model_config_dep.json) or a
+        ``PlannerConfig``; keys of ``state_dict`` this model does not own are ignored, as HF does."""
+        if pretrained_model_name_or_path is not None:
+            raise ValueError("only the reference's own usage (name None + explicit state_dict) is supported")
+        if not isinstance(config, PlannerConfig):
+            fields = PlannerConfig.__dataclass_fields__
+            kw = {k: getattr(config, k) for k in fields if hasattr(config, k)}
+            if getattr(config, "depth_feat_size", 128) == 0:
+                kw["use_depth_embedding"], kw["depth_feat_size"] = False, 128
+            config = PlannerConfig(**kw)
+        model = cls(config, device=device)
+        if state_dict is not None:
+            model.load_state_dict(state_dict, strict=False)
+        return model
+
     # ------------------------------------------------------------------ reference key layout
     @staticmethod
     def _ref_key(k):

@@ -82,3 +82,26 @@ def test_pretraining_fails_loudly_without_gpu():
         m(b, "sap")
     with pytest.raises(ValueError):
         m(b, "mrc")
+
+
+def test_from_pretrained_mirrors_the_reference_driver_call():
+    """train_r2r.py:146-148: from_pretrained(None, config=<object with the JSON's attributes>, state_dict=<checkpoint>):
+    foreign keys (e.g. a checkpoint that still carries heads this model does not own) are ignored, own keys load."""
+    import json
+    import types
+    from etpnav_b200.pretrain import B200PreTraining
+    js = dict(pred_head_dropout_prob=0.1, attention_probs_dropout_prob=0.1, hidden_dropout_prob=0.1, hidden_size=768,
+              image_feat_size=512, depth_feat_size=128, angle_feat_size=4, obj_feat_size=0, intermediate_size=3072,
+              num_l_layers=1, num_x_layers=2, num_pano_layers=2, layer_norm_eps=1e-12, max_position_embeddings=512,
+              max_action_steps=100, num_attention_heads=12, type_vocab_size=2, update_lang_bert=True, vocab_size=2048,
+              use_lang2visn_attn=True, graph_sprels=True, glocal_fuse=True)
+    hf = types.SimpleNamespace(**json.loads(json.dumps(js)))
+    w = make_weights(PlannerConfig(vocab_size=2048, num_l_layers=1, num_x_layers=2, use_lang2visn_attn=True, mlm_head=True), seed=4)
+    ck = {("bert." + k if not k.startswith(("mlm_head.", "global_sap_head.")) else k): v for k, v in w.items()}
+    ck["image_classifier.net.0.weight"] = torch.zeros(3, 3)        # an 'mrc' head of another run: ignored
+    m = B200PreTraining.from_pretrained(pretrained_model_name_or_path=None, config=hf, state_dict=ck, device="cpu")
+    assert m.config.num_x_layers == 2 and m.config.use_lang2visn_attn and m.config.mlm_head and m.config.use_depth_embedding
+    for k, v in w.items():
+        assert torch.equal(m.bert._pmap[k], v), k
+    with pytest.raises(ValueError):
+        B200PreTraining.from_pretrained("bert-base-uncased", config=hf)
