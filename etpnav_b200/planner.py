@@ -372,6 +372,14 @@ class B200Planner(nn.Module):
         self._drop_base = int(seed) & 0xFFFFFFFFFFFFFFFF
         self._drop_calls = 0
 
+    def set_dropout(self, p: float):
+        """What ``set_dropout(model, p)`` of the pre-training driver does to every ``nn.Dropout`` of the reference
+        (pretrain_src/pretrain_src/utils/misc.py:19-25): hidden, attention-probability and prediction-head dropout all
+        become ``p``.  (This module has no ``nn.Dropout`` children for that helper to find: the probabilities live in the
+        config and reach the kernels through ``etp_dropout``.)"""
+        cfg = self.config
+        cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = cfg.pred_head_dropout_prob = float(p)
+
     def _next_dropout(self):
         """``etp_dropout`` of the next forward call, or None in eval() mode (or when every probability is 0)."""
         cfg = self.config

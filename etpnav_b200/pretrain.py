@@ -453,6 +453,10 @@ class B200PreTraining(nn.Module):
             raise KeyError(f"unexpected keys: {unexpected[:5]}")
         return self.bert.load_state_dict(inner, strict=strict)
 
+    def set_dropout(self, p: float):
+        """Replacement for ``set_dropout(model, opts.dropout)`` (train_r2r.py:150, utils/misc.py:19-25)."""
+        self.bert.set_dropout(p)
+
     # ------------------------------------------------------------------ tasks
     def forward(self, batch, task, compute_loss=True):
         """pretrain_cmt.py:84-135."""

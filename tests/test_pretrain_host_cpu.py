@@ -105,3 +105,16 @@ def test_from_pretrained_mirrors_the_reference_driver_call():
         assert torch.equal(m.bert._pmap[k], v), k
     with pytest.raises(ValueError):
         B200PreTraining.from_pretrained("bert-base-uncased", config=hf)
+
+
+def test_set_dropout_reaches_the_kernel_arguments():
+    from etpnav_b200.pretrain import B200PreTraining
+    m = B200PreTraining(_cfg(), device="cpu").train()
+    m.set_dropout(0.25)
+    d = m.bert._next_dropout()
+    assert abs(d.p_hidden - 0.25) < 1e-7 and abs(d.p_attn - 0.25) < 1e-7 and abs(d.p_head - 0.25) < 1e-7
+    m.set_dropout(0.0)
+    assert m.bert._next_dropout() is None       # p = 0: the eval() code path
+    m.eval()
+    m.set_dropout(0.1)
+    assert m.bert._next_dropout() is None
