@@ -237,3 +237,30 @@ def sap_tail_fwd(relu_out, gamma, beta, w4, b4, visited, valid, logits, mean=Non
     rows, H = relu_out.shape
     _check(lib().etp_sap_tail_fwd(ptr(relu_out), ptr(gamma), ptr(beta), ptr(w4), ptr(b4), ptr(visited), ptr(valid),
                                   rows, H, ptr(logits), ptr(mean), ptr(rstd), stream_ptr()), "etp_sap_tail_fwd")
+
+
+def split3(x, form):
+    """fp32 [rows, K] -> bf16 [rows, 3K]: form 0 = hi|lo|hi (A operand), form 1 = hi|hi|lo (B operand) of the
+    split-bf16 x3 product (etp_split3, high-precision mode)."""
+    rows, K = x.shape
+    y = torch.empty(rows, 3 * K, dtype=torch.bfloat16, device=x.device)
+    L = lib()
+    L.etp_split3.argtypes = [p_void, p_void, C.c_int64, i32, i32, p_void]
+    _check(L.etp_split3(ptr(x.contiguous()), ptr(y), rows, K, form, stream_ptr()), "etp_split3")
+    return y
+
+
+def attention_f32_fwd(q, k, v, out, *, B, heads, Sq, Sk, scale=0.125, key_valid=None, mask_value=-10000.0, pair=None,
+                      pair_w=0.0, pair_b=0.0):
+    """fp32 attention of the high-precision mode; q/k/v/out: 2-D fp32 views [B*S, ld], head h at column h*64."""
+    a = AttnArgs()
+    a.B, a.heads, a.Sq, a.Sk = B, heads, Sq, Sk
+    a.q, a.ldq = ptr(q), q.stride(0)
+    a.k, a.ldk = ptr(k), k.stride(0)
+    a.v, a.ldv = ptr(v), v.stride(0)
+    a.scale, a.key_valid, a.mask_value = scale, ptr(key_valid), mask_value
+    a.pair, a.pair_w, a.pair_b = ptr(pair), pair_w, pair_b
+    a.out, a.ldo = ptr(out), out.stride(0)
+    L = lib()
+    L.etp_attention_f32_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+    _check(L.etp_attention_f32_fwd(C.byref(a), stream_ptr()), "etp_attention_f32_fwd")

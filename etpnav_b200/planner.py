@@ -105,6 +105,18 @@ def _declare():
                                         p_void, p_void, C.c_size_t, p_void, C.c_size_t, p_void, p_void, p_void]
     L.etp_backward_txt.argtypes = [C.POINTER(TxtWeights), C.POINTER(TxtWeights), p_void, p_void, i32, i32, p_void, p_void,
                                    C.c_size_t, p_void, C.c_size_t, p_void, C.POINTER(Dropout)]
+    # high-precision (split-bf16 x3) inference mode
+    L.etp_split3.argtypes = [p_void, p_void, C.c_int64, i32, i32, p_void]
+    L.etp_hp_nav_work_bytes.restype = C.c_size_t
+    L.etp_hp_nav_work_bytes.argtypes = [i32] * 4
+    for fn in ("etp_hp_pano_work_bytes", "etp_hp_txt_work_bytes"):
+        getattr(L, fn).restype = C.c_size_t
+        getattr(L, fn).argtypes = [i32] * 2
+    L.etp_forward_navigation_hp.argtypes = [C.POINTER(NavWeights), C.POINTER(NavInputs), p_void, p_void, p_void, C.c_size_t,
+                                            p_void]
+    L.etp_forward_panorama_hp.argtypes = [C.POINTER(PanoWeights), C.POINTER(PanoInputs), p_void, p_void, p_void, C.c_size_t,
+                                          p_void]
+    L.etp_forward_txt_hp.argtypes = [C.POINTER(TxtWeights), p_void, p_void, i32, i32, p_void, p_void, C.c_size_t, p_void]
     _declared = True
 
 
@@ -132,10 +144,13 @@ class B200Planner(nn.Module):
         self._bf16_fresh = False
         self._grad_structs = {}
         self._direct_grad = None      # PlannerTrainer: flat fp32 gradient buffer the backward accumulates into
+        self._tok_scratch = None      # PlannerTrainer without the txt group: sink of the token-type row-1 gradient
         self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         self._layer_events = None  # PlannerTrainer (world > 1): cudaEvent_t per x-layer, recorded by the nav backward
         self._drop_base = None   # dropout seed stream: base (torch.initial_seed() unless set) + call counter
         self._drop_calls = 0
+        self.precision = "bf16"  # "bf16" | "high" (set_precision): split-bf16 x3 GEMMs + fp32 attention, inference only
+        self._flat_hp, self._structs_hp, self._hp_key = None, None, None
         if config.fix_lang_embedding:  # vilmodel_cmt.py:675-679
             for n, p in self.named_parameters():
                 if n.startswith("embeddings.") or n.startswith("lang_encoder."):
@@ -207,10 +222,12 @@ class B200Planner(nn.Module):
 
     def _refresh_cache(self):
         """Re-cast the flat fp32 parameters to bf16 when any parameter changed (optimizer step, load)."""
-        if self._bf16_fresh and self._structs is not None:
-            return  # the fused AdamW keeps the bf16 image current (PlannerTrainer)
         key = self._version_key()
         if key == self._cache_key and self._structs is not None:
+            # nothing was written through torch since the image was made; the fused AdamW (PlannerTrainer) rewrites the
+            # flat buffer and its bf16 image together without bumping versions, and re-records the key it saw
+            if self.precision == "high":
+                self._refresh_hp(key)
             return
         if not self._flat.is_cuda:
             raise _L.EtpError("B200Planner parameters must live on a CUDA device (no CPU path exists)")
@@ -220,8 +237,49 @@ class B200Planner(nn.Module):
         _declare()
         _L.cast_bf16(self._flat, self._flat_bf16)
         self._cache_key = self._version_key()
+        self._bf16_fresh = False
         if self._structs is None:
             self._structs = self._build_structs(self._flat.data_ptr(), self._flat_bf16.data_ptr(), 2)
+        if self.precision == "high":
+            self._refresh_hp(self._cache_key)
+
+    # ------------------------------------------------------------------ high-precision inference mode
+    def set_precision(self, precision: str):
+        """``"bf16"`` (default): bf16 GEMM / attention operands, fp32 everywhere else — training and fast inference.
+        ``"high"``: inference only; every GEMM is a split-bf16 x3 product on the tensor cores (fp32-class accuracy, 3x
+        the GEMM work), attention in fp32: meets the reference's fp32 eval path (ss_trainer_ETP.py:513-756) within
+        rtol 1e-3 / atol 1e-4 (tests/test_precision_gpu.py)."""
+        if precision not in ("bf16", "high"):
+            raise ValueError("precision must be 'bf16' or 'high'")
+        self.precision = precision
+        return self
+
+    def _gemm_weight_names(self):
+        return [n for n, (_, _, shape) in self.layout.entries.items()
+                if len(shape) == 2 and shape[1] % 64 == 0 and "embedding" not in n]
+
+    def _refresh_hp(self, key):
+        """hi|hi|lo image of every GEMM weight ([out, 3*in] bf16 at element offset 3*off of ``_flat_hp``)."""
+        if self._flat_hp is not None and self._hp_key == key and not self._bf16_fresh:
+            return
+        L = _L.lib()
+        if self._flat_hp is None or self._flat_hp.device != self._flat.device:
+            self._flat_hp = torch.zeros(3 * self.layout.total, dtype=torch.bfloat16, device=self._flat.device)
+            self._structs_hp = None
+        for n in self._gemm_weight_names():
+            off, _, shape = self.layout.entries[n]
+            _L._check(L.etp_split3(C.c_void_p(self._flat.data_ptr() + 4 * off), C.c_void_p(self._flat_hp.data_ptr() + 6 * off),
+                                   shape[0], shape[1], 1, _L.stream_ptr()), "etp_split3")
+        if self._structs_hp is None:
+            self._structs_hp = self._build_structs(self._flat.data_ptr(), self._flat_hp.data_ptr(), 6)
+            self._b32, self._b16, self._s16 = self._flat.data_ptr(), self._flat_bf16.data_ptr(), 2
+        self._hp_key = key
+        self._bf16_fresh = False
+
+    def _hp_guard(self, wants_grad):
+        if wants_grad:
+            raise _L.EtpError("precision='high' is an inference mode (no backward exists for it): call under "
+                              "torch.no_grad(), or set_precision('bf16') for training")
 
     # ------------------------------------------------------------------ ctypes weight structs
     def _version_key(self):
@@ -411,6 +469,9 @@ class B200Planner(nn.Module):
             raise ValueError("sequence longer than max_position_embeddings")
         ids = txt_ids.contiguous().long()
         mk = self._mask_u8(txt_masks)
+        if self.precision == "high":
+            self._hp_guard(self._wants_grad("txt") and self.config.update_lang_bert)
+            return _txt_forward_hp(self, ids, mk)
         drop = self._next_dropout()
         if self._wants_grad("txt") and self.config.update_lang_bert:
             params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._group_names("txt")]
@@ -422,6 +483,10 @@ class B200Planner(nn.Module):
         self._refresh_cache()
         nt, vl = nav_types.contiguous().long(), view_lens.contiguous().long()
         loc = _f32c(loc_fts)
+        if self.precision == "high":
+            self._hp_guard(self._wants_grad("pano", rgb_fts, dep_fts))
+            out, masks = _pano_forward_hp(self, _f32c(rgb_fts), _f32c(dep_fts), loc, nt, vl)
+            return out, masks.view(torch.bool)
         drop = self._next_dropout()
         if self._wants_grad("pano", rgb_fts, dep_fts):
             params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._pano_param_names()]
@@ -440,6 +505,10 @@ class B200Planner(nn.Module):
         self._refresh_cache()
         aux = (self._mask_u8(txt_masks), gmap_step_ids.contiguous().long(), _f32c(gmap_pos_fts),
                self._mask_u8(gmap_masks), self._mask_u8(gmap_visited_masks), _f32c(gmap_pair_dists))
+        if self.precision == "high":
+            self._hp_guard(self._wants_grad("nav", txt_embeds, gmap_img_fts))
+            embeds, logits = _nav_forward_hp(self, _f32c(txt_embeds), _f32c(gmap_img_fts), aux)
+            return {"gmap_embeds": embeds, "global_logits": logits}
         drop = self._next_dropout()
         if self._wants_grad("nav", txt_embeds, gmap_img_fts):
             params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._group_names("nav")]
@@ -520,6 +589,44 @@ def _nav_forward(m, txt, img, aux, training, drop=None):
     return embeds, logits, saved, ni
 
 
+def _txt_forward_hp(m, ids, mk):
+    B, Lt = ids.shape
+    L = _L.lib()
+    out = torch.empty(B, Lt, 768, device=ids.device, dtype=torch.float32)
+    nbytes = L.etp_hp_txt_work_bytes(B, Lt)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=ids.device)
+    _L._check(L.etp_forward_txt_hp(C.byref(m._structs_hp["txt"]), _L.ptr(ids), _L.ptr(mk), B, Lt, _L.ptr(out), _L.ptr(work),
+                                   nbytes, _L.stream_ptr()), "etp_forward_txt_hp")
+    return out
+
+
+def _pano_forward_hp(m, rgb, dep, loc, nt, vl):
+    B, V = rgb.shape[:2]
+    L = _L.lib()
+    out = torch.empty(B, V, 768, device=rgb.device, dtype=torch.float32)
+    masks = torch.empty(B, V, device=rgb.device, dtype=torch.uint8)
+    pi = _pano_inputs(rgb, dep, loc, nt, vl)
+    nbytes = L.etp_hp_pano_work_bytes(B, V)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=rgb.device)
+    _L._check(L.etp_forward_panorama_hp(C.byref(m._structs_hp["pano"]), C.byref(pi), _L.ptr(out), _L.ptr(masks), _L.ptr(work),
+                                        nbytes, _L.stream_ptr()), "etp_forward_panorama_hp")
+    return out, masks
+
+
+def _nav_forward_hp(m, txt, img, aux):
+    B, N = img.shape[:2]
+    Lt = txt.shape[1]
+    L = _L.lib()
+    ni = _nav_inputs(txt, img, aux)
+    embeds = torch.empty(B, N, 768, device=img.device, dtype=torch.float32)
+    logits = torch.empty(B, N, device=img.device, dtype=torch.float32)
+    nbytes = L.etp_hp_nav_work_bytes(B, N, Lt, m.config.num_x_layers)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=img.device)
+    _L._check(L.etp_forward_navigation_hp(C.byref(m._structs_hp["nav"]), C.byref(ni), _L.ptr(embeds), _L.ptr(logits),
+                                          _L.ptr(work), nbytes, _L.stream_ptr()), "etp_forward_navigation_hp")
+    return embeds, logits
+
+
 # ----------------------------------------------------------------------------------------------------
 # autograd glue: one node per reference method; backward = one step-level C call
 # ----------------------------------------------------------------------------------------------------
@@ -535,6 +642,7 @@ class _NavFn(torch.autograd.Function):
         txt, img = _f32c(txt_embeds), _f32c(gmap_img_fts)
         embeds, logits, saved, _ = _nav_forward(m, txt, img, aux, 1, drop)
         ctx.m, ctx.saved, ctx.keep, ctx.nparams, ctx.drop = m, saved, (txt, img, aux), len(params), drop
+        ctx.in_dtypes = (txt_embeds.dtype, gmap_img_fts.dtype)
         return embeds, logits
 
     @staticmethod
@@ -560,6 +668,10 @@ class _NavFn(torch.autograd.Function):
                                             _L.ptr(dl), _L.ptr(ctx.saved), ctx.saved.numel(), _L.ptr(work), wbytes,
                                             _L.ptr(d_txt), _L.ptr(d_img), _L.stream_ptr()), "etp_backward_navigation")
         pg = _param_grads(m, m._group_names("nav"), gbuf, gstart, per_call, ctx.nparams)
+        if d_txt is not None and d_txt.dtype != ctx.in_dtypes[0]:
+            d_txt = d_txt.to(ctx.in_dtypes[0])
+        if d_img is not None and d_img.dtype != ctx.in_dtypes[1]:
+            d_img = d_img.to(ctx.in_dtypes[1])
         return (None, d_txt, d_img, None, None, None, *pg)
 
 
@@ -569,6 +681,7 @@ class _PanoFn(torch.autograd.Function):
         rgb, dep = _f32c(rgb_fts), _f32c(dep_fts)
         out, masks, saved, _ = _pano_forward(m, rgb, dep, loc, nt, vl, 1, drop)
         ctx.m, ctx.saved, ctx.keep, ctx.nparams, ctx.drop = m, saved, (rgb, dep, loc, nt, vl, masks), len(params), drop
+        ctx.in_dtypes = (rgb_fts.dtype, dep_fts.dtype)
         mb = masks.view(torch.bool)
         ctx.mark_non_differentiable(mb)
         return out, mb
@@ -584,6 +697,8 @@ class _PanoFn(torch.autograd.Function):
             gbuf, gstart, per_call = m._direct_grad, 0, False
             gst = m._grad_structs_for(gbuf, gstart)
             tok = None
+            if getattr(m, "_tok_scratch", None) is not None:
+                gst["pano"].tok_emb1 = C.c_void_p(m._tok_scratch.data_ptr())
         else:
             # group-sized scratch + 768 extra floats for the token-type row 1, which lives in the txt group
             gbuf = torch.zeros(ge - gs + 768, dtype=torch.float32, device=rgb.device)
@@ -610,6 +725,10 @@ class _PanoFn(torch.autograd.Function):
             pg.append(tt)
         if d_dep is None and ctx.needs_input_grad[2]:
             d_dep = torch.zeros_like(dep)
+        if d_rgb is not None and d_rgb.dtype != ctx.in_dtypes[0]:
+            d_rgb = d_rgb.to(ctx.in_dtypes[0])
+        if d_dep is not None and d_dep.dtype != ctx.in_dtypes[1]:
+            d_dep = d_dep.to(ctx.in_dtypes[1])
         return (None, d_rgb, d_dep, None, None, None, None, None, *pg)
 
 
@@ -646,8 +765,18 @@ class PlannerTrainer:
 
     def __init__(self, model, lr=1e-5, world_size=1, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, groups=("pano", "nav")):
         self.m, self.lr, self.world, self.betas, self.eps, self.wd = model, lr, world_size, betas, eps, weight_decay
-        model._refresh_cache()
         dev = model._flat.device
+        if world_size > 1:
+            # DDP broadcasts rank 0's parameters when it wraps the module (ss_trainer_ETP.py:211-212): replicas built from
+            # different seeds, or loaded on one rank only, must not silently diverge while their gradients are averaged
+            import torch.distributed as dist
+            with torch.no_grad():
+                dist.broadcast(model._flat, src=0)
+            model._cache_key = None
+            # ... and every rank must draw its own dropout masks
+            if model._drop_base is None:
+                model._drop_base = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (dist.get_rank() + 1)) & 0xFFFFFFFFFFFFFFFF
+        model._refresh_cache()
         model._direct_grad = torch.zeros(model.layout.total, dtype=torch.float32, device=dev)
         self.lo = min(model.layout.group_ranges[g][0] for g in groups)
         self.hi = max(model.layout.group_ranges[g][1] for g in groups)
@@ -655,6 +784,14 @@ class PlannerTrainer:
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.t = 0
+        # torch.optim.AdamW skips parameters without a gradient (frozen by fix_pano_embedding / fix_lang_embedding,
+        # vilmodel_cmt.py:675-682): only the runs of the slice whose parameters require a gradient are stepped (one run
+        # when nothing is frozen), so frozen weights see neither an update nor weight decay
+        self.active = self._active_ranges(model, self.lo, self.hi)
+        # forward_panorama reads row 1 of the token-type table, which lives in the txt group: when that group is not
+        # stepped here its gradient goes to a scratch row instead of piling up, unapplied, in the flat gradient buffer
+        gs, ge = model.layout.group_ranges["txt"]
+        model._tok_scratch = None if (self.lo <= gs and ge <= self.hi) else torch.zeros(768, dtype=torch.float32, device=dev)
         # data parallel: the gradient slice is reduced in buckets, in the order the backward completes them, on a side
         # stream: x-layer i's bucket starts as soon as the event the nav backward records for it fires
         self.buckets, self.side, self._events = None, None, []
@@ -674,8 +811,29 @@ class PlannerTrainer:
         L.etp_adamw_step.argtypes = [p_void, p_void, p_void, p_void, p_void, C.c_int64, f32, f32, f32, f32, f32, i32, f32,
                                      p_void]
 
+    @staticmethod
+    def _active_ranges(model, lo, hi):
+        """Maximal runs [a, b) of the flat layout inside [lo, hi) whose parameters all require a gradient (the alignment
+        padding between two trainable tensors is part of the run: it holds zeros and stays zero)."""
+        ents = sorted((off, off + numel, model._pmap[name].requires_grad)
+                      for name, (off, numel, _) in model.layout.entries.items() if lo <= off < hi)
+        runs, cur = [], None
+        for i, (a, b, req) in enumerate(ents):
+            nxt = ents[i + 1][0] if i + 1 < len(ents) else hi
+            if req:
+                cur = [a, nxt] if cur is None else [cur[0], nxt]
+            elif cur is not None:
+                cur[1] = a
+                runs.append(tuple(cur))
+                cur = None
+        if cur is not None:
+            runs.append((cur[0], hi))
+        return runs
+
     def zero_grad(self):
         self.m._direct_grad[self.lo:self.hi].zero_()
+        if self.m._tok_scratch is not None:
+            self.m._tok_scratch.zero_()
 
     def forward_backward(self, d):
         m = self.m
@@ -719,11 +877,14 @@ class PlannerTrainer:
             scale = allreduce_buckets_(g, self.buckets, self.world, self.side, waits)
             main.wait_stream(self.side)
         self.t += 1
-        _L._check(_L.lib().etp_adamw_step(
-            C.c_void_p(m._flat.data_ptr() + 4 * self.lo), C.c_void_p(m._flat_bf16.data_ptr() + 2 * self.lo), _L.ptr(g),
-            _L.ptr(self.exp_avg), _L.ptr(self.exp_avg_sq), self.hi - self.lo, self.lr, self.betas[0], self.betas[1], self.eps,
-            self.wd, self.t, scale, _L.stream_ptr()), "etp_adamw_step")
-        m._bf16_fresh = True  # AdamW rewrote the bf16 image of the updated slice
+        for a, b in self.active:
+            o = a - self.lo
+            _L._check(_L.lib().etp_adamw_step(
+                C.c_void_p(m._flat.data_ptr() + 4 * a), C.c_void_p(m._flat_bf16.data_ptr() + 2 * a),
+                C.c_void_p(g.data_ptr() + 4 * o), C.c_void_p(self.exp_avg.data_ptr() + 4 * o),
+                C.c_void_p(self.exp_avg_sq.data_ptr() + 4 * o), b - a, self.lr, self.betas[0], self.betas[1], self.eps,
+                self.wd, self.t, scale, _L.stream_ptr()), "etp_adamw_step")
+        m._bf16_fresh = True  # AdamW rewrote the flat parameters and their bf16 image (a high-precision image is now stale)
 
     def step(self, d):
         self.zero_grad()

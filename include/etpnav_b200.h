@@ -313,6 +313,28 @@ int etp_forward_txt(const etp_txt_weights* w, const int64_t* txt_ids, const uint
                     const etp_dropout* dropout);
 
 /* ---------------------------------------------------------------------------------------------
+ * high-precision forward mode (inference): what the reference's eval()/inference() rollouts compute in fp32
+ * (ss_trainer_ETP.py:513-756, no autocast) and what BASELINE.json's parity band (rtol 1e-3 / atol 1e-4) needs.
+ * Every contraction stays on tcgen05 as a SPLIT-bf16 x3 product realised by tripling K:
+ *   A' = [A_hi | A_lo | A_hi] (etp_split3 form 0),  B' = [B_hi | B_hi | B_lo] (form 1),  D = A'.B'^T = etp_gemm(K' = 3K);
+ * attention runs in fp32 on the CUDA cores (etp_attention_f32_fwd: etp_attn_args with q/k/v/out FLOAT pointers, lse and
+ * impl ignored); activations stay fp32.  The weight structs are the ones of the bf16 mode with every GEMM-weight
+ * pointer redirected to the form-1 image of that weight ([out, 3*in] bf16).  `work`: scratch of etp_hp_*_work_bytes.
+ * No activation record, no backward.
+ * ------------------------------------------------------------------------------------------- */
+int etp_split3(const float* x, void* y_bf16, int64_t rows, int32_t K, int32_t form, void* stream);
+int etp_attention_f32_fwd(const etp_attn_args* args, void* stream);
+size_t etp_hp_nav_work_bytes(int32_t B, int32_t N, int32_t L, int32_t num_x_layers);
+size_t etp_hp_pano_work_bytes(int32_t B, int32_t V);
+size_t etp_hp_txt_work_bytes(int32_t B, int32_t L);
+int etp_forward_navigation_hp(const etp_nav_weights* w, const etp_nav_inputs* in, float* gmap_embeds,
+                              float* global_logits, void* work, size_t work_bytes, void* stream);
+int etp_forward_panorama_hp(const etp_pano_weights* w, const etp_pano_inputs* in, float* pano_embeds,
+                            uint8_t* pano_masks, void* work, size_t work_bytes, void* stream);
+int etp_forward_txt_hp(const etp_txt_weights* w, const int64_t* txt_ids, const uint8_t* txt_masks, int32_t B, int32_t L,
+                       float* txt_embeds, void* work, size_t work_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * step level, backward (autograd counterparts; the reference gets these from torch autograd via
  * scaler.scale(loss).backward(), ss_trainer_ETP.py:504).
  * `grads` is the same struct type as the weights with EVERY pointer redirected into a flat fp32

@@ -79,6 +79,71 @@ def test_backward_matches_golden(name):
         f.write(json.dumps(rep) + "\n")
 
 
+def test_parameter_gradients_full_tensors_c1():
+    """Every parameter gradient of the c1_bert fixture as a FULL tensor: (i) against the fp32 oracle port run here on the
+    same inputs (the port's gradients are pinned to the reference's by tests/test_oracle.py), relative L2 and cosine per
+    tensor; (ii) against the gradient sketches of the UNMODIFIED reference (tests/golden_grads, oracle/make_golden_grads.py:
+    all row sums, all column sums, two full rows per matrix; full 1-D tensors) — a sign or indexing error confined to any
+    slice of a weight gradient moves its row / column sums."""
+    from etpnav_b200.planner import B200Planner
+    from oracle import planner_port as P
+    from oracle.make_golden_grads import TEXT_PREFIXES
+    from tests.common import GOLDEN_GRADS_DIR
+    gold, cfg, sd, inp = load_case("c1_bert")
+    no_dropout(cfg)
+    sk = torch.load(os.path.join(GOLDEN_GRADS_DIR, "c1_bert.pt"), weights_only=False)
+    m = B200Planner(cfg, device="cuda")
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    d = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    txt = gold["txt_embeds"].cuda()
+    pano, pm = m.forward_panorama(d["rgb_fts"], d["dep_fts"], d["loc_fts"], d["nav_types"], d["view_lens"])
+    nav = m.forward_navigation(txt, d["txt_masks"], None, d["gmap_step_ids"], d["gmap_img_fts"], d["gmap_pos_fts"],
+                               d["gmap_masks"], d["gmap_visited_masks"], d["gmap_pair_dists"])
+    golden_loss(gold, pano, pm, nav["gmap_embeds"], nav["global_logits"], inp).backward()
+    sdc = {k: (v.cuda().clone().requires_grad_(True) if not k.startswith(TEXT_PREFIXES) else v.cuda()) for k, v in sd.items()}
+    pano_o, pm_o = P.forward_panorama(sdc, cfg, d["rgb_fts"], d["dep_fts"], d["loc_fts"], d["nav_types"], d["view_lens"])
+    nav_o = P.forward_navigation(sdc, cfg, txt, d["txt_masks"], None, d["gmap_step_ids"], d["gmap_img_fts"], d["gmap_pos_fts"],
+                                 d["gmap_masks"], d["gmap_visited_masks"], d["gmap_pair_dists"])
+    golden_loss(gold, pano_o, pm_o, nav_o["gmap_embeds"], nav_o["global_logits"], inp).backward()
+    torch.cuda.synchronize()
+    checked, worst = 0, ("", 0.0)
+    for k, ref in sk["sketch"].items():
+        g = m._pmap[k].grad
+        assert g is not None, k
+        go = sdc[k].grad
+        # (i) full tensor vs the oracle
+        if go.norm() < 1e-6:
+            assert g.norm() < 1e-2, k     # analytically zero (key biases, sprel bias): bf16 noise only
+            continue
+        r = _rel(g, go)
+        cos = torch.nn.functional.cosine_similarity(g.flatten().double(), go.flatten().double(), dim=0).item()
+        worst = max(worst, (k, r), key=lambda t: t[1])
+        lim = 0.25 if go.numel() == 1 else REL_NORM_PARAM
+        assert r < lim and cos > 1 - lim * lim, (k, r, cos)
+        # (ii) sketch of the unmodified reference's gradient
+        gc = g.detach().float().cpu()
+        if "full" in ref:
+            assert _rel(gc, ref["full"]) < lim, (k, "full")
+        else:
+            g2 = gc.reshape(gc.shape[0], -1)
+            R = g2.shape[0]
+            # bf16 rounding errors are independent per element: summed over a row / column they grow like the sum of
+            # independent entries would, so every vector is measured against max(|reference vector|, the norm the vector
+            # would have if the summed entries had random signs) — this keeps analytically-cancelling sums (columns of a
+            # weight feeding a LayerNorm sum to ~0) from turning rounding noise into a huge relative error
+            row_norm = g2.norm().item() / R ** 0.5
+            for name, got, want, floor in (("row_sum", g2.double().sum(1).float(), ref["row_sum"], row_norm * R ** 0.5),
+                                           ("col_sum", g2.double().sum(0).float(), ref["col_sum"], row_norm * R ** 0.5),
+                                           ("rows", g2[ref["rows"]], ref["row_vals"], row_norm * 2 ** 0.5)):
+                err = (got - want).norm().item()
+                assert err < 1.5 * lim * max(want.norm().item(), floor, 1e-12), (k, name, err, want.norm().item(), floor)
+        checked += 1
+    assert checked >= 140, checked
+    with open(REPORT, "a") as f:
+        f.write(json.dumps({"case": "c1_bert", "kind": "full_param_grads", "tensors": checked, "worst_rel_l2": worst}) + "\n")
+
+
 def test_txt_backward_matches_oracle():
     """forward_txt backward (language encoder) against the fp32 oracle port."""
     from etpnav_b200.config import PlannerConfig

@@ -200,3 +200,80 @@ def test_txt_matches_oracle_with_the_same_masks():
             assert prm.grad.norm() < 1e-2, n
             continue
         assert _rel(prm.grad, sdc[n].grad) < 0.12, (n, _rel(prm.grad, sdc[n].grad))
+
+
+def test_benched_c3_configuration_with_dropout_matches_oracle():
+    """The configuration bench.py times (BASELINE.json configs[2]: B=64, 12 views, 80 nodes, 200 tokens, SIX cross-modal
+    layers, train() dropout on) against the fp32 oracle fed with the kernels' own masks.  The CUDA path runs the full
+    batch; the oracle runs the first S episodes — a dropout mask is a function of the element index in the full
+    tensor with the batch outermost, so the first S episodes' flags are a prefix of every site's stream."""
+    from etpnav_b200.config import PlannerConfig
+    from etpnav_b200.planner import B200Planner
+    from etpnav_b200.synth import make_inputs, make_weights
+    from oracle import planner_port as P
+    from tests.common import BF16_LOGIT_TOL
+    B, V, N, L, X, S = 64, 12, 80, 200, 6, 2
+    cfg = PlannerConfig(vocab_size=2048, num_l_layers=0, num_x_layers=X)   # dropout probabilities: the reference's 0.1
+    assert cfg.hidden_dropout_prob == 0.1 and cfg.attention_probs_dropout_prob == 0.1
+    sd = make_weights(cfg, seed=41)
+    inp = make_inputs(cfg, B, V, N, L, seed=41, ragged=False)
+    m = B200Planner(cfg, device="cuda")
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    m.set_dropout_seed(4321)
+    d = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
+    txt_k = d["txt_embeds"].clone().requires_grad_(True)
+    img_k = d["gmap_img_fts"].clone().requires_grad_(True)
+    rgb_k = d["rgb_fts"].clone().requires_grad_(True)
+    dp = _next_struct(m)
+    pano, pmask = m.forward_panorama(rgb_k, d["dep_fts"], d["loc_fts"], d["nav_types"], d["view_lens"])
+    dn = _next_struct(m)
+    nav = m.forward_navigation(txt_k, d["txt_masks"], None, d["gmap_step_ids"], img_k, d["gmap_pos_fts"], d["gmap_masks"],
+                               d["gmap_visited_masks"], d["gmap_pair_dists"])
+    g = torch.Generator().manual_seed(3)
+    wp = torch.randn(S, V, 768, generator=g).cuda()
+    we = torch.randn(S, N, 768, generator=g).cuda()
+    # the loss only looks at the first S episodes, so the two sides differentiate the same function
+    loss = (torch.nn.functional.cross_entropy(nav["global_logits"][:S], d["labels"][:S], reduction="sum")
+            + (pano[:S] * wp).sum() * 0.01 + (nav["gmap_embeds"][:S] * we).sum() * 0.01)
+    loss.backward()
+    torch.cuda.synchronize()
+
+    sdc = {k: v.cuda().clone().requires_grad_(True) for k, v in sd.items()}
+    s = {k: (v[:S].clone() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    txt_o, img_o, rgb_o = (s[k].clone().requires_grad_(True) for k in ("txt_embeds", "gmap_img_fts", "rgb_fts"))
+    hp, hn = _KernelMasks(dp, cfg), _KernelMasks(dn, cfg)
+    pano_o, _ = P.forward_panorama(sdc, cfg, rgb_o, s["dep_fts"], s["loc_fts"], s["nav_types"], s["view_lens"], drop=hp)
+    nav_o = P.forward_navigation(sdc, cfg, txt_o, s["txt_masks"], None, s["gmap_step_ids"], img_o, s["gmap_pos_fts"],
+                                 s["gmap_masks"], s["gmap_visited_masks"], s["gmap_pair_dists"], drop=hn)
+    loss_o = (torch.nn.functional.cross_entropy(nav_o["global_logits"], s["labels"], reduction="sum")
+              + (pano_o * wp).sum() * 0.01 + (nav_o["gmap_embeds"] * we).sum() * 0.01)
+    loss_o.backward()
+    assert len(hn.sites) == 5 * X + 1
+    lg, lo = nav["global_logits"][:S], nav_o["global_logits"]
+    assert torch.equal(torch.isinf(lg), torch.isinf(lo))
+    fin = ~torch.isinf(lo)
+    assert torch.equal(lg.argmax(1), lo.argmax(1))
+    e_log = (lg[fin] - lo[fin]).abs().max().item()
+    e_emb = (nav["gmap_embeds"][:S] - nav_o["gmap_embeds"]).abs().max().item()
+    e_pano = (pano[:S] - pano_o).abs().max().item()
+    print(f"c3 as benched (X=6, dropout on): logit {e_log:.4g} embed {e_emb:.4g} pano {e_pano:.4g}")
+    # dropout scales kept activations by 1/(1-p) and six layers compound: allow 2x the dropout-free envelope
+    assert e_log < 2 * BF16_LOGIT_TOL, e_log
+    assert e_emb < 8e-2 and e_pano < 6e-2, (e_emb, e_pano)
+    assert _rel(txt_k.grad[:S], txt_o.grad) < 0.1, _rel(txt_k.grad[:S], txt_o.grad)
+    assert _rel(img_k.grad[:S], img_o.grad) < 0.1
+    assert _rel(rgb_k.grad[:S], rgb_o.grad) < 0.1
+    assert txt_k.grad[S:].abs().max().item() == 0.0 and img_k.grad[S:].abs().max().item() == 0.0   # episodes are independent
+    worst = ("", 0.0)
+    for n, prm in m.named_parameters():
+        go = sdc[n].grad
+        if prm.grad is None or go is None:
+            continue
+        if go.norm() < 1e-5:
+            assert prm.grad.norm() < 1e-2, n
+            continue
+        r = _rel(prm.grad, go)
+        worst = max(worst, (n, r), key=lambda t: t[1])
+        assert r < (0.3 if go.numel() == 1 else 0.15), (n, r)
+    print("c3 as benched: worst full-tensor parameter-gradient rel L2", worst)

@@ -72,3 +72,33 @@ def test_port_matches_reference_fp64():
         fin = ~torch.isinf(n_ref["global_logits"])
         assert torch.equal(fin, ~torch.isinf(n_port["global_logits"]))
         assert (n_ref["global_logits"][fin] - n_port["global_logits"][fin]).abs().max() < 1e-11
+
+
+def test_port_full_gradients_match_reference_sketches():
+    """The port's FULL parameter gradients on c1_bert against the sketches of the unmodified reference's gradients
+    (tests/golden_grads: all row sums, all column sums, two full rows per matrix, full 1-D tensors)."""
+    import os
+    from oracle.make_golden_grads import TEXT_PREFIXES
+    from tests.common import GOLDEN_GRADS_DIR
+    gold, cfg, sd, inp = load_case("c1_bert")
+    sk = torch.load(os.path.join(GOLDEN_GRADS_DIR, "c1_bert.pt"), weights_only=False)
+    sd = {k: (v.clone().requires_grad_(True) if not k.startswith(TEXT_PREFIXES) else v) for k, v in sd.items()}
+    txt = gold["txt_embeds"]
+    pano, pm = P.forward_panorama(sd, cfg, inp["rgb_fts"], inp["dep_fts"], inp["loc_fts"], inp["nav_types"], inp["view_lens"])
+    nav = P.forward_navigation(sd, cfg, txt, inp["txt_masks"], None, inp["gmap_step_ids"], inp["gmap_img_fts"],
+                               inp["gmap_pos_fts"], inp["gmap_masks"], inp["gmap_visited_masks"], inp["gmap_pair_dists"])
+    loss = golden_loss(gold, pano, pm, nav["gmap_embeds"], nav["global_logits"], inp)
+    assert torch.allclose(loss, sk["loss"], rtol=1e-5, atol=1e-4)
+    loss.backward()
+    assert len(sk["sketch"]) >= 150
+    for k, ref in sk["sketch"].items():
+        g = sd[k].grad
+        assert g is not None, k
+        if "full" in ref:
+            assert torch.allclose(g, ref["full"], rtol=2e-3, atol=1e-5 * float(ref["full"].abs().max()) + 2e-7), k
+            continue
+        g2 = g.reshape(g.shape[0], -1)
+        big = float(g2.abs().max()) * g2.shape[1] ** 0.5
+        assert torch.allclose(g2[ref["rows"]], ref["row_vals"], rtol=2e-3, atol=1e-5 * float(g2.abs().max()) + 2e-7), k
+        assert torch.allclose(g2.double().sum(1).float(), ref["row_sum"], rtol=2e-3, atol=2e-5 * big + 2e-7), k
+        assert torch.allclose(g2.double().sum(0).float(), ref["col_sum"], rtol=2e-3, atol=2e-5 * float(g2.abs().max()) * g2.shape[0] ** 0.5 + 2e-7), k
