@@ -277,6 +277,7 @@ int forward_navigation_hp(const etp_nav_weights& w, const etp_nav_inputs& in, fl
                           void* work, size_t work_bytes, cudaStream_t s) {
   const int B = in.B, N = in.N, L = in.L, X = w.num_x_layers;
   ETP_REQUIRE(B > 0 && N > 0 && L > 0 && X >= 0, "forward_navigation_hp: bad shape");
+  ETP_REQUIRE(in.txt_embeds != nullptr, "forward_navigation_hp: fp32 txt_embeds required");
   Arena ar(work, work_bytes);
   HpNavBufs b;
   b.carve(ar, static_cast<size_t>(B) * N, static_cast<size_t>(B) * L, X);

@@ -204,6 +204,8 @@ int embed_txt_bwd(const float* dx, const int64_t* ids, const float* sum_pre, con
 // the bf16 image of the parameters.  grad_scale multiplies the gradient first (1/world_size after all-reduce).
 int adamw_step(float* param, bf16* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-               cudaStream_t stream);
+               cudaStream_t stream, const uint8_t* flags = nullptr, const float* normsq = nullptr, float max_norm = 0.0f);
+// out[0] += sum g^2 over the blocks whose flag bit 0 is set (all of them when flags == nullptr)
+int grad_sumsq(const float* grad, int64_t n, const uint8_t* flags, float* out, cudaStream_t stream);
 
 }  // namespace etp

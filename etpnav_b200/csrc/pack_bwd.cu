@@ -349,14 +349,27 @@ int embed_txt_bwd(const float* dx, const int64_t* ids, const float* sum_pre, con
 
 // ---------------------------------------------------------------------------------------------------
 // AdamW (torch.optim.AdamW, ss_trainer_ETP.py:213): p *= 1 - lr*wd ; m, v update ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+// flags (optional): one byte per 64-element block of the flat layout (every tensor starts on a 64-element boundary):
+// bit 0 = the block belongs to a trainable parameter (torch's AdamW skips parameters without a gradient), bit 1 = weight
+// decay applies (the reference's pre-training optimizer has a no-decay group for biases and LayerNorm, optim/misc.py:14-20).
+// normsq (optional): device scalar holding sum g^2 over the trainable blocks; with max_norm > 0 the gradient is scaled by
+// min(1, max_norm / (gscale * sqrt(normsq) + 1e-6)) like torch.nn.utils.clip_grad_norm_ (train_r2r.py:279-284).
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, bf16* __restrict__ pb, const float* __restrict__ g,
                                                      float* __restrict__ m, float* __restrict__ v, int64_t n4, float lr,
                                                      float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                     float gscale) {
+                                                     float gscale, const uint8_t* __restrict__ flags,
+                                                     const float* __restrict__ normsq, float max_norm) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory
+  if (normsq != nullptr && max_norm > 0.0f) {
+    const float total = gscale * sqrtf(__ldg(normsq));
+    gscale *= fminf(1.0f, max_norm / (total + 1e-6f));
+  }
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t fl = flags ? flags[i >> 4] : 3u;
+    if (!(fl & 1u)) continue;
+    const float decay = (fl & 2u) ? 1.0f - lr * wd : 1.0f;
     float4 pv = reinterpret_cast<float4*>(p)[i];
     const float4 gv = reinterpret_cast<const float4*>(g)[i];
     float4 mv = reinterpret_cast<float4*>(m)[i];
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, bf16*
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float gr = gg[k] * gscale;
-      pp[k] *= 1.0f - lr * wd;
+      pp[k] *= decay;
       mm[k] = b1 * mm[k] + (1.0f - b1) * gr;
       vq[k] = b2 * vq[k] + (1.0f - b2) * gr * gr;
       const float denom = sqrtf(vq[k]) / bc2_sqrt + eps;
@@ -383,7 +396,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, bf16*
 
 int adamw_step(float* param, bf16* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-               cudaStream_t stream) {
+               cudaStream_t stream, const uint8_t* flags, const float* normsq, float max_norm) {
   ETP_REQUIRE(n % 4 == 0, "adamw: element count must be a multiple of 4 (flat buffers are 64-element aligned)");
   ETP_REQUIRE(step >= 1, "adamw: step counts from 1");
   if (n == 0) return ETP_OK;
@@ -392,7 +405,41 @@ int adamw_step(float* param, bf16* param_bf16, const float* grad, float* exp_avg
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
   ETP_CHECK_CUDA(launch_pdl(adamw_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, param, param_bf16, grad, exp_avg, exp_avg_sq, n / 4, lr, beta1,
-                                                             beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale));
+                                                             beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, flags, normsq, max_norm));
+  ETP_LAUNCHED();
+  return ETP_OK;
+}
+
+// out[0] += sum of g^2 over the trainable 64-element blocks (the squared global gradient norm of clip_grad_norm_)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n4, const uint8_t* __restrict__ flags,
+                                                     float* __restrict__ out) {
+  griddep_launch();
+  griddep_wait();
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (flags && !(flags[i >> 4] & 1u)) continue;
+    const float4 t = reinterpret_cast<const float4*>(g)[i];
+    acc += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k];
+    atomicAdd(out, s);
+  }
+}
+
+int grad_sumsq(const float* grad, int64_t n, const uint8_t* flags, float* out, cudaStream_t stream) {
+  ETP_REQUIRE(n % 4 == 0 && grad && out, "grad_sumsq: bad argument");
+  if (n == 0) return ETP_OK;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  ETP_CHECK_CUDA(launch_pdl(sumsq_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, grad, n / 4, flags, out));
   ETP_LAUNCHED();
   return ETP_OK;
 }

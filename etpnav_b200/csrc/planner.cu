@@ -192,7 +192,12 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
   DropCtx dc;
   if (in.dropout) { dc.seed = in.dropout->seed; dc.p_hidden = in.dropout->p_hidden; dc.p_attn = in.dropout->p_attn; dc.p_head = in.dropout->p_head; }
 
-  ETP_TRY(cast_f32_to_bf16(in.txt_embeds, rec.txtb, static_cast<int64_t>(B) * L * kH, s));
+  const bf16* txtb = static_cast<const bf16*>(in.txt_embeds_bf16);
+  if (txtb == nullptr) {
+    ETP_REQUIRE(in.txt_embeds != nullptr, "forward_navigation: txt_embeds (fp32) or txt_embeds_bf16 is required");
+    ETP_TRY(cast_f32_to_bf16(in.txt_embeds, rec.txtb, static_cast<int64_t>(B) * L * kH, s));
+    txtb = rec.txtb;
+  }
   NodePackArgs np;
   np.rows = rows; np.img_fts = in.gmap_img_fts; np.step_ids = in.gmap_step_ids; np.pos_fts = in.gmap_pos_fts;
   np.pos_w = w.pos_w; np.pos_b = w.pos_b; np.pos_g = w.pos_g; np.pos_bb = w.pos_bb; np.step_emb = w.step_emb;
@@ -202,7 +207,7 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
 
   // text K|V of every layer in ONE GEMM: [B*L,768] x [X*1536,768]^T (they depend only on txt_embeds)
   if (X > 0)
-    ETP_TRY(linear(rec.txtb, B * L, kH, w.xkv_all_w, X * 2 * kH, w.xkv_all_b, 0, nullptr, nullptr, rec.kv_all, nullptr, s));
+    ETP_TRY(linear(txtb, B * L, kH, w.xkv_all_w, X * 2 * kH, w.xkv_all_b, 0, nullptr, nullptr, rec.kv_all, nullptr, s));
   const float* x_f32 = np.x_f32;
   const bf16* x_bf16 = rec.x0b;
   for (int i = 0; i < X; ++i) {
@@ -336,6 +341,7 @@ int forward_lang2visn(const etp_nav_weights& w, const etp_nav_inputs& in, float*
   const int B = in.B, N = in.N, L = in.L, X = w.num_x_layers;
   ETP_REQUIRE(B > 0 && N > 0 && L > 0 && X >= 1, "forward_lang2visn: bad shape");
   ETP_REQUIRE(N <= 1024 && L <= 1024, "forward_lang2visn: at most 1024 nodes / tokens");
+  ETP_REQUIRE(in.txt_embeds != nullptr, "forward_lang2visn: fp32 txt_embeds required (the tokens are the residual stream)");
   Arena ar(saved, saved_bytes);
   L2VRecord rec;
   rec.carve(ar, B, N, L, X, training);

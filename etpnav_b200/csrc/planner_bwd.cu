@@ -248,7 +248,8 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
   }
   // text side, all layers at once: kv_all = txt . Wkv_all^T + b  ->  one wgrad, one dgrad (bias grads: above)
   if (X > 0) {
-    ETP_TRY(wgrad(sc.dkv, kv_rows, ldkv, ldkv, rec.txtb, kH, kH, const_cast<void*>(g.xkv_all_w), s));
+    const bf16* txtb = in.txt_embeds_bf16 ? static_cast<const bf16*>(in.txt_embeds_bf16) : rec.txtb;
+    ETP_TRY(wgrad(sc.dkv, kv_rows, ldkv, ldkv, txtb, kH, kH, const_cast<void*>(g.xkv_all_w), s));
     if (d_txt_embeds) ETP_TRY(dgrad(sc.dkv, kv_rows, ldkv, ldkv, w.xkv_all_w, kH, nullptr, dtxt, nullptr, 0, nullptr, s));
   } else if (d_txt_embeds) {
     ETP_CHECK_CUDA(cudaMemsetAsync(d_txt_embeds, 0, static_cast<size_t>(kv_rows) * kH * 4, s));
@@ -517,6 +518,18 @@ ETP_API int etp_adamw_step(float* param, void* param_bf16, const float* grad, fl
                            void* stream) {
   return adamw_step(param, static_cast<bf16*>(param_bf16), grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                     step, grad_scale, S(stream));
+}
+
+/* AdamW with per-block flags (one byte per 64 elements: bit 0 trainable, bit 1 weight decay; NULL = all set) and optional
+ * global-norm clipping: normsq = device scalar with sum g^2 (etp_grad_sumsq), max_norm <= 0 disables it. */
+ETP_API int etp_adamw_step_ex(float* param, void* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                              float grad_scale, const uint8_t* flags, const float* normsq, float max_norm, void* stream) {
+  return adamw_step(param, static_cast<bf16*>(param_bf16), grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                    step, grad_scale, S(stream), flags, normsq, max_norm);
+}
+ETP_API int etp_grad_sumsq(const float* grad, int64_t n, const uint8_t* flags, float* out, void* stream) {
+  return grad_sumsq(grad, n, flags, out, S(stream));
 }
 
 }  // extern "C"

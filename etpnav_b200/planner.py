@@ -49,7 +49,7 @@ class NavInputs(C.Structure):
     _fields_ = [("B", i32), ("N", i32), ("L", i32)] + [
         (n, p_void) for n in ("txt_embeds", "txt_masks", "gmap_step_ids", "gmap_img_fts", "gmap_pos_fts",
                               "gmap_masks", "gmap_visited_masks", "gmap_pair_dists")] + [
-        ("dropout", C.POINTER(Dropout)), ("layer_done_events", C.POINTER(p_void))]
+        ("dropout", C.POINTER(Dropout)), ("layer_done_events", C.POINTER(p_void)), ("txt_embeds_bf16", p_void)]
 
 
 class PanoLayerWeights(C.Structure):
@@ -126,6 +126,11 @@ class _Holder(nn.Module):
 
 def _f32c(t):
     return t.detach().float().contiguous()
+
+
+def _txtc(t):
+    """txt_embeds as the navigation kernels take it: bf16 stays bf16 (no cast kernel), everything else becomes fp32."""
+    return t.detach().contiguous() if t.dtype == torch.bfloat16 else _f32c(t)
 
 
 class B200Planner(nn.Module):
@@ -255,8 +260,10 @@ class B200Planner(nn.Module):
         return self
 
     def _gemm_weight_names(self):
+        # every 2-D parameter consumed as a GEMM B operand; the embedding TABLES (word / position / token-type / step /
+        # nav-type: ``<...>embedding(s).weight``) are gathered in fp32 and skipped
         return [n for n, (_, _, shape) in self.layout.entries.items()
-                if len(shape) == 2 and shape[1] % 64 == 0 and "embedding" not in n]
+                if len(shape) == 2 and shape[1] % 64 == 0 and "embedding" not in n.split(".")[-2]]
 
     def _refresh_hp(self, key):
         """hi|hi|lo image of every GEMM weight ([out, 3*in] bf16 at element offset 3*off of ``_flat_hp``)."""
@@ -514,7 +521,7 @@ class B200Planner(nn.Module):
             params = [] if self._direct_grad is not None else [self._pmap[n] for n in self._group_names("nav")]
             embeds, logits = _NavFn.apply(self, txt_embeds, gmap_img_fts, aux, drop, self._anchor_t(), *params)
         else:
-            embeds, logits, _, _ = _nav_forward(self, _f32c(txt_embeds), _f32c(gmap_img_fts), aux, 0, drop)
+            embeds, logits, _, _ = _nav_forward(self, _txtc(txt_embeds), _f32c(gmap_img_fts), aux, 0, drop)
         return {"gmap_embeds": embeds, "global_logits": logits}
 
     # ------------------------------------------------------------------ training helper
@@ -569,7 +576,11 @@ def _nav_inputs(txt, img, aux, drop=None):
     if drop is not None:
         ni.dropout = C.pointer(drop)
     ni.B, ni.N, ni.L = img.shape[0], img.shape[1], txt.shape[1]
-    ni.txt_embeds, ni.txt_masks, ni.gmap_step_ids = _L.ptr(txt), _L.ptr(tm), _L.ptr(ids)
+    if txt.dtype == torch.bfloat16:     # bf16 instruction embeddings are consumed as they are (etp_nav_inputs.txt_embeds_bf16)
+        ni.txt_embeds_bf16 = _L.ptr(txt)
+    else:
+        ni.txt_embeds = _L.ptr(txt)
+    ni.txt_masks, ni.gmap_step_ids = _L.ptr(tm), _L.ptr(ids)
     ni.gmap_img_fts, ni.gmap_pos_fts, ni.gmap_masks = _L.ptr(img), _L.ptr(pos), _L.ptr(gm)
     ni.gmap_visited_masks, ni.gmap_pair_dists = _L.ptr(vm), _L.ptr(pd)
     return ni
@@ -639,7 +650,7 @@ def _param_grads(m, names, gbuf, gstart, per_call, nparams):
 class _NavFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, m, txt_embeds, gmap_img_fts, aux, drop, anchor, *params):
-        txt, img = _f32c(txt_embeds), _f32c(gmap_img_fts)
+        txt, img = _txtc(txt_embeds), _f32c(gmap_img_fts)
         embeds, logits, saved, _ = _nav_forward(m, txt, img, aux, 1, drop)
         ctx.m, ctx.saved, ctx.keep, ctx.nparams, ctx.drop = m, saved, (txt, img, aux), len(params), drop
         ctx.in_dtypes = (txt_embeds.dtype, gmap_img_fts.dtype)
@@ -660,7 +671,7 @@ class _NavFn(torch.autograd.Function):
         dl = _f32c(d_logits) if d_logits is not None else None
         if dl is not None:
             dl = torch.nan_to_num(dl, nan=0.0, posinf=0.0, neginf=0.0)
-        d_txt = torch.empty_like(txt) if ctx.needs_input_grad[1] else None
+        d_txt = torch.empty(txt.shape, dtype=torch.float32, device=txt.device) if ctx.needs_input_grad[1] else None
         d_img = torch.empty_like(img) if ctx.needs_input_grad[2] else None
         wbytes = L.etp_nav_bwd_work_bytes(B, N, Lt, m.config.num_x_layers)
         work = torch.empty(wbytes, dtype=torch.uint8, device=img.device)

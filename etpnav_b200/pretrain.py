@@ -407,6 +407,8 @@ class B200PreTraining(nn.Module):
         config.mlm_head = True
         self.config = config
         self.bert = B200TextPathCMT(config, device=device)
+        self._register_state_dict_hook(self._sd_post_hook)
+        self._register_load_state_dict_pre_hook(self._sd_load_pre_hook)
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path=None, config=None, state_dict=None, device="cuda"):
@@ -432,26 +434,41 @@ class B200PreTraining(nn.Module):
     def _ref_key(k):
         return k if k.startswith(("mlm_head.", "global_sap_head.")) else "bert." + k
 
-    def state_dict(self, *a, **kw):
-        inner = self.bert.state_dict()
-        out = type(inner)((self._ref_key(k), v) for k, v in inner.items())
-        out["mlm_head.predictions.decoder.weight"] = out["bert.embeddings.word_embeddings.weight"]
-        return out
+    # The reference's key layout is produced / consumed by nn.Module's own state_dict machinery through two hooks, so it
+    # also holds when this model is a CHILD (DDP / DataParallel / any wrapper: train_r2r.py's ModelSaver calls
+    # ``model.state_dict()`` on the wrapper and strips ``module.``, utils/save.py:23-46): a parent's recursion reaches the
+    # hooks with its own ``destination`` / ``prefix``.
+    @staticmethod
+    def _sd_post_hook(module, state_dict, prefix, local_metadata):
+        for head in ("mlm_head.", "global_sap_head."):
+            src = prefix + "bert." + head
+            for k in [k for k in state_dict if k.startswith(src)]:
+                state_dict[prefix + head + k[len(src):]] = state_dict.pop(k)
+        w = prefix + "bert.embeddings.word_embeddings.weight"
+        if w in state_dict:   # tied decoder (pretrain_cmt.py:79-82)
+            state_dict[prefix + "mlm_head.predictions.decoder.weight"] = state_dict[w]
+        return state_dict
 
-    def load_state_dict(self, sd, strict=True):
-        own = set(self.bert.state_dict().keys())
-        inner, unexpected = {}, []
-        for k, v in sd.items():
-            if k == "mlm_head.predictions.decoder.weight" or k.endswith("position_ids"):
-                continue
-            kk = k[5:] if k.startswith("bert.") else k
-            if kk in own:
-                inner[kk] = v
-            else:
-                unexpected.append(k)
-        if strict and unexpected:
-            raise KeyError(f"unexpected keys: {unexpected[:5]}")
-        return self.bert.load_state_dict(inner, strict=strict)
+    @staticmethod
+    def _sd_load_pre_hook(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        state_dict.pop(prefix + "mlm_head.predictions.decoder.weight", None)
+        for k in [k for k in state_dict if k.startswith(prefix) and k.endswith("position_ids")]:
+            state_dict.pop(k)
+        for head in ("mlm_head.", "global_sap_head."):
+            src = prefix + head
+            for k in [k for k in state_dict if k.startswith(src)]:
+                state_dict[prefix + "bert." + head + k[len(src):]] = state_dict.pop(k)
+
+    def load_state_dict(self, sd, strict=True, **kw):
+        """Keys this model does not own are ignored unless ``strict`` (HF ``from_pretrained(state_dict=...)`` semantics)."""
+        own = set(self.state_dict().keys())
+        sd = {k: v for k, v in sd.items() if not k.endswith("position_ids")}
+        foreign = [k for k in sd if k not in own]
+        if strict and foreign:
+            raise KeyError(f"unexpected keys: {foreign[:5]}")
+        out = super().load_state_dict({k: v for k, v in sd.items() if k in own}, strict=strict, **kw)
+        self.bert._cache_key = None
+        return out
 
     def set_dropout(self, p: float):
         """Replacement for ``set_dropout(model, opts.dropout)`` (train_r2r.py:150, utils/misc.py:19-25)."""
@@ -518,24 +535,53 @@ class B200PreTraining(nn.Module):
 class PretrainTrainer:
     """Fused pre-training iteration (pretrain_src/pretrain_src/train_r2r.py:231-297): one task batch forward + backward
     through the step-level C calls with every parameter gradient accumulated straight into ONE flat fp32 buffer, one NCCL
-    all-reduce of that buffer when data-parallel (the reference wraps the model in DDP, train_r2r.py:113-116), and the
-    fused AdamW of the navigation trainer over the whole flat parameter buffer (betas (0.9, 0.98), weight decay 0.01 as
-    run_pt/r2r_pretrain_habitat.json; the reference's no-decay list for biases / LayerNorm and its grad-norm clipping are
-    not reproduced)."""
+    all-reduce of that buffer when data-parallel (the reference wraps the model in DDP, train_r2r.py:113-116; rank 0's
+    parameters are broadcast first, as DDP does), and the fused AdamW over the whole flat parameter buffer with the
+    reference's optimizer semantics: betas (0.9, 0.98), weight decay 0.01 except for biases and LayerNorm
+    (optim/misc.py:14-20), global gradient-norm clipping at 5.0 (run_pt/r2r_pretrain_habitat.json ``grad_norm``,
+    train_r2r.py:279-284), frozen parameters (``requires_grad = False``) left untouched."""
 
-    def __init__(self, model: "B200PreTraining", lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, world_size=1):
+    NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")   # optim/misc.py:14
+
+    def __init__(self, model: "B200PreTraining", lr=5e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, world_size=1,
+                 grad_norm=5.0):
         self.model, self.m = model, model.bert
         self.lr, self.betas, self.eps, self.wd, self.world = lr, betas, eps, weight_decay, world_size
+        self.grad_norm = grad_norm if (grad_norm is not None and grad_norm > 0) else 0.0
         m = self.m
-        m._refresh_cache()
         dev = m._flat.device
+        if world_size > 1:
+            import torch.distributed as dist
+            with torch.no_grad():
+                dist.broadcast(m._flat, src=0)
+            m._cache_key = None
+            if m._drop_base is None:
+                m._drop_base = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (dist.get_rank() + 1)) & 0xFFFFFFFFFFFFFFFF
+        m._refresh_cache()
         n = m.layout.total
         m._direct_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flags = self.block_flags(m).to(dev)
+        self.normsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.t = 0
-        _L.lib().etp_adamw_step.argtypes = [p_void, p_void, p_void, p_void, p_void, C.c_int64, C.c_float, C.c_float,
-                                            C.c_float, C.c_float, C.c_float, i32, C.c_float, p_void]
+        L = _L.lib()
+        L.etp_adamw_step_ex.argtypes = [p_void, p_void, p_void, p_void, p_void, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_float, i32, C.c_float, p_void, p_void, C.c_float, p_void]
+        L.etp_grad_sumsq.argtypes = [p_void, C.c_int64, p_void, p_void, p_void]
+
+    @classmethod
+    def block_flags(cls, m):
+        """One byte per 64 elements of the flat layout: bit 0 trainable, bit 1 weight decay (host tensor)."""
+        assert m.layout.total % 64 == 0
+        fl = torch.zeros(m.layout.total // 64, dtype=torch.uint8)
+        for name, (off, numel, _) in m.layout.entries.items():
+            assert off % 64 == 0
+            if not m._pmap[name].requires_grad:
+                continue
+            v = 1 | (0 if any(nd in name for nd in cls.NO_DECAY) else 2)
+            fl[off // 64:(off + numel + 63) // 64] = v
+        return fl
 
     def step(self, batch, task):
         m = self.m
@@ -548,8 +594,17 @@ class PretrainTrainer:
             dist.all_reduce(m._direct_grad, op=dist.ReduceOp.SUM)
             scale = 1.0 / self.world
         self.t += 1
-        _L._check(_L.lib().etp_adamw_step(_L.ptr(m._flat), _L.ptr(m._flat_bf16), _L.ptr(m._direct_grad), _L.ptr(self.exp_avg),
-                                          _L.ptr(self.exp_avg_sq), m.layout.total, self.lr, self.betas[0], self.betas[1],
-                                          self.eps, self.wd, self.t, scale, _L.stream_ptr()), "etp_adamw_step")
+        L = _L.lib()
+        n = m.layout.total
+        normsq = None
+        if self.grad_norm > 0:
+            self.normsq.zero_()
+            _L._check(L.etp_grad_sumsq(_L.ptr(m._direct_grad), n, _L.ptr(self.flags), _L.ptr(self.normsq), _L.stream_ptr()),
+                      "etp_grad_sumsq")
+            normsq = self.normsq
+        _L._check(L.etp_adamw_step_ex(_L.ptr(m._flat), _L.ptr(m._flat_bf16), _L.ptr(m._direct_grad), _L.ptr(self.exp_avg),
+                                      _L.ptr(self.exp_avg_sq), n, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                                      self.t, scale, _L.ptr(self.flags), _L.ptr(normsq), self.grad_norm, _L.stream_ptr()),
+                  "etp_adamw_step_ex")
         m._bf16_fresh = True
         return loss

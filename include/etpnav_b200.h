@@ -247,6 +247,10 @@ typedef struct {
    * event X when the whole navigation group is, so the caller can start the all-reduce of those gradient slices on
    * another stream while the rest of the backward runs */
   void* const* layer_done_events;
+  /* optional: bf16 image of txt_embeds [B,L,768] (raw uint16 storage).  When non-NULL the navigation forward / backward
+   * read the instruction through it (their first act on txt_embeds is a cast to bf16 for TMA anyway) and txt_embeds may be
+   * NULL: a host that keeps, or stages across PCIe, the instruction embeddings in bf16 saves the cast and half the bytes. */
+  const void* txt_embeds_bf16;
 } etp_nav_inputs;
 
 /* Bytes of the activation record forward_navigation writes (and backward reads) when training != 0;
@@ -362,6 +366,17 @@ int etp_backward_txt(const etp_txt_weights* w, const etp_txt_weights* grads, con
 int etp_adamw_step(float* param, void* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                    void* stream);
+
+/* The same update with the knobs of the reference's pre-training optimizer (pretrain_src/pretrain_src/optim/misc.py:14-20:
+ * no weight decay for biases / LayerNorm; train_r2r.py:279-284: clip_grad_norm_) and of frozen parameters
+ * (vilmodel_cmt.py:675-682; torch's AdamW skips parameters without a gradient).  flags: one byte per 64 elements of the
+ * flat layout (every tensor starts on a 64-element boundary): bit 0 = trainable, bit 1 = weight decay applies; NULL = all.
+ * normsq: DEVICE scalar = sum of g^2 over the trainable blocks (etp_grad_sumsq ADDS to it; zero it first); with
+ * max_norm > 0 the gradient is scaled by min(1, max_norm / (grad_scale * sqrt(normsq) + 1e-6)).  n % 64 == 0 with flags. */
+int etp_adamw_step_ex(float* param, void* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                      const uint8_t* flags, const float* normsq, float max_norm, void* stream);
+int etp_grad_sumsq(const float* grad, int64_t n, const uint8_t* flags, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * pre-training twin: GlocalTextPathCMT of pretrain_src/pretrain_src/model/vilmodel.py:656-754.

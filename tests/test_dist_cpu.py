@@ -92,7 +92,7 @@ def _pretrain_worker(rank, world, port, out):
         def __call__(self, *a):
             seen["grad_scale"] = a[12].value if hasattr(a[12], "value") else a[12]
             return 0
-    stub.etp_adamw_step = Adam()
+    stub.etp_adamw_step_ex = Adam()
     L.lib = lambda: stub
     L.require_device = lambda: None
     L.stream_ptr = lambda: C.c_void_p(0)

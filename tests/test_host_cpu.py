@@ -142,3 +142,59 @@ def test_checkpoint_interop_finetune_and_pretrain_layouts():
     assert not res.missing_keys and not res.unexpected_keys
     for k, v in src.items():
         assert torch.equal(m.state_dict()[k], v), k
+
+
+def test_trainer_steps_only_trainable_runs():
+    """torch.optim.AdamW skips parameters without a gradient: with fix_pano_embedding (vilmodel_cmt.py:680-682) the
+    panorama group is neither updated nor decayed — PlannerTrainer's stepped runs exclude it."""
+    from etpnav_b200.planner import B200Planner, PlannerTrainer
+    cfg = PlannerConfig(vocab_size=512, num_l_layers=1, num_x_layers=2)
+    m = B200Planner(cfg, device="cpu")
+    lo = min(m.layout.group_ranges[g][0] for g in ("pano", "nav"))
+    hi = max(m.layout.group_ranges[g][1] for g in ("pano", "nav"))
+    assert PlannerTrainer._active_ranges(m, lo, hi) == [(lo, hi)]                       # nothing frozen: one run
+    mf = B200Planner(PlannerConfig(vocab_size=512, num_l_layers=1, num_x_layers=2, fix_pano_embedding=True), device="cpu")
+    assert PlannerTrainer._active_ranges(mf, lo, hi) == [mf.layout.group_ranges["nav"]]
+    # one frozen tensor in the middle splits the run around it
+    name = "global_encoder.encoder.x_layers.0.visn_inter.dense.weight"
+    m._pmap[name].requires_grad = False
+    off, numel, _ = m.layout.entries[name]
+    runs = PlannerTrainer._active_ranges(m, lo, hi)
+    assert len(runs) == 2 and runs[0][1] == off and runs[1][0] >= off + numel and runs[0][0] == lo and runs[1][1] == hi
+
+
+def test_pretraining_state_dict_survives_wrapping():
+    """B200PreTraining keeps the reference's key layout (bert.*, mlm_head.*, global_sap_head.* at top level, tied decoder
+    alias) when it is a child module (DDP / DataParallel: train_r2r.py's ModelSaver strips ``module.``) — both ways."""
+    import torch.nn as nn
+    from etpnav_b200.pretrain import B200PreTraining, PretrainTrainer
+
+    def make():
+        return B200PreTraining(PlannerConfig(vocab_size=512, num_l_layers=1, num_x_layers=1, num_pano_layers=1), device="cpu")
+
+    class Wrap(nn.Module):
+        def __init__(self, mod):
+            super().__init__()
+            self.module = mod
+    m = make()
+    sd = m.state_dict()
+    assert "mlm_head.predictions.decoder.weight" in sd and "global_sap_head.net.0.weight" in sd
+    assert "bert.embeddings.word_embeddings.weight" in sd and not any(k.startswith("bert.mlm_head") for k in sd)
+    wsd = Wrap(m).state_dict()
+    assert len(wsd) == len(sd) > 100 and set(wsd) == {"module." + k for k in sd}        # not empty, reference keys
+    stripped = {k[7:]: v.clone() + 1.0 for k, v in wsd.items()}                          # what ModelSaver writes
+    m2 = make()
+    m2.load_state_dict(stripped, strict=True)
+    assert all(torch.equal(m2.state_dict()[k], stripped[k]) for k in stripped)
+    w3 = Wrap(make())
+    w3.load_state_dict(wsd, strict=True)                                                 # parent recursion reaches the hooks
+    assert all(torch.equal(w3.state_dict()[k], wsd[k]) for k in wsd)
+    # optimizer block flags: biases / LayerNorm carry no weight decay (optim/misc.py:14), frozen tensors are inactive
+    m.bert._pmap["embeddings.word_embeddings.weight"].requires_grad = False
+    fl = PretrainTrainer.block_flags(m.bert)
+    ent = m.bert.layout.entries
+    at = lambda n: int(fl[ent[n][0] // 64])
+    assert at("embeddings.word_embeddings.weight") == 0
+    assert at("lang_encoder.layer.0.attention.self.query.weight") == 3
+    assert at("lang_encoder.layer.0.attention.self.query.bias") == 1
+    assert at("lang_encoder.layer.0.attention.output.LayerNorm.weight") == 1

@@ -99,5 +99,5 @@ def test_trainer_wiring(stub):
     for task in ("mlm", "sap"):
         loss = tr.step(b, task)
         assert loss.dim() == 0
-    assert tr.t == 2 and "etp_adamw_step" in stub.calls
+    assert tr.t == 2 and "etp_adamw_step_ex" in stub.calls and "etp_grad_sumsq" in stub.calls
     assert all(p.grad is None for p in model.bert._pmap.values())   # gradients live in the flat buffer only
