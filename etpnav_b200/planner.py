@@ -803,13 +803,14 @@ class PlannerTrainer:
         # stepped here its gradient goes to a scratch row instead of piling up, unapplied, in the flat gradient buffer
         gs, ge = model.layout.group_ranges["txt"]
         model._tok_scratch = None if (self.lo <= gs and ge <= self.hi) else torch.zeros(768, dtype=torch.float32, device=dev)
-        # data parallel: the gradient slice is reduced in buckets, in the order the backward completes them, on a side
-        # stream: x-layer i's bucket starts as soon as the event the nav backward records for it fires
-        self.buckets, self.side, self._events = None, None, []
-        if world_size > 1:
-            from .dist import gradient_buckets
-            self.buckets = [(nm, a - self.lo, b - self.lo) for nm, a, b in
-                            gradient_buckets(model.layout, model.config, self.lo, self.hi)]
+        # The update runs bucket by bucket, in the order the backward completes the buckets, on a SIDE stream: x-layer i's
+        # bucket starts as soon as the event the nav backward records for it fires, so its (data-parallel) all-reduce and
+        # its AdamW run under the rest of the backward; only the last bucket (panorama group) is exposed.
+        from .dist import gradient_buckets
+        self.buckets = [(nm, a - self.lo, b - self.lo) for nm, a, b in
+                        gradient_buckets(model.layout, model.config, self.lo, self.hi)]
+        self.side, self._events = None, []
+        if dev.type == "cuda":
             self.side = torch.cuda.Stream(dev)
             L0 = _L.lib()
             L0.etp_event_create.restype = p_void
@@ -865,36 +866,56 @@ class PlannerTrainer:
         logits.backward(dlogits)
         return logits, loss_sum / logits.shape[0]
 
+    def _bucket_runs(self, a, b):
+        """Trainable runs (absolute flat offsets) inside bucket [a, b) (offsets relative to self.lo)."""
+        out = []
+        for ra, rb in self.active:
+            x, y = max(ra, self.lo + a), min(rb, self.lo + b)
+            if x < y:
+                out.append((x, y))
+        return out
+
+    def _adamw(self, a, b, scale, stream_ptr):
+        m, o = self.m, a - self.lo
+        _L._check(_L.lib().etp_adamw_step(
+            C.c_void_p(m._flat.data_ptr() + 4 * a), C.c_void_p(m._flat_bf16.data_ptr() + 2 * a),
+            C.c_void_p(m._direct_grad.data_ptr() + 4 * a), C.c_void_p(self.exp_avg.data_ptr() + 4 * o),
+            C.c_void_p(self.exp_avg_sq.data_ptr() + 4 * o), b - a, self.lr, self.betas[0], self.betas[1], self.eps,
+            self.wd, self.t, scale, stream_ptr), "etp_adamw_step")
+
     def optimizer_step(self):
+        """Everything here is only ENQUEUED: the backward kernels are still running.  Per bucket, on the side stream: wait
+        for the bucket's completion event, all-reduce it (SUM over ranks; DDP's 1/world is folded into AdamW's grad_scale),
+        AdamW over its trainable runs.  The compute stream joins the side stream at the end."""
         m = self.m
         g = m._direct_grad[self.lo:self.hi]
-        scale = 1.0
-        if self.world > 1:
-            # SUM over ranks (DDP's 1/world is folded into AdamW's grad_scale).  Everything below is only ENQUEUED here:
-            # the backward kernels are still running; each layer bucket waits for its own event, the last bucket for
-            # the end of the backward.
-            from .dist import allreduce_buckets_
-            L0 = _L.lib()
-            main = torch.cuda.current_stream()
-            X = m.config.num_x_layers
-            waits = []
-            for nm, _, _ in self.buckets:
-                if nm.startswith("x_layer_") or nm == "nav_head":
-                    ev = self._events[X if nm == "nav_head" else int(nm.split("_")[-1])]
-                    waits.append(lambda s, ev=ev: _L._check(L0.etp_stream_wait_event(C.c_void_p(s.cuda_stream), C.c_void_p(ev)),
-                                                            "etp_stream_wait_event"))
-                else:
-                    waits.append(lambda s: s.wait_stream(main))
-            scale = allreduce_buckets_(g, self.buckets, self.world, self.side, waits)
-            main.wait_stream(self.side)
         self.t += 1
-        for a, b in self.active:
-            o = a - self.lo
-            _L._check(_L.lib().etp_adamw_step(
-                C.c_void_p(m._flat.data_ptr() + 4 * a), C.c_void_p(m._flat_bf16.data_ptr() + 2 * a),
-                C.c_void_p(g.data_ptr() + 4 * o), C.c_void_p(self.exp_avg.data_ptr() + 4 * o),
-                C.c_void_p(self.exp_avg_sq.data_ptr() + 4 * o), b - a, self.lr, self.betas[0], self.betas[1], self.eps,
-                self.wd, self.t, scale, _L.stream_ptr()), "etp_adamw_step")
+        scale = 1.0 / self.world if self.world > 1 else 1.0
+        if self.side is None:      # no device (host-logic tests with a stubbed library)
+            if self.world > 1:
+                from .dist import allreduce_buckets_
+                allreduce_buckets_(g, self.buckets, self.world)
+            for a, b in self.active:
+                self._adamw(a, b, scale, _L.stream_ptr())
+            m._bf16_fresh = True
+            return
+        L0 = _L.lib()
+        main = torch.cuda.current_stream()
+        side_ptr = C.c_void_p(self.side.cuda_stream)
+        X = m.config.num_x_layers
+        for nm, a, b in self.buckets:
+            if nm.startswith("x_layer_") or nm == "nav_head":
+                ev = self._events[X if nm == "nav_head" else int(nm.split("_")[-1])]
+                _L._check(L0.etp_stream_wait_event(side_ptr, C.c_void_p(ev)), "etp_stream_wait_event")
+            else:
+                self.side.wait_stream(main)       # final only when the whole backward is
+            with torch.cuda.stream(self.side):
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM)
+                for x, y in self._bucket_runs(a, b):
+                    self._adamw(x, y, scale, side_ptr)
+        main.wait_stream(self.side)
         m._bf16_fresh = True  # AdamW rewrote the flat parameters and their bf16 image (a high-precision image is now stale)
 
     def step(self, d):

@@ -125,6 +125,6 @@ def test_high_precision_is_inference_only():
     m.eval()
     with torch.no_grad():
         a = m.forward_panorama(d["rgb_fts"], d["dep_fts"], d["loc_fts"], d["nav_types"], d["view_lens"])[0].clone()
-        m.img_embeddings.pano_encoder.layers[0].linear2.weight.mul_(1.5)
+        m._pmap["img_embeddings.pano_encoder.layers.0.linear2.weight"].mul_(1.5)
         b = m.forward_panorama(d["rgb_fts"], d["dep_fts"], d["loc_fts"], d["nav_types"], d["view_lens"])[0]
     assert (a - b).abs().max().item() > 1e-3
