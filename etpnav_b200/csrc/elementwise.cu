@@ -279,6 +279,92 @@ int colsum_f32(const float* x, int rows, int cols, int ld, float* out, cudaStrea
   return colsum_impl<float>(x, rows, cols, ld, out, stream);
 }
 
+// Several column sums in ONE launch (the bias gradients of one transformer layer: d b_q, d b_v of the cross- and the
+// self-attention): out_j[c] += sum_r x_j[r, c] for up to 8 bf16 matrices.  A CTA = (job, 64-column block, row slab);
+// thread = (8 columns as one 16-byte load, one of 32 row lanes), four rows in flight per thread.
+struct ColsumJobs {
+  int n, total_ctas;
+  const bf16* x[8];
+  float* out[8];
+  int rows[8], cols[8], ld[8], gx[8], rpc[8], cta_start[8];
+};
+__global__ void __launch_bounds__(256) colsum_grouped_kernel(const ColsumJobs jb) {
+  griddep_launch();
+  griddep_wait();
+  __shared__ float red[32][65];
+  int j = 0;
+  while (j + 1 < jb.n && static_cast<int>(blockIdx.x) >= jb.cta_start[j + 1]) ++j;
+  const int local = blockIdx.x - jb.cta_start[j];
+  const int cb = local % jb.gx[j], rb = local / jb.gx[j];
+  const int tc = threadIdx.x & 7, tr = threadIdx.x >> 3;
+  const int c = cb * 64 + tc * 8;
+  const int r0 = rb * jb.rpc[j], r1 = min(jb.rows[j], r0 + jb.rpc[j]);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (c < jb.cols[j]) {
+    const bf16* base = jb.x[j] + c;
+    const size_t ld = jb.ld[j];
+    auto add8 = [&](const uint4& u) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
+      }
+    };
+    int r = r0 + tr;
+    for (; r + 96 < r1; r += 128) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + r * ld));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + (r + 32) * ld));
+      const uint4 d = __ldg(reinterpret_cast<const uint4*>(base + (r + 64) * ld));
+      const uint4 e = __ldg(reinterpret_cast<const uint4*>(base + (r + 96) * ld));
+      add8(a); add8(b); add8(d); add8(e);
+    }
+    for (; r < r1; r += 32) add8(__ldg(reinterpret_cast<const uint4*>(base + r * ld)));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[tr][tc * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) s += red[w][threadIdx.x];
+    const int cc = cb * 64 + threadIdx.x;
+    if (cc < jb.cols[j]) atomicAdd(jb.out[j] + cc, s);
+  }
+}
+
+int colsum_bf16_grouped(const ColsumJob* jobs, int n, cudaStream_t stream) {
+  ETP_REQUIRE(jobs != nullptr && n >= 0 && n <= 8, "colsum_grouped: 0..8 jobs");
+  ColsumJobs jb;
+  jb.n = 0;
+  long long work = 0;
+  for (int i = 0; i < n; ++i) {
+    if (jobs[i].out == nullptr || jobs[i].rows <= 0) continue;
+    ETP_REQUIRE(jobs[i].cols % 8 == 0 && jobs[i].ld % 8 == 0 && (reinterpret_cast<uintptr_t>(jobs[i].x) & 15) == 0,
+                "colsum_grouped: 16-byte aligned rows of a multiple of 8 columns required");
+    const int k = jb.n++;
+    jb.x[k] = jobs[i].x; jb.out[k] = jobs[i].out; jb.rows[k] = jobs[i].rows; jb.cols[k] = jobs[i].cols; jb.ld[k] = jobs[i].ld;
+    jb.gx[k] = (jobs[i].cols + 63) / 64;
+    work += static_cast<long long>(jb.gx[k]) * jobs[i].rows;
+  }
+  if (jb.n == 0) return ETP_OK;
+  // ~6 CTAs per SM over all jobs: rows per CTA from the total (64-column x row) work, at least 128 rows
+  long long rpc = (work + 6LL * num_sms() - 1) / (6LL * num_sms());
+  if (rpc < 128) rpc = 128;
+  int start = 0;
+  for (int k = 0; k < jb.n; ++k) {
+    jb.rpc[k] = static_cast<int>(rpc);
+    jb.cta_start[k] = start;
+    start += jb.gx[k] * ((jb.rows[k] + jb.rpc[k] - 1) / jb.rpc[k]);
+  }
+  jb.total_ctas = start;
+  ETP_CHECK_CUDA(launch_pdl(colsum_grouped_kernel, dim3(start), dim3(256), 0, stream, jb));
+  ETP_LAUNCHED();
+  return ETP_OK;
+}
+
 __global__ void cast_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n4) {
   griddep_launch();  // PDL (common.cuh): let the next kernel get scheduled ...
   griddep_wait();    // ... and wait for the previous one before touching memory

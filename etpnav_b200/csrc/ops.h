@@ -61,6 +61,13 @@ int layernorm_bwd(const float* dy, const float* x, const float* gamma, const flo
 // out[c] += sum_r x[r, c]   (bias gradients)
 int colsum_bf16(const bf16* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
 int colsum_f32(const float* x, int rows, int cols, int ld, float* out, cudaStream_t stream);
+// up to 8 of them in one launch (jobs with out == nullptr are skipped); cols, ld multiples of 8, x 16-byte aligned
+struct ColsumJob {
+  const bf16* x = nullptr;
+  int rows = 0, cols = 0, ld = 0;
+  float* out = nullptr;
+};
+int colsum_bf16_grouped(const ColsumJob* jobs, int n, cudaStream_t stream);
 int cast_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream);
 int dropout_mask(DropHost d, int64_t n, uint8_t* out, cudaStream_t stream);  // keep flags of one site (tests)
 int add_f32(float* dst, const float* src, int64_t n, cudaStream_t stream);  // dst += src

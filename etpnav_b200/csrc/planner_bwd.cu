@@ -118,6 +118,26 @@ struct WgradBatch {
   }
 };
 
+// Bias gradients that need their own pass (d b_q, and d b_v under attention dropout) are collected per layer and run as
+// ONE grouped column-sum launch at the layer's end, where every dY operand is still intact (the layer's weight
+// gradients, flushed right after, read the same buffers).
+struct BiasBatch {
+  ColsumJob j[8];
+  int n = 0;
+  int add(const bf16* dY, int rows, int cols, int ld, const void* db, cudaStream_t s) {
+    if (db == nullptr) return ETP_OK;
+    if (n == 8) ETP_TRY(flush(s));
+    ColsumJob& q = j[n++];
+    q.x = dY; q.rows = rows; q.cols = cols; q.ld = ld; q.out = static_cast<float*>(const_cast<void*>(db));
+    return ETP_OK;
+  }
+  int flush(cudaStream_t s) {
+    int rc = n > 0 ? colsum_bf16_grouped(j, n, s) : ETP_OK;
+    n = 0;
+    return rc;
+  }
+};
+
 static int bias_grad(const bf16* dY, int rows, int cols, int ld, const void* db, cudaStream_t s) {
   if (db == nullptr) return ETP_OK;
   return colsum_bf16(dY, rows, cols, ld, static_cast<float*>(const_cast<void*>(db)), s);
@@ -129,8 +149,8 @@ static inline float* F(const void* p) { return static_cast<float*>(const_cast<vo
 static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weights& g, const LayerRecord& rec,
                               const bf16* a_bf16, const float* dx_out, float* da, int B, int S, const uint8_t* key_valid,
                               const float* pair, const float* pair_w, const float* pair_b, float* dpair_w, float* dpair_b,
-                              BwdScratch& sc, WgradBatch& wb, cudaStream_t s, const DropCtx& dc, uint32_t site_base,
-                              int layer) {
+                              BwdScratch& sc, WgradBatch& wb, BiasBatch& bb, cudaStream_t s, const DropCtx& dc,
+                              uint32_t site_base, int layer) {
   const int rows = B * S;
   // x = LN(t3)
   // (bias gradients ride along: column sums of dt3 inside the LayerNorm backward, of dpre inside the dgrad epilogue)
@@ -171,8 +191,8 @@ static int self_ffn_block_bwd(const etp_layer_weights& w, const etp_layer_weight
   }
   ETP_TRY(attention_bwd_dispatch(at, s));
   // qkv = a.Wqkv^T + b
-  ETP_TRY(bias_grad(sc.dqkv, rows, kH, 3 * kH, g.sqkv_b, s));  // query part only (see above)
-  if (pdrop && g.sqkv_b) ETP_TRY(bias_grad(sc.dqkv + 2 * kH, rows, kH, 3 * kH, F(g.sqkv_b) + 2 * kH, s));
+  ETP_TRY(bb.add(sc.dqkv, rows, kH, 3 * kH, g.sqkv_b, s));  // query part only (see above)
+  if (pdrop && g.sqkv_b) ETP_TRY(bb.add(sc.dqkv + 2 * kH, rows, kH, 3 * kH, F(g.sqkv_b) + 2 * kH, s));
   ETP_TRY(wb.add(sc.dqkv, rows, 3 * kH, 3 * kH, a_bf16, kH, kH, g.sqkv_w, s));
   ETP_TRY(dgrad(sc.dqkv, rows, 3 * kH, 3 * kH, w.sqkv_w, kH, sc.g0, da, nullptr, 0, nullptr, s));  // da = dqkv.Wqkv + dt2
   return ETP_OK;
@@ -216,8 +236,9 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     const LayerRecord& r = rec.layers[i];
     const bf16* x_in = i > 0 ? rec.layers[i - 1].xb : rec.x0b;
     WgradBatch wb;
+    BiasBatch bb;
     ETP_TRY(self_ffn_block_bwd(lw, lg, r, r.ab, P, Q, B, N, in.gmap_masks, w.sprel_w ? in.gmap_pair_dists : nullptr, w.sprel_w,
-                               w.sprel_b, F(g.sprel_w), F(g.sprel_b), sc, wb, s, dc, kSiteNav, i));
+                               w.sprel_b, F(g.sprel_w), F(g.sprel_b), sc, wb, bb, s, dc, kSiteNav, i));
     // a = LN(t1),  t1 = ctx1.Wo^T + bo + x_in
     ETP_TRY(layernorm_bwd(Q, r.t1, lw.xln_g, r.st1, r.st1 + rows, rows, kH, sc.g0, 0, sc.gb, F(lg.xln_g), F(lg.xln_b), s,
                           F(lg.xo_b), dc.hidden(drop_site(kSiteNav, i, kDropXOut))));
@@ -238,10 +259,11 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
       at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
     }
     ETP_TRY(attention_bwd_dispatch(at, s));
-    ETP_TRY(bias_grad(sc.dq, rows, kH, kH, lg.xq_b, s));
-    if (pdrop && lg.xkv_b) ETP_TRY(bias_grad(dkv_i + kH, kv_rows, kH, ldkv, F(lg.xkv_b) + kH, s));
+    ETP_TRY(bb.add(sc.dq, rows, kH, kH, lg.xq_b, s));
+    if (pdrop && lg.xkv_b) ETP_TRY(bb.add(dkv_i + kH, kv_rows, kH, ldkv, F(lg.xkv_b) + kH, s));
     ETP_TRY(wb.add(sc.dq, rows, kH, kH, x_in, kH, kH, lg.xq_w, s));
     ETP_TRY(dgrad(sc.dq, rows, kH, kH, lw.xq_w, kH, sc.g0, P, nullptr, 0, nullptr, s));  // dx_in = dq.Wq + dt1
+    ETP_TRY(bb.flush(s));  // the layer's bias gradients that need a pass of their own, one launch
     ETP_TRY(wb.flush(s));  // the layer's six weight gradients, one launch
     if (in.layer_done_events && in.layer_done_events[i])
       ETP_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(in.layer_done_events[i]), s));
@@ -295,8 +317,9 @@ int backward_lang2visn(const etp_nav_weights& w, const etp_nav_weights& g, const
     const LayerRecord& r = rec.layers[i];
     const bf16* x_in = i > 0 ? rec.layers[i - 1].xb : rec.txtb;
     WgradBatch wb;
+    BiasBatch bb;
     ETP_TRY(self_ffn_block_bwd(lw, lg, r, r.ab, dx, Q, B, L, in.txt_masks, nullptr, nullptr, nullptr, nullptr, nullptr, sc, wb,
-                               s, dc, kSiteL2V, i));
+                               bb, s, dc, kSiteL2V, i));
     ETP_TRY(layernorm_bwd(Q, r.t1, lw.xln_g, r.st1, r.st1 + rows, rows, kH, sc.g0, 0, sc.gb, F(lg.xln_g), F(lg.xln_b), s,
                           F(lg.xo_b), dc.hidden(drop_site(kSiteL2V, i, kDropXOut))));
     ETP_TRY(wb.add(sc.gb, rows, kH, kH, r.ctx1, kH, kH, lg.xo_w, s));
@@ -315,12 +338,13 @@ int backward_lang2visn(const etp_nav_weights& w, const etp_nav_weights& g, const
       at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
     }
     ETP_TRY(attention_bwd_dispatch(at, s));
-    ETP_TRY(bias_grad(sc.dq, rows, kH, kH, lg.xq_b, s));
-    if (pdrop && lg.xkv_b) ETP_TRY(bias_grad(dkv_i + kH, kv_rows, kH, ldkv, F(lg.xkv_b) + kH, s));
+    ETP_TRY(bb.add(sc.dq, rows, kH, kH, lg.xq_b, s));
+    if (pdrop && lg.xkv_b) ETP_TRY(bb.add(dkv_i + kH, kv_rows, kH, ldkv, F(lg.xkv_b) + kH, s));
     ETP_TRY(wb.add(sc.dq, rows, kH, kH, x_in, kH, kH, lg.xq_w, s));
     // dx_in = dq.Wq + dt1; the first layer's input is the caller's txt_embeds
     float* dst = (i == 0 && d_txt_embeds) ? d_txt_embeds : P;
     ETP_TRY(dgrad(sc.dq, rows, kH, kH, lw.xq_w, kH, sc.g0, dst, nullptr, 0, nullptr, s));
+    ETP_TRY(bb.flush(s));
     ETP_TRY(wb.flush(s));
     dx = P;
   }
@@ -389,8 +413,10 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
       at.drop_key = d.key; at.drop_thr = d.thr; at.drop_scale = d.scale;
     }
     ETP_TRY(attention_bwd(at, s));
-    ETP_TRY(bias_grad(sc.dqkv, rows, kH, 3 * kH, lg.in_b, s));  // query part
-    if (pdrop && lg.in_b) ETP_TRY(bias_grad(sc.dqkv + 2 * kH, rows, kH, 3 * kH, F(lg.in_b) + 2 * kH, s));
+    BiasBatch bb;
+    ETP_TRY(bb.add(sc.dqkv, rows, kH, 3 * kH, lg.in_b, s));  // query part
+    if (pdrop && lg.in_b) ETP_TRY(bb.add(sc.dqkv + 2 * kH, rows, kH, 3 * kH, F(lg.in_b) + 2 * kH, s));
+    ETP_TRY(bb.flush(s));
     ETP_TRY(wb.add(sc.dqkv, rows, 3 * kH, 3 * kH, r.y1b, kH, kH, lg.in_w, s));
     ETP_TRY(dgrad(sc.dqkv, rows, 3 * kH, 3 * kH, lw.in_w, kH, nullptr, Bf, nullptr, 0, nullptr, s));  // dy1
     ETP_TRY(wb.flush(s));  // the layer's four weight gradients, one launch (sc.gb is rewritten just below)
@@ -440,8 +466,10 @@ int backward_txt(const etp_txt_weights& w, const etp_txt_weights& g, const int64
     const bf16* a_bf16 = i > 0 ? rec.layers[i - 1].xb : rec.x0b;
     float* da = (dx == P) ? Q : P;
     WgradBatch wb;
+    BiasBatch bb;
     ETP_TRY(self_ffn_block_bwd(w.layers[i], g.layers[i], rec.layers[i], a_bf16, dx, da, B, L, txt_masks, nullptr, nullptr,
-                               nullptr, nullptr, nullptr, sc, wb, s, dc, kSiteTxt, i));
+                               nullptr, nullptr, nullptr, sc, wb, bb, s, dc, kSiteTxt, i));
+    ETP_TRY(bb.flush(s));
     ETP_TRY(wb.flush(s));
     dx = da;
   }
