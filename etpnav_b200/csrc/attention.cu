@@ -31,8 +31,9 @@ __global__ void __launch_bounds__(256) attention_fwd_kernel(const AttnArgs a, in
   const int Sk = a.Sk;
 
   // stage K, V (bf16) and the per-key mask
-  const bf16* kg = a.k + static_cast<size_t>(b) * Sk * a.ldk + h * kD;
-  const bf16* vg = a.v + static_cast<size_t>(b) * Sk * a.ldv + h * kD;
+  const int kvb = a.kv_rows ? __ldg(a.kv_rows + b) : b;  // row of the K / V tensor this batch element reads
+  const bf16* kg = a.k + static_cast<size_t>(kvb) * Sk * a.ldk + h * kD;
+  const bf16* vg = a.v + static_cast<size_t>(kvb) * Sk * a.ldv + h * kD;
   for (int i = threadIdx.x; i < Sk * 8; i += 256) {
     const int r = i >> 3, c = (i & 7) * 8;
     const uint4 kk = *reinterpret_cast<const uint4*>(kg + static_cast<size_t>(r) * a.ldk + c);

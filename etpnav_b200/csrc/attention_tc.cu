@@ -48,6 +48,7 @@ struct AttnDev {
   const float* pair_b_dev;
   float* lse;
   Drop drop;  // attention-probability dropout (thr 0 = off)
+  const int32_t* kv_rows;  // optional batch-row map of the K / V tensor (see AttnArgs)
 };
 
 ETP_DEVICE float ex2_approx(float x) {
@@ -129,9 +130,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto load_kv = [&](int item, int j, int st) {
         int b, h, q0;
         item_bhq(item, b, h, q0);
+        const int kvb = p.kv_rows ? __ldg(p.kv_rows + b) : b;
         mbar_arrive_expect_tx(&kv_full[st], 2 * kTile);
-        tma_load_3d(sK + st * kTile, &tmK, &kv_full[st], h * kD, j * kBK, b);
-        tma_load_3d(sV + st * kTile, &tmV, &kv_full[st], h * kD, j * kBK, b);
+        tma_load_3d(sK + st * kTile, &tmK, &kv_full[st], h * kD, j * kBK, kvb);
+        tma_load_3d(sV + st * kTile, &tmV, &kv_full[st], h * kD, j * kBK, kvb);
       };
       // S of step (ii, s): waits for its tiles, then 4 MMAs into S buffer s & 1
       auto issue_s = [&](int ii, int s, bool first_block) {
@@ -378,9 +380,11 @@ int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream) {
   const uint64_t W = static_cast<uint64_t>(a.heads) * kD;
   int rc = get_tmap_3d(a.q, W, a.Sq, a.B, a.ldq, static_cast<uint64_t>(a.Sq) * a.ldq, kD, kBQ, &tq);
   if (rc) return rc;
-  rc = get_tmap_3d(a.k, W, a.Sk, a.B, a.ldk, static_cast<uint64_t>(a.Sk) * a.ldk, kD, kBK, &tk);
+  const int kvB = a.kv_rows ? a.kv_B : a.B;
+  ETP_REQUIRE(kvB > 0, "attention_tc: kv_B must be given with kv_rows");
+  rc = get_tmap_3d(a.k, W, a.Sk, kvB, a.ldk, static_cast<uint64_t>(a.Sk) * a.ldk, kD, kBK, &tk);
   if (rc) return rc;
-  rc = get_tmap_3d(a.v, W, a.Sk, a.B, a.ldv, static_cast<uint64_t>(a.Sk) * a.ldv, kD, kBK, &tv);
+  rc = get_tmap_3d(a.v, W, a.Sk, kvB, a.ldv, static_cast<uint64_t>(a.Sk) * a.ldv, kD, kBK, &tv);
   if (rc) return rc;
   rc = get_tmap_3d(a.out, W, a.Sq, a.B, a.ldo, static_cast<uint64_t>(a.Sq) * a.ldo, kD, kBQ, &to);
   if (rc) return rc;
@@ -395,6 +399,7 @@ int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream) {
   d.mask_value = a.mask_value; d.pair = a.pair; d.pair_w = a.pair_w; d.pair_b = a.pair_b;
   d.pair_w_dev = a.pair_w_dev; d.pair_b_dev = a.pair_b_dev; d.lse = a.lse;
   d.drop = Drop{a.drop_key, a.drop_thr, a.drop_scale};
+  d.kv_rows = a.kv_rows;
   ETP_REQUIRE(!a.drop_thr || static_cast<int64_t>(a.B) * a.heads * a.Sq * a.Sk < (int64_t(1) << 32), "attention: dropout index range");
   const int items = a.B * a.heads * ((a.Sq + kBQ - 1) / kBQ);
   const int grid = items < num_sms() ? items : num_sms();

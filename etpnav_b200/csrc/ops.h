@@ -145,6 +145,10 @@ struct AttnArgs {
   // dropout of the attention probabilities (train mode; thr 0 = off): element index ((b*heads+h)*Sq+q)*Sk+k
   uint32_t drop_key = 0, drop_thr = 0;
   float drop_scale = 1.0f;
+  // optional: K / V live in a tensor of kv_B batch rows and query batch b reads row kv_rows[b] of it (device int32 [B]);
+  // the episode-level text K|V cache of an inference rollout whose batch shrinks (etp_nav_inputs.txt_kv_rows)
+  const int32_t* kv_rows = nullptr;
+  int kv_B = 0;
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t stream);
 

@@ -192,8 +192,13 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
   DropCtx dc;
   if (in.dropout) { dc.seed = in.dropout->seed; dc.p_hidden = in.dropout->p_hidden; dc.p_attn = in.dropout->p_attn; dc.p_head = in.dropout->p_head; }
 
+  const bf16* kv_cache = static_cast<const bf16*>(in.txt_kv_all);
+  if (kv_cache) {
+    ETP_REQUIRE(!training, "forward_navigation: the text K|V cache is an inference feature (the backward needs txt_embeds)");
+    ETP_REQUIRE(in.txt_kv_rows == nullptr || in.txt_kv_batch > 0, "forward_navigation: txt_kv_batch must be given with txt_kv_rows");
+  }
   const bf16* txtb = static_cast<const bf16*>(in.txt_embeds_bf16);
-  if (txtb == nullptr) {
+  if (txtb == nullptr && kv_cache == nullptr) {
     ETP_REQUIRE(in.txt_embeds != nullptr, "forward_navigation: txt_embeds (fp32) or txt_embeds_bf16 is required");
     ETP_TRY(cast_f32_to_bf16(in.txt_embeds, rec.txtb, static_cast<int64_t>(B) * L * kH, s));
     txtb = rec.txtb;
@@ -206,7 +211,7 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
   ETP_TRY(node_pack_fwd(np, s));
 
   // text K|V of every layer in ONE GEMM: [B*L,768] x [X*1536,768]^T (they depend only on txt_embeds)
-  if (X > 0)
+  if (X > 0 && kv_cache == nullptr)
     ETP_TRY(linear(txtb, B * L, kH, w.xkv_all_w, X * 2 * kH, w.xkv_all_b, 0, nullptr, nullptr, rec.kv_all, nullptr, s));
   const float* x_f32 = np.x_f32;
   const bf16* x_bf16 = rec.x0b;
@@ -220,6 +225,11 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
     at.q = r.q; at.ldq = kH;
     at.k = r.kv; at.ldk = r.ldkv;
     at.v = r.kv + kH; at.ldv = r.ldkv;
+    if (kv_cache) {   // episode-level cache: layer i's slice of the cached [., X*1536] rows, read through the batch-row map
+      at.k = kv_cache + static_cast<size_t>(i) * 2 * kH; at.v = at.k + kH;
+      at.ldk = at.ldv = X * 2 * kH;
+      at.kv_rows = in.txt_kv_rows; at.kv_B = in.txt_kv_rows ? in.txt_kv_batch : B;
+    }
     at.scale = 0.125f; at.key_valid = in.txt_masks; at.mask_value = -10000.0f;
     at.out = r.ctx1; at.ldo = kH; at.lse = r.lse1;
     {
@@ -436,6 +446,20 @@ ETP_API int etp_forward_navigation(const etp_nav_weights* w, const etp_nav_input
   ETP_REQUIRE(w && in && gmap_embeds && global_logits && saved, "etp_forward_navigation: null argument");
   return forward_navigation(*w, *in, gmap_embeds, global_logits, saved, saved_bytes, training != 0, S(stream));
 }
+ETP_API int etp_encode_text_kv(const etp_nav_weights* w, const float* txt_embeds, const void* txt_embeds_bf16, int32_t B,
+                               int32_t L, void* kv_all, void* work, void* stream) {
+  ETP_REQUIRE(w && kv_all && (txt_embeds || txt_embeds_bf16), "etp_encode_text_kv: null argument");
+  ETP_REQUIRE(B > 0 && L > 0 && w->num_x_layers > 0, "etp_encode_text_kv: bad shape");
+  const bf16* tb = static_cast<const bf16*>(txt_embeds_bf16);
+  if (tb == nullptr) {
+    ETP_REQUIRE(work != nullptr, "etp_encode_text_kv: scratch needed for the fp32 input");
+    ETP_TRY(cast_f32_to_bf16(txt_embeds, static_cast<bf16*>(work), static_cast<int64_t>(B) * L * kH, S(stream)));
+    tb = static_cast<const bf16*>(work);
+  }
+  return linear(tb, B * L, kH, w->xkv_all_w, w->num_x_layers * 2 * kH, w->xkv_all_b, 0, nullptr, nullptr,
+                static_cast<bf16*>(kv_all), nullptr, S(stream));
+}
+
 ETP_API int etp_forward_panorama(const etp_pano_weights* w, const etp_pano_inputs* in, float* pano_embeds,
                                  uint8_t* pano_masks, void* saved, size_t saved_bytes, int32_t training, void* stream) {
   ETP_REQUIRE(w && in && pano_embeds && pano_masks && saved, "etp_forward_panorama: null argument");

@@ -49,7 +49,8 @@ class NavInputs(C.Structure):
     _fields_ = [("B", i32), ("N", i32), ("L", i32)] + [
         (n, p_void) for n in ("txt_embeds", "txt_masks", "gmap_step_ids", "gmap_img_fts", "gmap_pos_fts",
                               "gmap_masks", "gmap_visited_masks", "gmap_pair_dists")] + [
-        ("dropout", C.POINTER(Dropout)), ("layer_done_events", C.POINTER(p_void)), ("txt_embeds_bf16", p_void)]
+        ("dropout", C.POINTER(Dropout)), ("layer_done_events", C.POINTER(p_void)), ("txt_embeds_bf16", p_void),
+        ("txt_kv_all", p_void), ("txt_kv_rows", p_void), ("txt_kv_batch", i32)]
 
 
 class PanoLayerWeights(C.Structure):
@@ -106,6 +107,7 @@ def _declare():
     L.etp_backward_txt.argtypes = [C.POINTER(TxtWeights), C.POINTER(TxtWeights), p_void, p_void, i32, i32, p_void, p_void,
                                    C.c_size_t, p_void, C.c_size_t, p_void, C.POINTER(Dropout)]
     # high-precision (split-bf16 x3) inference mode
+    L.etp_encode_text_kv.argtypes = [C.POINTER(NavWeights), p_void, p_void, i32, i32, p_void, p_void, p_void]
     L.etp_split3.argtypes = [p_void, p_void, C.c_int64, i32, i32, p_void]
     L.etp_hp_nav_work_bytes.restype = C.c_size_t
     L.etp_hp_nav_work_bytes.argtypes = [i32] * 4
@@ -118,6 +120,34 @@ def _declare():
                                           p_void]
     L.etp_forward_txt_hp.argtypes = [C.POINTER(TxtWeights), p_void, p_void, i32, i32, p_void, p_void, C.c_size_t, p_void]
     _declared = True
+
+
+class TextKV:
+    """Episode-level handle of the instruction's key|value projections for ALL cross-modal layers
+    (``B200Planner.encode_text_kv``): bf16 ``[B0 * L, X * 1536]``, computed ONCE per episode instead of at every step
+    of every layer (the reference recomputes them although ``txt_embeds`` is constant over the episode,
+    vilmodel_cmt.py:326-328).  Pass it to ``forward_navigation`` in place of ``txt_embeds`` (inference / eval rollouts).
+    Indexing it like the trainer indexes ``all_txt_embeds[not_done_index]`` (ss_trainer_ETP.py:819-821) keeps the cache
+    and records the surviving episodes as a row map — no data moves."""
+
+    def __init__(self, kv_all, batch, length, rows=None):
+        self.kv_all, self.batch, self.length, self.rows = kv_all, batch, length, rows
+
+    def __len__(self):
+        return self.batch if self.rows is None else int(self.rows.numel())
+
+    @property
+    def shape(self):
+        return (len(self), self.length, 768)
+
+    def __getitem__(self, idx):
+        dev = self.kv_all.device
+        base = torch.arange(self.batch, device=dev, dtype=torch.int32) if self.rows is None else self.rows
+        if not torch.is_tensor(idx):
+            idx = torch.as_tensor(idx, device=dev)
+        idx = idx.to(dev)
+        rows = base[idx] if idx.dtype == torch.bool else base[idx.long()]
+        return TextKV(self.kv_all, self.batch, self.length, rows.to(torch.int32).contiguous())
 
 
 class _Holder(nn.Module):
@@ -512,6 +542,13 @@ class B200Planner(nn.Module):
         self._refresh_cache()
         aux = (self._mask_u8(txt_masks), gmap_step_ids.contiguous().long(), _f32c(gmap_pos_fts),
                self._mask_u8(gmap_masks), self._mask_u8(gmap_visited_masks), _f32c(gmap_pair_dists))
+        if isinstance(txt_embeds, TextKV):
+            if self.precision != "bf16" or self._wants_grad("nav", gmap_img_fts):
+                raise _L.EtpError("a TextKV handle serves bf16-mode inference (torch.no_grad()): the backward needs txt_embeds")
+            if len(txt_embeds) != gmap_img_fts.shape[0] or txt_embeds.length != txt_masks.shape[1]:
+                raise ValueError("TextKV handle and the step's batch disagree: index the handle like all_txt_embeds")
+            embeds, logits, _, _ = _nav_forward(self, txt_embeds, _f32c(gmap_img_fts), aux, 0, None)
+            return {"gmap_embeds": embeds, "global_logits": logits}
         if self.precision == "high":
             self._hp_guard(self._wants_grad("nav", txt_embeds, gmap_img_fts))
             embeds, logits = _nav_forward_hp(self, _f32c(txt_embeds), _f32c(gmap_img_fts), aux)
@@ -523,6 +560,23 @@ class B200Planner(nn.Module):
         else:
             embeds, logits, _, _ = _nav_forward(self, _txtc(txt_embeds), _f32c(gmap_img_fts), aux, 0, drop)
         return {"gmap_embeds": embeds, "global_logits": logits}
+
+    def encode_text_kv(self, txt_embeds):
+        """Once per episode (after ``forward_txt``): the key|value projections of the instruction for every x-layer, as a
+        ``TextKV`` handle that ``forward_navigation`` accepts in place of ``txt_embeds`` (eval / inference rollouts).
+        Bit-identical to what the un-cached step computes; saves the [B*L,768] x [X*1536,768] GEMM at every step."""
+        self._refresh_cache()
+        t = _txtc(txt_embeds)
+        B, Lt = t.shape[:2]
+        X = self.config.num_x_layers
+        if X == 0:
+            raise ValueError("no cross-modal layers: nothing to cache")
+        kv = torch.empty(B * Lt, X * 1536, dtype=torch.bfloat16, device=t.device)
+        work = torch.empty(B * Lt * 768, dtype=torch.bfloat16, device=t.device) if t.dtype != torch.bfloat16 else None
+        _L._check(_L.lib().etp_encode_text_kv(C.byref(self._structs["nav"]), _L.ptr(t) if work is not None else None,
+                                              _L.ptr(t) if work is None else None, B, Lt, _L.ptr(kv), _L.ptr(work),
+                                              _L.stream_ptr()), "etp_encode_text_kv")
+        return TextKV(kv, B, Lt)
 
     # ------------------------------------------------------------------ training helper
     def make_trainer(self, lr=1e-5, world_size=1, **kw):
@@ -576,7 +630,11 @@ def _nav_inputs(txt, img, aux, drop=None):
     if drop is not None:
         ni.dropout = C.pointer(drop)
     ni.B, ni.N, ni.L = img.shape[0], img.shape[1], txt.shape[1]
-    if txt.dtype == torch.bfloat16:     # bf16 instruction embeddings are consumed as they are (etp_nav_inputs.txt_embeds_bf16)
+    if isinstance(txt, TextKV):         # episode-level K|V cache (+ the surviving episodes' row map)
+        ni.txt_kv_all, ni.txt_kv_batch = _L.ptr(txt.kv_all), txt.batch
+        ni.txt_kv_rows = _L.ptr(txt.rows)
+        ni._keep = txt
+    elif txt.dtype == torch.bfloat16:   # bf16 instruction embeddings are consumed as they are (etp_nav_inputs.txt_embeds_bf16)
         ni.txt_embeds_bf16 = _L.ptr(txt)
     else:
         ni.txt_embeds = _L.ptr(txt)

@@ -251,6 +251,15 @@ typedef struct {
    * read the instruction through it (their first act on txt_embeds is a cast to bf16 for TMA anyway) and txt_embeds may be
    * NULL: a host that keeps, or stages across PCIe, the instruction embeddings in bf16 saves the cast and half the bytes. */
   const void* txt_embeds_bf16;
+  /* optional, inference only: the instruction's key|value projections of ALL x-layers, computed once per episode by
+   * etp_encode_text_kv (bf16 [txt_kv_batch * L, num_x_layers * 1536]).  The reference recomputes them at every step of
+   * every layer although txt_embeds is constant over the episode (vilmodel_cmt.py:326-328; 24 % of the forward FLOPs at
+   * B64/N80/L200).  txt_kv_rows (device int32 [B], or NULL = identity) maps the step's batch rows to rows of the
+   * episode batch the cache was built for: the trainer shrinks the batch as episodes finish
+   * (all_txt_embeds[not_done_index], ss_trainer_ETP.py:819-821).  With txt_kv_all set, txt_embeds may be NULL. */
+  const void* txt_kv_all;
+  const int32_t* txt_kv_rows;
+  int32_t txt_kv_batch;
 } etp_nav_inputs;
 
 /* Bytes of the activation record forward_navigation writes (and backward reads) when training != 0;
@@ -260,6 +269,11 @@ size_t etp_nav_saved_bytes(int32_t B, int32_t N, int32_t L, int32_t num_x_layers
  * outputs: gmap_embeds fp32 [B,N,768], global_logits fp32 [B,N] (-inf at visited / padded nodes). */
 int etp_forward_navigation(const etp_nav_weights* w, const etp_nav_inputs* in, float* gmap_embeds,
                            float* global_logits, void* saved, size_t saved_bytes, int32_t training, void* stream);
+/* Episode-level text K|V cache for inference rollouts: kv_all[b*L + l, i*1536 : (i+1)*1536] = key|value projection of
+ * x-layer i of token (b, l) (visual_attention.att.{key,value}, vilmodel_cmt.py:327-328), bf16.  txt_embeds fp32 [B,L,768]
+ * (or txt_embeds_bf16, the other NULL); work: B*L*768 bf16 of scratch (unused with the bf16 input). */
+int etp_encode_text_kv(const etp_nav_weights* w, const float* txt_embeds, const void* txt_embeds_bf16, int32_t B, int32_t L,
+                       void* kv_all, void* work, void* stream);
 
 /* ImageEmbeddings + pano encoder (vilmodel_cmt.py:454-486; common/transformer.py:127-182) */
 typedef struct {
