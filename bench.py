@@ -597,6 +597,18 @@ def main():
     ms_per_step = total_ms / a.steps
     value = world / (ms_per_step * 1e-3)
 
+    # host side of one step: time to ENQUEUE it with an empty launch queue (no synchronisation inside): if this is close
+    # to ms_per_step the step is launch-bound on the host, not GPU-bound
+    host_ms = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step(resident)
+        host_ms.append((time.perf_counter() - t0) * 1e3)
+    torch.cuda.synchronize()
+    host_ms.sort()
+    host_enqueue_ms = host_ms[len(host_ms) // 2]
+
     # end-to-end: host blob -> ONE H2D copy -> step -> D2H logits, through the public API.  Every step's inputs cross PCIe
     # inside the timed region; the copy of step t+1 is issued on a side stream while step t computes
     # (etpnav_b200.pipeline.HostBatchStager: two device slots), the compute stream waits on its event.
@@ -743,7 +755,8 @@ def main():
                         "ms_per_step": e2e_ms, "copies_per_step": {"h2d": 1, "d2h": 1},
                         "staging": "one pinned blob per step (all 14 input tensors, 256-byte aligned), txt_embeds as bf16",
                         "numa": numa},
-                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clk.summary(),
+                "roofline": roof, "cpu_baseline": cpu}
         if soak:
             line["sustained"] = soak
         if dp:

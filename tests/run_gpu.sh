@@ -17,6 +17,12 @@ run_one() {
       timeout 2400 python -m pytest -m gpu -q "$@" > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.txt ;;
     bench)
       timeout 1500 python bench.py "$@" > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err ;;
+    benchto)   # benchto <name> [bench args]: quick line (no CPU / eager / soak legs) -> gpurun_out/bench_<name>.json
+      name=$1; shift
+      timeout 900 python bench.py --no-cpu-baseline --no-gpu-eager --no-soak "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; echo "bench $name rc=$?"; cat gpurun_out/bench_$name.json; tail -2 gpurun_out/bench_$name.err ;;
+    benchn)    # benchn <N> <name> [bench args]: torchrun over N GPUs of this box
+      n=$1; name=$2; shift; shift
+      timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $n --no-cpu-baseline --no-gpu-eager "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; echo "bench $name rc=$?"; cat gpurun_out/bench_$name.json; tail -2 gpurun_out/bench_$name.err ;;
     report)
       timeout 900 python bench.py --no-cpu-baseline --no-gpu-eager --kernel-report gpurun_out/kernel_report.txt "$@" > gpurun_out/bench_report.json 2> gpurun_out/bench_report.err
       echo "report rc=$?"; cat gpurun_out/bench_report.json; head -40 gpurun_out/kernel_report.txt ;;
