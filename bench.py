@@ -75,6 +75,11 @@ def parse():
     ap.add_argument("--text-kv", action="store_true",
                     help="fwd mode: the instruction's key|value projections are computed once per episode "
                          "(B200Planner.encode_text_kv, outside the timed step) and reused by every step, as in an eval rollout")
+    ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"],
+                    help="N > 1: dtype of the gradient buckets on the wire (fp32 = DDP default; bf16 = compressed all-reduce)")
+    ap.add_argument("--comm-sms", type=int, default=0,
+                    help="N > 1: SMs the persistent grids leave to the collective (etp_set_sm_reserve)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: NCCL_MAX_CTAS for this run (0 = NCCL's default)")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel CUDA-event table of the profiled pass here")
     ap.add_argument("--text-law", default=None, choices=["r2r"],
                     help="ragged instruction lengths: 'r2r' = normal(32, 12) clipped to [8, 80] BERT tokens (BASELINE.json "
@@ -110,6 +115,7 @@ def config_dict(a, mode, world):
     """The ``config`` object of the JSON line — built by ONE function for both arms so they compare equal."""
     return {"workload": workload_name(a, mode), "name": a.config, "mode": mode, "global_batch": a.batch * max(1, world),
             "parallelism": f"dp{max(1, world)}", "x_layers": a.x_layers, "dropout": a.dropout if mode == "train" else "n/a",
+            "grad_comm": (a.grad_comm if (world > 1 and mode == "train") else "n/a"),
             "l2": "no flush: the per-step working set (activation record + weights, > 1 GB in train mode) exceeds the 126 MB L2"}
 
 
@@ -513,6 +519,8 @@ def main():
     numa = bind_to_gpu_numa(local)      # before any pinned allocation: the staging blob lives next to this GPU's PCIe root
     if world > 1:
         import torch.distributed as dist
+        if a.nccl_max_ctas > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(a.nccl_max_ctas)
         # NCCL prints its version banner on stdout at first use: keep stdout for the one JSON line
         sys.stdout.flush()
         saved_fd = os.dup(1)
@@ -548,7 +556,7 @@ def main():
 
     if mode == "train":
         model.train()
-        trainer = model.make_trainer(lr=1e-5, world_size=world)
+        trainer = model.make_trainer(lr=1e-5, world_size=world, grad_comm=a.grad_comm, comm_sms=a.comm_sms)
 
         def step(d):
             return trainer.step(d)
@@ -712,7 +720,7 @@ def main():
             m2.load_state_dict(sd0, strict=True)
             m2.train()
             m2.set_dropout_seed(777)
-            t2 = m2.make_trainer(lr=1e-5, world_size=w_)
+            t2 = m2.make_trainer(lr=1e-5, world_size=w_, grad_comm=a.grad_comm, comm_sms=a.comm_sms)
             m2.set_dropout_seed(777)
             t2.step(same)
             torch.cuda.synchronize()

@@ -38,6 +38,7 @@ ETP_API int etp_stream_wait_event(void* stream, void* event) {
   ETP_CHECK_CUDA(cudaStreamWaitEvent(S(stream), static_cast<cudaEvent_t>(event), 0));
   return ETP_OK;
 }
+ETP_API void etp_set_sm_reserve(int32_t n) { set_sm_reserve(n); }
 ETP_API void etp_prof_gemm_enable(int on) { prof_enable(on != 0); }
 ETP_API int etp_prof_gemm_collect(double* total_ms, double* total_flops, long long* launches) {
   ETP_REQUIRE(total_ms && total_flops && launches, "etp_prof_gemm_collect: null argument");

@@ -191,6 +191,11 @@ int prof_collect(double* ms, double* flops, long long* count, char* report, size
   return ETP_OK;
 }
 
+// SMs the persistent grids (GEMM pairs, attention, row kernels) size themselves for.  A data-parallel host can hold a few
+// SMs back for the collective's CTAs (etp_set_sm_reserve): a persistent all-SM cluster grid otherwise waits, tile after
+// tile, for the SM pairs an NCCL kernel occupies, and the all-reduce waits for SMs the GEMMs never release.
+static std::atomic<int> g_sm_reserve{0};
+void set_sm_reserve(int n) { g_sm_reserve.store(n < 0 ? 0 : n); }
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -199,7 +204,9 @@ int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  int avail = n - g_sm_reserve.load(std::memory_order_relaxed);
+  avail &= ~1;              // whole SM pairs (cta_group::2 clusters)
+  return avail < 2 ? 2 : avail;
 }
 
 }  // namespace etp

@@ -832,8 +832,16 @@ class PlannerTrainer:
     all-reduce of that buffer's step slice (the reference's DDP mean, ss_trainer_ETP.py:211-212) and a fused
     AdamW (torch.optim.AdamW defaults, :213) that also refreshes the bf16 weight image."""
 
-    def __init__(self, model, lr=1e-5, world_size=1, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, groups=("pano", "nav")):
+    def __init__(self, model, lr=1e-5, world_size=1, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, groups=("pano", "nav"),
+                 grad_comm="fp32", comm_sms=0):
+        """``grad_comm``: dtype the gradient buckets cross NVLink in — "fp32" (DDP's default, the reference) or "bf16"
+        (each bucket is rounded to bf16 for the all-reduce and widened again: half the bytes, like DDP's bf16 compression
+        hook; gradients are still ACCUMULATED and applied in fp32).  ``comm_sms``: SMs the library's persistent grids leave
+        to the collective's CTAs while training data-parallel (etp_set_sm_reserve; pair it with NCCL_MAX_CTAS)."""
         self.m, self.lr, self.world, self.betas, self.eps, self.wd = model, lr, world_size, betas, eps, weight_decay
+        if grad_comm not in ("fp32", "bf16"):
+            raise ValueError("grad_comm must be 'fp32' or 'bf16'")
+        self.grad_comm, self.comm_sms, self._comm_buf = grad_comm, int(comm_sms), None
         dev = model._flat.device
         if world_size > 1:
             # DDP broadcasts rank 0's parameters when it wraps the module (ss_trainer_ETP.py:211-212): replicas built from
@@ -877,6 +885,11 @@ class PlannerTrainer:
             X = model.config.num_x_layers
             self._events = [L0.etp_event_create() for _ in range(X + 1)]   # one per x-layer + "nav group complete"
             model._layer_events = (p_void * (X + 1))(*self._events)
+            if world_size > 1:
+                L0.etp_set_sm_reserve.argtypes = [i32]
+                L0.etp_set_sm_reserve(self.comm_sms)
+                if grad_comm == "bf16":
+                    self._comm_buf = torch.empty(n, dtype=torch.bfloat16, device=dev)
         L = _L.lib()
         L.etp_adamw_step.argtypes = [p_void, p_void, p_void, p_void, p_void, C.c_int64, f32, f32, f32, f32, f32, i32, f32,
                                      p_void]
@@ -970,7 +983,13 @@ class PlannerTrainer:
             with torch.cuda.stream(self.side):
                 if self.world > 1:
                     import torch.distributed as dist
-                    dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM)
+                    if self._comm_buf is not None:
+                        c = self._comm_buf[a:b]
+                        c.copy_(g[a:b])                                   # fp32 -> bf16 (round to nearest even)
+                        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+                        g[a:b].copy_(c)                                   # back into the fp32 buffer AdamW reads
+                    else:
+                        dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM)
                 for x, y in self._bucket_runs(a, b):
                     self._adamw(x, y, scale, side_ptr)
         main.wait_stream(self.side)

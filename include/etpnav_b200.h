@@ -49,6 +49,10 @@ int etp_check_device(void);
 void* etp_event_create(void);                       /* cudaEventCreateWithFlags(disable timing); NULL on error */
 void etp_event_destroy(void* event);
 int etp_stream_wait_event(void* stream, void* event);   /* cudaStreamWaitEvent */
+/* Leave `n` SMs to other kernels: the library's persistent grids (one CTA or CTA pair per SM) size themselves for the
+ * remaining ones.  A data-parallel host sets this to the CTA count of its gradient all-reduce (NCCL_MAX_CTAS) so the
+ * collective and the backward GEMMs do not queue for the same SMs; 0 (default) = use every SM. */
+void etp_set_sm_reserve(int32_t n);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long etp_launch_count(void);
 /* CUDA-event timing of every tcgen05 GEMM launch (for the roofline line of bench.py): enable, run steps,
