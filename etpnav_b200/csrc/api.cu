@@ -9,6 +9,8 @@ const char* last_error_cstr();
 void prof_enable(bool on);
 int prof_collect(double* ms, double* flops, long long* count, char* report, size_t cap);
 int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream);
+int attention_tc_fwd_v1(const AttnArgs& a, cudaStream_t stream);
+int attention_tc2_fwd(const AttnArgs& a, cudaStream_t stream);
 int attention_dispatch(const AttnArgs& a, cudaStream_t stream);
 int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream);
 void attention_bwd_tc_set_debug(void* dev_buf);
@@ -97,7 +99,9 @@ ETP_API int etp_attention_fwd(const etp_attn_args* g, void* stream) {
   a.pair_w_dev = g->pair_w_dev; a.pair_b_dev = g->pair_b_dev;
   a.out = static_cast<bf16*>(g->out); a.ldo = g->ldo; a.lse = g->lse;
   if (g->impl == 1) return attention_fwd(a, S(stream));
-  if (g->impl == 2) return attention_tc_fwd(a, S(stream));
+  if (g->impl == 2) return attention_tc_fwd(a, S(stream));      /* tcgen05, generation chosen by ETP_ATTN_V2 */
+  if (g->impl == 3) return attention_tc2_fwd(a, S(stream));     /* tcgen05, two CTAs per SM */
+  if (g->impl == 4) return attention_tc_fwd_v1(a, S(stream));   /* tcgen05, one CTA per SM */
   return attention_dispatch(a, S(stream));
 }
 

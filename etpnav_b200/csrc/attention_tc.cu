@@ -373,7 +373,15 @@ bool attention_tc_supported(const AttnArgs& a) {
   return al16(a.q) && al16(a.k) && al16(a.v) && al16(a.out) && (a.pair == nullptr || al16(a.pair));
 }
 
+int attention_tc2_fwd(const AttnArgs& a, cudaStream_t stream);  // attention_tc2.cu: two CTAs per SM
+bool attention_use_v2();
+
+int attention_tc_fwd_v1(const AttnArgs& a, cudaStream_t stream);
 int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream) {
+  return attention_use_v2() ? attention_tc2_fwd(a, stream) : attention_tc_fwd_v1(a, stream);
+}
+
+int attention_tc_fwd_v1(const AttnArgs& a, cudaStream_t stream) {
   ETP_REQUIRE(a.B > 0 && a.Sq > 0 && a.Sk > 0 && a.heads > 0, "attention_tc: empty problem");
   ETP_REQUIRE(attention_tc_supported(a), "attention_tc: unsupported layout");
   CUtensorMap tq, tk, tv, to;

@@ -98,7 +98,7 @@ int etp_gemm(const etp_gemm_args* args, void* stream);
 /* softmax(scale*q.k^T + bias).v, head dim 64; bias = (key_valid ? 0 : mask_value) + pair_w*pair + pair_b.
  * BertOutAttention (vilmodel_cmt.py:325-352), BertSelfAttention (:103-141, graph bias :391-393),
  * nn.MultiheadAttention in the pano encoder (common/transformer.py:176).  impl: 0 auto, 1 CUDA-core,
- * 2 tcgen05. */
+ * 2 tcgen05 (3 / 4 force its two-CTAs-per-SM / one-CTA-per-SM generation; 2 follows ETP_ATTN_V2, default the former). */
 typedef struct {
   int32_t B, heads, Sq, Sk;
   const void* q; int32_t ldq;

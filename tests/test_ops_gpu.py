@@ -178,10 +178,11 @@ def _attn_ref(q, k, v, B, h, Sq, Sk, scale, key_valid, mask_value, pair, pw, pb)
     return o, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 3, 4])   # CUDA-core, tcgen05 two-CTAs-per-SM (attention_tc2.cu), tcgen05 one-CTA (attention_tc.cu)
 @pytest.mark.parametrize("B,Sq,Sk,mode", [(3, 12, 12, "pano"), (2, 16, 80, "x"), (4, 40, 40, "self"),
                                            (2, 80, 200, "x"), (2, 80, 80, "self"), (1, 120, 512, "x"),
-                                           (2, 150, 150, "self"), (3, 11, 17, "x"), (2, 200, 200, "txt")])
+                                           (2, 150, 150, "self"), (3, 11, 17, "x"), (2, 200, 200, "txt"),
+                                           (30, 80, 200, "x"), (30, 80, 80, "self")])   # > 2 x 148 items: every CTA walks several
 def test_attention_fwd(L, impl, B, Sq, Sk, mode):
     g = _gen(B * 100 + Sq + Sk)
     h = 12
