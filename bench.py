@@ -72,6 +72,8 @@ def parse():
                          "the north_star's >=10x target is stated against")
     ap.add_argument("--no-soak", action="store_true", help="skip the >= 3 s sustained run (clocks / power under a long region)")
     ap.add_argument("--no-dp-check", action="store_true", help="N > 1: skip the data-parallel gradient self-check step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "high"],
+                    help="fwd mode: 'high' = the fp32-class inference mode (split-bf16 x3 GEMMs + fp32 attention)")
     ap.add_argument("--text-kv", action="store_true",
                     help="fwd mode: the instruction's key|value projections are computed once per episode "
                          "(B200Planner.encode_text_kv, outside the timed step) and reused by every step, as in an eval rollout")
@@ -131,7 +133,8 @@ def torch_dropout_hook(cfg):
 
 def workload_name(a, mode):
     what = ("fwd+bwd+AdamW, train() dropout " + a.dropout) if mode == "train" else (
-        "fwd (episode-level text K|V cache)" if getattr(a, "text_kv", False) else "fwd")
+        "fwd (episode-level text K|V cache)" if getattr(a, "text_kv", False) else
+        ("fwd, precision=high (split-bf16 x3 GEMMs, fp32 attention)" if getattr(a, "precision", "bf16") == "high" else "fwd"))
     law = ", R2R-CE-like text lengths (normal(32,12) in [8,80], padded)" if a.text_law else ""
     fam = ", XLM-R shape (eps 1e-5)" if getattr(a, "xlmr", False) else ""
     return (f"planner step {what}: forward_panorama+forward_navigation, B={a.batch}/GPU, V={a.views}, N={a.nodes}, "
@@ -546,7 +549,7 @@ def main():
     step_keys = keys_pano + keys_nav + ["labels"]
     resident = {k: host[k].to(dev) for k in step_keys}
     # host side of the e2e leg: ONE pinned blob per step (txt_embeds staged as bf16: the kernels' first act on it is that cast)
-    stager = HostBatchStager(dev, slots=2, bf16_keys=("txt_embeds",))
+    stager = HostBatchStager(dev, slots=2, bf16_keys=() if a.precision == "high" else ("txt_embeds",))
     # (with --text-kv the instruction stays on the device for the whole episode, as forward_txt's output does in the
     # reference: it is not a per-step input any more)
     blob, blob_meta = stager.pack({k: host[k] for k in step_keys if not (a.text_kv and mode == "fwd" and k == "txt_embeds")})
@@ -561,7 +564,7 @@ def main():
         def step(d):
             return trainer.step(d)
     else:
-        model.eval()
+        model.eval().set_precision(a.precision)
         text_kv = None
         if a.text_kv:   # once per episode, like forward_txt: not part of the per-step path
             with torch.no_grad():
@@ -757,11 +760,13 @@ def main():
                              "training path, ss_trainer_ETP.py:502)"}
         line = {"metric": metric_name(a), "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps,
                 "warmup": max(3, a.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "vs_baseline": None, "dtype": ("bf16x3 (split) / f32" if (mode == "fwd" and a.precision == "high") else "bf16"),
+                "data": "synthetic",
                 "config": config_dict(a, mode, world),
                 "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_ms, "copies_per_step": {"h2d": 1, "d2h": 1},
-                        "staging": "one pinned blob per step (all 14 input tensors, 256-byte aligned), txt_embeds as bf16",
+                        "staging": "one pinned blob per step (all input tensors, 256-byte aligned)"
+                                   + ("" if a.precision == "high" else ", txt_embeds as bf16"),
                         "numa": numa},
                 "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clk.summary(),
                 "roofline": roof, "cpu_baseline": cpu}

@@ -246,6 +246,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int b, h, q0;
       item_bhq(item, b, h, q0);
       const int q = q0 + r;
+      // a warp whose 32 rows all lie past the last query (rows 96..127 of an 80-node map) has nothing to compute: its P
+      // rows only feed output rows the TMA store clips.  It keeps every barrier / phase, skips TMEM reads and the math.
+      const bool warp_live = q0 + quad * 32 < p.Sq;  // warp-uniform: tcgen05.ld / st are warp collectives
       const float* pair_row = (kPair && q < p.Sq) ? p.pair + (static_cast<size_t>(b) * p.Sq + q) * p.Sk : nullptr;
       float m = -INFINITY, l = 0.f;  // running row maximum (shared by the row's two threads), this thread's half-row sum
 
@@ -271,14 +274,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int key_h = k0 + wq * 64;
         // ---- pass A: row maximum over this thread's 64 keys
         float mloc = -INFINITY;
+        if (warp_live) {
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          uint32_t vs[32];
-          tmem_ld32(tSr + sub * 32, vs);
-          tmem_ld_wait();
-          bias32(vs, kbh + sub * 32, pair_row, key_h + sub * 32);
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t vs[32];
+            tmem_ld32(tSr + sub * 32, vs);
+            tmem_ld_wait();
+            bias32(vs, kbh + sub * 32, pair_row, key_h + sub * 32);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mloc = fmaxf(mloc, __uint_as_float(vs[i]));
+            for (int i = 0; i < 32; ++i) mloc = fmaxf(mloc, __uint_as_float(vs[i]));
+          }
         }
         sMax[wq * kBQ + r] = mloc;
         named_bar_sync(2, kMathThreads);
@@ -291,7 +296,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           // P.V of the previous block must have landed
           mbar_wait(o_ready, ph ^ 1);
           tc_fence_after();
-          if (__any_sync(0xffffffffu, alpha != 1.0f)) {   // warp-uniform: tcgen05.ld / st are warp collectives
+          if (warp_live && __any_sync(0xffffffffu, alpha != 1.0f)) {   // warp-uniform: tcgen05.ld / st are warp collectives
             uint32_t v[32];
             tmem_ld32(tO + lane_sel + wq * 32, v);
             tmem_ld_wait();
@@ -307,6 +312,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint8_t* prow = sP + wq * 16384 + r * 128;
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
+          if (!warp_live) break;
           uint32_t vs[32];
           tmem_ld32(tSr + sub * 32, vs);
           tmem_ld_wait();
@@ -347,12 +353,15 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_wait(o_ready, (s - 1) & 1);
       tc_fence_after();
       float o[32];
-      {
+      if (warp_live) {
         uint32_t v[32];
         tmem_ld32(tO + lane_sel + wq * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
       }
       tc_fence_before();
       // ---- item epilogue: row sum over the two halves, normalise, stage the bf16 tile, one TMA store, lse ----
