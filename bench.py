@@ -632,9 +632,24 @@ def main():
             lg = step(d)
             logits_host.copy_(lg, non_blocking=True)
 
+    def h2d_alone_gbps():
+        """The blob's host -> device copy with nothing else on the GPU (GB/s): tells a slow / contended host link (this
+        number is low too) from a copy starved by the overlapped compute (this number is fine, e2e is not)."""
+        dst = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            dst.copy_(blob[:h2d_bytes], non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return 4 * h2d_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    h2d_before = h2d_alone_gbps()
     e2e_run(3)
     e2e_ms = timed(lambda: e2e_run(a.steps), 1) / a.steps
     e2e_val = world / (e2e_ms * 1e-3)
+    h2d_after = h2d_alone_gbps()
     clk.__exit__()
 
     # sustained: the same step for >= 3 s (power / clocks settle on a long region; the 20-step figure is a 0.1 s burst)
@@ -767,7 +782,7 @@ def main():
                         "ms_per_step": e2e_ms, "copies_per_step": {"h2d": 1, "d2h": 1},
                         "staging": "one pinned blob per step (all input tensors, 256-byte aligned)"
                                    + ("" if a.precision == "high" else ", txt_embeds as bf16"),
-                        "numa": numa},
+                        "numa": numa, "h2d_alone_gbps": [round(h2d_before, 2), round(h2d_after, 2)]},
                 "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clk.summary(),
                 "roofline": roof, "cpu_baseline": cpu}
         if soak:

@@ -125,7 +125,12 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
   __syncwarp();
   griddep_launch();  // PDL: the next kernel may start its own prologue
-  griddep_wait();    // previous kernel complete; nothing above touched global memory or TMEM
+  // Programmatic dependent launch lets this CTA pair become resident while the previous kernel drains.  What does not touch
+  // global memory — the pair's barrier hand-shake and the TMEM allocation — can run in that shadow (early_setup): the
+  // allocation can only wait for TMEM columns of a CTA of the PREVIOUS kernel still resident on this SM, which frees
+  // them when it exits and never waits for this grid (every kernel of the library is fully resident when it signals
+  // launch_dependents).  Otherwise everything waits for the previous grid first.
+  if (!p.early_setup) griddep_wait();
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   if (warp == 1) {
     tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols);
@@ -135,6 +140,7 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   cluster_sync_all();  // peer allocated too (execution barrier only) ...
   __syncthreads();     // ... and the TMEM base address written by warp 1 is visible to this CTA's warps
   tc_fence_after();
+  if (p.early_setup) griddep_wait();  // previous kernel complete: its results (our operands) are visible from here on
   const uint32_t tmem_base = *tmem_ptr;
 
   const int num_tiles = kGrouped ? gp->total_tiles : p.tiles_m * p.tiles_n * p.k_splits;
@@ -550,6 +556,8 @@ int launch_grouped_tt(const GemmArgs* a, int n, cudaStream_t stream) {
   GemmDev d;
   memset(&d, 0, sizeof(d));
   d.alpha = 1.0f;
+  static const int early = [] { const char* e = getenv("ETP_GEMM_EARLY"); return e ? atoi(e) : 0; }();
+  d.early_setup = early;
   auto kern = gemm_tcgen05_grouped_kernel<BN, true, true>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -597,6 +605,8 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   ETP_REQUIRE(!a.drop_thr || (a.k_splits == 1 && !a.atomic && static_cast<int64_t>(a.M) * a.N < (int64_t(1) << 32)),
               "gemm: dropout needs whole-K tiles and < 2^32 elements");
   d.k_splits = a.k_splits;
+  static const int early = [] { const char* e = getenv("ETP_GEMM_EARLY"); return e ? atoi(e) : 0; }();
+  d.early_setup = early;
   // tile-N: 256-wide pair tiles unless N is small / not a multiple of 256, or they would leave most pairs idle
   int bn = a.block_n;
   const int tm = (a.M + 2 * BM - 1) / (2 * BM);

@@ -109,7 +109,7 @@ class HostBatchStager:
 
     def __init__(self, device, slots: int = 2, bf16_keys=("txt_embeds",)):
         self.device = torch.device(device)
-        self.stream = torch.cuda.Stream(self.device)
+        self.stream = torch.cuda.Stream(self.device, priority=-1)   # copies are dispatched ahead of queued compute
         self.bf16_keys = tuple(bf16_keys)
         self.nslots = slots
         self.dev_blobs = [None] * slots
