@@ -136,3 +136,64 @@ def test_two_rank_pretrain_trainer_allreduce(tmp_path):
     # the stubbed backward kernels add nothing; the loss.backward() of the stub graph may not touch the buffer either
     assert torch.equal(r0["g"], want)
     assert abs(float(r0["scale"]) - 0.5) < 1e-7 and abs(float(r1["scale"]) - 0.5) < 1e-7
+
+
+# ----------------------------------------------------------------------------------------------------
+# PlannerTrainer's data-parallel host logic with the C library stubbed: rank 0's parameters are broadcast at
+# construction (ranks built from different seeds end up equal, like under DDP), the update runs bucket by bucket
+# (all-reduce, then AdamW over the bucket's trainable runs with grad_scale = 1 / world), frozen groups are skipped.
+# ----------------------------------------------------------------------------------------------------
+def _planner_trainer_worker(rank, world, port, out):
+    import ctypes as C
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from etpnav_b200 import lib as L
+    from etpnav_b200 import planner
+    from tests.test_pretrain_dryrun_cpu import _StubLib, _fake_refresh
+    stub = _StubLib()
+    calls = []
+
+    class Adam:
+        restype = None
+        argtypes = None
+
+        def __call__(self, *a):
+            v = lambda x: x.value if hasattr(x, "value") else x
+            calls.append((v(a[0]), int(v(a[5])), float(v(a[12]))))     # (param pointer, element count, grad_scale)
+            return 0
+    stub.etp_adamw_step = Adam()
+    L.lib = lambda: stub
+    L.require_device = lambda: None
+    L.stream_ptr = lambda: C.c_void_p(0)
+    planner._declared = True
+    planner.B200Planner._refresh_cache = _fake_refresh
+    torch.manual_seed(100 + rank)                                        # different initial weights per rank
+    cfg = PlannerConfig(vocab_size=64, num_l_layers=0, num_x_layers=2, fix_pano_embedding=True)
+    m = planner.B200Planner(cfg, device="cpu")
+    before = m._flat.clone()
+    tr = m.make_trainer(lr=1e-3, world_size=world)
+    m._direct_grad[tr.lo:tr.hi] = torch.arange(tr.hi - tr.lo, dtype=torch.float32) % 13 * (rank + 1)
+    tr.optimizer_step()
+    base = m._flat.data_ptr()
+    torch.save({"before": before, "after_bcast": m._flat.clone(), "g": m._direct_grad[tr.lo:tr.hi].clone(),
+                "calls": [((p - base) // 4, n, s) for p, n, s in calls], "active": tr.active, "lo": tr.lo, "hi": tr.hi,
+                "nav": m.layout.group_ranges["nav"], "drop_base": m._drop_base}, f"{out}/t{rank}.pt")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_planner_trainer_update_pipeline(tmp_path):
+    world = 2
+    mp.spawn(_planner_trainer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "t0.pt"), torch.load(tmp_path / "t1.pt")
+    assert not torch.equal(r0["before"], r1["before"])                   # built from different seeds ...
+    assert torch.equal(r0["after_bcast"], r1["after_bcast"]) and torch.equal(r0["after_bcast"], r0["before"])   # ... rank 0 wins
+    n = r0["hi"] - r0["lo"]
+    assert torch.equal(r0["g"], r1["g"]) and torch.equal(r0["g"], torch.arange(n, dtype=torch.float32) % 13 * 3.0)   # SUM
+    assert r0["drop_base"] != r1["drop_base"]                            # every rank draws its own dropout masks
+    # frozen panorama group: only the nav group is stepped, bucket by bucket, every element exactly once, scale 1 / world
+    assert r0["active"] == [tuple(r0["nav"])]
+    spans = sorted((a, a + cnt) for a, cnt, _ in r0["calls"])
+    assert spans[0][0] == r0["nav"][0] and spans[-1][1] == r0["nav"][1]
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+    assert all(abs(s - 0.5) < 1e-7 for _, _, s in r0["calls"]) and len(r0["calls"]) >= 1   # (per bucket on a CUDA device)
