@@ -12,6 +12,7 @@ the policy already holds on the device (differentiable, so the averaged panorama
 No CPU / PyTorch fallback: without the library or a B200 the calls raise.
 """
 import ctypes as C
+from itertools import accumulate, chain
 from operator import itemgetter
 
 import numpy as np
@@ -50,42 +51,45 @@ def heading_from_quaternion(coeffs):
 def flatten_gmaps(gmaps, cur_vp, cur_pos, cur_ori):
     """GraphMap objects (models/graph_utils.py:133; anything with ``node_pos, ghost_pos, ghost_aug_pos, node_stepId,
     ghost_fronts, shortest_dist, shortest_path``) -> (meta int32 [B,8], f64 blob, i32 blob, vp id lists, n_max,
-    max_ghosts) in the layout ``etp_gmap_pack`` documents (include/etpnav_b200.h).  Pure re-layout."""
-    meta = np.zeros((len(gmaps), 8), dtype=np.int32)
-    f64, i32b, vp_ids = [], [], []
-    off_f, off_i, n_max, max_g = 0, 0, 1, 0
+    max_ghosts) in the layout ``etp_gmap_pack`` documents (include/etpnav_b200.h).  Pure re-layout: the values of the whole
+    batch are appended to two Python lists by C-level row getters (``itemgetter`` / ``map`` / ``chain``) and converted to
+    arrays ONCE, instead of one numpy conversion per table row."""
+    B = len(gmaps)
+    meta = np.zeros((B, 8), dtype=np.int32)
+    fvals, ivals, vp_ids = [], [], []
+    fext, iext = fvals.extend, ivals.extend
+    n_max, max_g = 1, 0
     for e, gm in enumerate(gmaps):
-        nid, gid = list(gm.node_pos.keys()), list(gm.ghost_pos.keys())
-        ix = {vp: k for k, vp in enumerate(nid)}
+        nid, gid = list(gm.node_pos), list(gm.ghost_pos)
         n, g = len(nid), len(gid)
-        fronts = [[ix[f] for f in gm.ghost_fronts[v]] for v in gid]
-        nfront = [len(f) for f in fronts]
-        sd, sp = gm.shortest_dist, gm.shortest_path
+        ix = dict(zip(nid, range(n)))
         # row getters run the per-row dictionary reads in C (itemgetter with one key returns a scalar: wrap it)
         row = itemgetter(*nid) if n > 1 else (lambda d, k=nid[0]: (d[k],))
-        fe = np.empty(4 + 3 * n + 3 * g + n * n, dtype=np.float64)
-        fe[0:3] = np.asarray(cur_pos[e], dtype=np.float64).reshape(3)
-        fe[3] = heading_from_quaternion(cur_ori[e])
-        fe[4:4 + 3 * n] = np.asarray(row(gm.node_pos), dtype=np.float64).reshape(-1)
+        off_f, off_i = len(fvals), len(ivals)
+        cp = cur_pos[e]
+        fext((float(cp[0]), float(cp[1]), float(cp[2]), heading_from_quaternion(cur_ori[e])))
+        fext(np.asarray(row(gm.node_pos), dtype=np.float64).ravel().tolist())
         if g:
-            fe[4 + 3 * n:4 + 3 * n + 3 * g] = np.asarray([gm.ghost_aug_pos[v] for v in gid], dtype=np.float64).reshape(-1)
-        fe[4 + 3 * n + 3 * g:] = np.asarray([row(sd[a]) for a in nid], dtype=np.float64).reshape(-1)
-        nnz = sum(nfront)
-        ie = np.empty(n + g + 1 + nnz + n * n, dtype=np.int32)
-        ie[0:n] = row(gm.node_stepId)
-        ie[n] = 0
+            fext(np.asarray(itemgetter(*gid)(gm.ghost_aug_pos) if g > 1 else (gm.ghost_aug_pos[gid[0]],),
+                            dtype=np.float64).ravel().tolist())
+        sd, sp = gm.shortest_dist, gm.shortest_path
+        for a in nid:
+            fext(row(sd[a]))
+        iext(row(gm.node_stepId))
+        ivals.append(0)
+        nnz = 0
         if g:
-            np.cumsum(nfront, out=ie[n + 1:n + g + 1])
-            ie[n + g + 1:n + g + 1 + nnz] = [k for f in fronts for k in f]
-        ie[n + g + 1 + nnz:] = np.asarray([list(map(len, row(sp[a]))) for a in nid], dtype=np.int32).reshape(-1)
+            fronts = list(map(gm.ghost_fronts.__getitem__, gid))         # lists of node ids, one per ghost
+            lens = list(accumulate(map(len, fronts)))
+            nnz = lens[-1]
+            iext(lens)
+            iext(map(ix.__getitem__, chain.from_iterable(fronts)))
+        for a in nid:
+            iext(map(len, row(sp[a])))
         meta[e, :6] = (n, g, ix[cur_vp[e]], off_f, off_i, nnz)
-        f64.append(fe)
-        i32b.append(ie)
-        off_f += len(fe)
-        off_i += len(ie)
         n_max, max_g = max(n_max, 1 + n + g), max(max_g, g)
         vp_ids.append([None] + nid + gid)
-    return meta, np.concatenate(f64), np.concatenate(i32b), vp_ids, n_max, max_g
+    return meta, np.array(fvals, dtype=np.float64), np.array(ivals, dtype=np.int32), vp_ids, n_max, max_g
 
 
 def _to_device(arr, dtype, device):
