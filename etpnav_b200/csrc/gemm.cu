@@ -49,17 +49,12 @@ constexpr int kThreadsOf(int ew) { return 64 + ew * 32; }
 constexpr int kTS = 36;  // staging pitch (floats): 16-byte aligned rows, conflict-free for STS.128 rows / LDS.32 columns
 constexpr int kScratchBytesOf(int ew) { return ew * 32 * kTS * 4; }
 
-// MINB = 2: the "two CTA pairs per TPC" variant for problems that are a single round of 256x256 tiles (the thirty-seven
-// 5120x768x768 GEMMs of a training step: 60 tiles on 74 pairs, 4.4 us of MMA inside 17-24 us of launch + prologue +
-// pipeline fill + epilogue).  256x128 tiles, 8 epilogue warps, 3 stages: 110 KB of shared memory and 256 TMEM columns per
-// CTA, so two CTAs are resident per SM and one's epilogue / fill overlaps the other's main loop; all 120 tiles of such a
-// problem are in flight at once.
-template <int BN, int EW, int MINB = 1>
+template <int BN, int EW>
 struct PairCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / 2) * BK * 2;  // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (MINB == 2) ? 3 : ((EW == 8) ? ((BN == 256) ? 5 : 7) : ((BN == 256) ? 4 : 6));
+  static constexpr int kStages = (EW == 8) ? ((BN == 256) ? 5 : 7) : ((BN == 256) ? 4 : 6);
   static constexpr int kScratchBytes = kScratchBytesOf(EW);
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -88,10 +83,9 @@ struct TileRef {
   int m_blk, n_blk, kb0, kb1, g;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool kGrouped, int EW, int MINB = 1>
+template <int BN, bool A_MN, bool B_MN, bool kGrouped, int EW>
 ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, const GroupParams* gp) {
-  using Cfg = PairCfg<BN, EW, MINB>;
-  constexpr bool kPrefetchNext = (EW == 8) && (MINB == 1);  // next-chunk residual prefetch: 168 registers, one CTA per SM only
+  using Cfg = PairCfg<BN, EW>;
   constexpr int kEpiWarps = EW;
   constexpr int kScratchBytes = Cfg::kScratchBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -131,12 +125,7 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
   __syncwarp();
   griddep_launch();  // PDL: the next kernel may start its own prologue
-  // Programmatic dependent launch lets this CTA pair become resident while the previous kernel drains.  What does not touch
-  // global memory — the pair's barrier hand-shake and the TMEM allocation — can run in that shadow (early_setup): the
-  // allocation can only wait for TMEM columns of a CTA of the PREVIOUS kernel still resident on this SM, which frees
-  // them when it exits and never waits for this grid (every kernel of the library is fully resident when it signals
-  // launch_dependents).  Otherwise everything waits for the previous grid first.
-  if (!p.early_setup) griddep_wait();
+  griddep_wait();    // previous kernel complete; nothing above touched global memory or TMEM
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   if (warp == 1) {
     tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols);
@@ -146,7 +135,6 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   cluster_sync_all();  // peer allocated too (execution barrier only) ...
   __syncthreads();     // ... and the TMEM base address written by warp 1 is visible to this CTA's warps
   tc_fence_after();
-  if (p.early_setup) griddep_wait();  // previous kernel complete: its results (our operands) are visible from here on
   const uint32_t tmem_base = *tmem_ptr;
 
   const int num_tiles = kGrouped ? gp->total_tiles : p.tiles_m * p.tiles_n * p.k_splits;
@@ -297,7 +285,7 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
         uint32_t r[32];
         tmem_ld32(taddr0 + c * 32, r);
         float2 Rn[16];
-        if constexpr (kPrefetchNext) {
+        if constexpr (EW == 8) {
           if (e.resid && c + 1 < kChunks) load_resid(c + 1, Rn);  // next chunk's residual while this one is processed
         } else {
           if (e.resid && c > 0) load_resid(c, R);  // (chunk 0 was requested before the accumulator was ready)
@@ -443,7 +431,7 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
             }
           }
         }
-        if constexpr (kPrefetchNext) {
+        if constexpr (EW == 8) {
           if (e.resid && c + 1 < kChunks) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) R[k] = Rn[k];
@@ -482,13 +470,6 @@ template <int BN, bool A_MN, bool B_MN, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsOf(EW), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   gemm_body<BN, A_MN, B_MN, false, EW>(tmA, tmB, p, nullptr);
-}
-
-// two resident CTAs per SM (see PairCfg<.., MINB = 2>)
-template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsOf(8), 2)
-gemm_tcgen05_two_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  gemm_body<128, A_MN, B_MN, false, 8, 2>(tmA, tmB, p, nullptr);
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -531,40 +512,6 @@ int launch_pair_ew(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
   return ETP_OK;
 }
 
-template <bool A_MN, bool B_MN>
-int launch_two(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
-  constexpr int BN = 128;
-  using Cfg = PairCfg<BN, 8, 2>;
-  static_assert(Cfg::kSmemBytes <= 113 * 1024, "two CTAs per SM need <= 113 KB each");
-  CUtensorMap tmA, tmB;
-  int rc;
-  if (!A_MN) rc = get_tmap_2d(a.A, a.M, a.K, a.lda, BM, BK, &tmA);
-  else       rc = get_tmap_2d(a.A, a.K, a.M, a.lda, BK, 64, &tmA);
-  if (rc) return rc;
-  if (!B_MN) rc = get_tmap_2d(a.B, a.N, a.K, a.ldb, BN / 2, BK, &tmB);
-  else       rc = get_tmap_2d(a.B, a.K, a.N, a.ldb, BK, 64, &tmB);
-  if (rc) return rc;
-  auto kern = gemm_tcgen05_two_kernel<A_MN, B_MN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ETP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  const int tiles = dev.tiles_m * dev.tiles_n * dev.k_splits;
-  const int slots = num_sms();  // (num_sms / 2) pairs x two resident CTAs per SM
-  const int grid = 2 * (tiles < slots ? tiles : slots);
-  if (g_prof_on) {
-    char tag[160];
-    snprintf(tag, sizeof(tag), "M%d N%d K%d bn128 two/SM %s%s ks%d%s%s%s%s%s%s", a.M, a.N, a.K, A_MN ? "T" : "N", B_MN ? "T" : "N",
-             dev.k_splits, a.bias ? " bias" : "", a.act ? (a.act == 1 ? " gelu" : " relu") : "", a.aux_mode ? " aux" : "",
-             a.resid ? " resid" : "", a.out_f32 ? (a.atomic ? " red32" : " f32") : "", (a.out_bf16 ? " bf16" : ""));
-    prof_tag(tag, 2.0 * a.M * a.N * a.K);
-  }
-  ETP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreadsOf(8)), Cfg::kSmemBytes, stream, tmA, tmB, dev));
-  ETP_LAUNCHED();
-  return ETP_OK;
-}
-
 template <int BN, bool A_MN, bool B_MN>
 int launch_pair(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
   // 16 epilogue warps for every single-problem launch: measured on one box (tests/run_gpu_ab.sh) the c3 training step
@@ -603,8 +550,6 @@ int launch_grouped_tt(const GemmArgs* a, int n, cudaStream_t stream) {
   GemmDev d;
   memset(&d, 0, sizeof(d));
   d.alpha = 1.0f;
-  static const int early = [] { const char* e = getenv("ETP_GEMM_EARLY"); return e ? atoi(e) : 0; }();
-  d.early_setup = early;
   auto kern = gemm_tcgen05_grouped_kernel<BN, true, true>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -652,8 +597,6 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
   ETP_REQUIRE(!a.drop_thr || (a.k_splits == 1 && !a.atomic && static_cast<int64_t>(a.M) * a.N < (int64_t(1) << 32)),
               "gemm: dropout needs whole-K tiles and < 2^32 elements");
   d.k_splits = a.k_splits;
-  static const int early = [] { const char* e = getenv("ETP_GEMM_EARLY"); return e ? atoi(e) : 0; }();
-  d.early_setup = early;
   // tile-N: 256-wide pair tiles unless N is small / not a multiple of 256, or they would leave most pairs idle
   int bn = a.block_n;
   const int tm = (a.M + 2 * BM - 1) / (2 * BM);
@@ -672,22 +615,11 @@ int gemm(const GemmArgs& a, cudaStream_t stream) {
     }
   }
   ETP_REQUIRE(bn == 128 || bn == 256, "gemm: block_n must be 128 or 256");
-  // one round (or less) of 256x256 tiles: 256x128 tiles with two resident CTAs per SM instead (PairCfg<.., MINB = 2>)
-  static const int two_ok = [] { const char* e = getenv("ETP_GEMM_TWO"); return e ? atoi(e) : 1; }();
-  const bool two = two_ok && a.block_n == 0 && a.k_splits == 1 && a.N >= 128 &&
-                   tm * ((a.N + 255) / 256) <= num_sms() / 2 && a.M >= 1024 && a.K <= 1024;
-  if (two) bn = 128;
   d.tiles_m = tm;
   d.tiles_n = (a.N + bn - 1) / bn;
   const int total_kb = (a.K + BK - 1) / BK;
   d.kb_per_split = (total_kb + a.k_splits - 1) / a.k_splits;
   d.k_splits = (total_kb + d.kb_per_split - 1) / d.kb_per_split;  // drop empty splits
-  if (two) {
-    if (!a.a_mn && !a.b_mn) return launch_two<false, false>(a, d, stream);
-    if (!a.a_mn && a.b_mn) return launch_two<false, true>(a, d, stream);
-    if (a.a_mn && a.b_mn) return launch_two<true, true>(a, d, stream);
-    return launch_two<true, false>(a, d, stream);
-  }
 #define ETP_PAIR_DISPATCH(BN_)                                                          \
   if (!a.a_mn && !a.b_mn) return launch_pair<BN_, false, false>(a, d, stream);          \
   if (!a.a_mn && a.b_mn) return launch_pair<BN_, false, true>(a, d, stream);            \

@@ -26,7 +26,6 @@ struct GemmDev {
   float* colsum;  // fp32 [N] += column sums of the final value
   uint32_t drop_key, drop_thr;  // dropout of the activated value before the residual add (thr 0 = off)
   float drop_scale;
-  int early_setup;  // 1: cluster barrier + TMEM allocation run BEFORE griddepcontrol.wait (hidden behind the previous kernel's tail)
 };
 
 }  // namespace etp
