@@ -501,6 +501,11 @@ def _latest_profile(prefix_glob):
 
 
 def main():
+    # One hardware work queue per CUDA stream: the step uses three streams (compute, the trainer's update stream, the
+    # input stager's copy stream).  With the default of 8 connections two of them can share a queue, and then the next
+    # step's host->device copy sits behind the update stream's pending event wait (observed: e2e 94-112 steps/s in some
+    # processes, 178-183 in others, same box, the copy alone at 55 GB/s in both).  Must be set before the CUDA context exists.
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     a = parse()
     if a.workload == "pretrain":
         return run_pretrain_workload(a)
