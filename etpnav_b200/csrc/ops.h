@@ -216,6 +216,7 @@ int embed_txt_bwd(const float* dx, const int64_t* ids, const float* sum_pre, con
 int adamw_step(float* param, bf16* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                cudaStream_t stream, const uint8_t* flags = nullptr, const float* normsq = nullptr, float max_norm = 0.0f);
+void set_adamw_ctas_per_sm(int n);  // grid size of the update kernel: 16 (default, alone at the HBM roofline) .. 1 (background)
 // out[0] += sum g^2 over the blocks whose flag bit 0 is set (all of them when flags == nullptr)
 int grad_sumsq(const float* grad, int64_t n, const uint8_t* flags, float* out, cudaStream_t stream);
 

@@ -4,6 +4,8 @@
 // or, where only a few hundred rows exist, added straight to global memory with 128-bit vector reductions.
 // (Shared-memory float atomics are CAS loops: with eight warps adding to the same 768 addresses they cost ~20 us
 // per ROW in the first version of these kernels.)
+#include <atomic>
+
 #include "common.cuh"
 #include "host.h"
 #include "ops.h"
@@ -394,6 +396,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, bf16*
   }
 }
 
+static std::atomic<int> g_adamw_ctas_per_sm{16};
+void set_adamw_ctas_per_sm(int n) { g_adamw_ctas_per_sm.store(n < 1 ? 1 : (n > 16 ? 16 : n)); }
+
 int adamw_step(float* param, bf16* param_bf16, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                cudaStream_t stream, const uint8_t* flags, const float* normsq, float max_norm) {
@@ -403,7 +408,11 @@ int adamw_step(float* param, bf16* param_bf16, const float* grad, float* exp_avg
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   int64_t blocks = (n / 4 + 255) / 256;
-  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
+  // default: 16 CTAs per SM (the update alone at the HBM roofline).  A host that runs the update on a side stream UNDER
+  // the backward pass (PlannerTrainer) asks for a small grid (etp_set_adamw_ctas_per_sm): one grid-striding CTA per SM
+  // streams at a fraction of the bandwidth but leaves the registers / thread slots the persistent GEMM CTAs need.
+  const int per_sm = g_adamw_ctas_per_sm.load(std::memory_order_relaxed);
+  if (blocks > static_cast<int64_t>(per_sm) * num_sms()) blocks = static_cast<int64_t>(per_sm) * num_sms();
   ETP_CHECK_CUDA(launch_pdl(adamw_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, param, param_bf16, grad, exp_avg, exp_avg_sq, n / 4, lr, beta1,
                                                              beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, flags, normsq, max_norm));
   ETP_LAUNCHED();

@@ -556,6 +556,7 @@ ETP_API int etp_adamw_step_ex(float* param, void* param_bf16, const float* grad,
   return adamw_step(param, static_cast<bf16*>(param_bf16), grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                     step, grad_scale, S(stream), flags, normsq, max_norm);
 }
+ETP_API void etp_set_adamw_ctas_per_sm(int32_t n) { set_adamw_ctas_per_sm(n); }
 ETP_API int etp_grad_sumsq(const float* grad, int64_t n, const uint8_t* flags, float* out, void* stream) {
   return grad_sumsq(grad, n, flags, out, S(stream));
 }

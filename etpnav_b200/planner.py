@@ -885,6 +885,11 @@ class PlannerTrainer:
             X = model.config.num_x_layers
             self._events = [L0.etp_event_create() for _ in range(X + 1)]   # one per x-layer + "nav group complete"
             model._layer_events = (p_void * (X + 1))(*self._events)
+            # the update runs UNDER the backward: a small grid-striding grid, so it does not take the registers / thread
+            # slots the persistent GEMM CTA pairs need (ETP_ADAMW_CTAS overrides: 16 = the stand-alone roofline grid)
+            import os as _os
+            L0.etp_set_adamw_ctas_per_sm.argtypes = [i32]
+            L0.etp_set_adamw_ctas_per_sm(int(_os.environ.get("ETP_ADAMW_CTAS", "2")))
             if world_size > 1:
                 L0.etp_set_sm_reserve.argtypes = [i32]
                 L0.etp_set_sm_reserve(self.comm_sms)

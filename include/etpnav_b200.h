@@ -395,6 +395,9 @@ int etp_adamw_step_ex(float* param, void* param_bf16, const float* grad, float* 
                       float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                       const uint8_t* flags, const float* normsq, float max_norm, void* stream);
 int etp_grad_sumsq(const float* grad, int64_t n, const uint8_t* flags, float* out, void* stream);
+/* CTAs per SM of the update kernel: 16 (default: the update alone runs at the HBM roofline) down to 1 (a host that runs it
+ * on a side stream under the backward pass: a small grid-striding grid leaves the SM resources to the GEMM CTAs). */
+void etp_set_adamw_ctas_per_sm(int32_t n);
 
 /* ---------------------------------------------------------------------------------------------
  * pre-training twin: GlocalTextPathCMT of pretrain_src/pretrain_src/model/vilmodel.py:656-754.
