@@ -35,6 +35,11 @@ ETP_API void* etp_event_create(void) {
 ETP_API void etp_event_destroy(void* event) {
   if (event) cudaEventDestroy(static_cast<cudaEvent_t>(event));
 }
+ETP_API int etp_event_record(void* event, void* stream) {
+  ETP_REQUIRE(event != nullptr, "etp_event_record: null event");
+  ETP_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), S(stream)));
+  return ETP_OK;
+}
 ETP_API int etp_stream_wait_event(void* stream, void* event) {
   ETP_REQUIRE(event != nullptr, "etp_stream_wait_event: null event");
   ETP_CHECK_CUDA(cudaStreamWaitEvent(S(stream), static_cast<cudaEvent_t>(event), 0));

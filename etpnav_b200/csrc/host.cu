@@ -196,6 +196,7 @@ int prof_collect(double* ms, double* flops, long long* count, char* report, size
 // tile, for the SM pairs an NCCL kernel occupies, and the all-reduce waits for SMs the GEMMs never release.
 static std::atomic<int> g_sm_reserve{0};
 void set_sm_reserve(int n) { g_sm_reserve.store(n < 0 ? 0 : n); }
+int get_sm_reserve() { return g_sm_reserve.load(); }
 int num_sms() {
   static int n = 0;
   if (n == 0) {

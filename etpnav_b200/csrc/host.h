@@ -74,7 +74,8 @@ int get_tmap_3d(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t
                 uint32_t box1, CUtensorMap* out);
 
 int num_sms();               // SMs available to the library's persistent grids (device SMs minus the reserve)
-void set_sm_reserve(int n);  // SMs left to other kernels (collectives) while data-parallel training
+void set_sm_reserve(int n);
+int get_sm_reserve();  // SMs left to other kernels (collectives) while data-parallel training
 
 // host side of the dropout scheme (common.cuh: Drop): key of a site from the call's seed (splitmix64), threshold and
 // scale from the probability.  p <= 0 gives thr = 0 (off).

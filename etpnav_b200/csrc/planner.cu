@@ -203,16 +203,23 @@ int forward_navigation(const etp_nav_weights& w, const etp_nav_inputs& in, float
     ETP_TRY(cast_f32_to_bf16(in.txt_embeds, rec.txtb, static_cast<int64_t>(B) * L * kH, s));
     txtb = rec.txtb;
   }
+  // text K|V of every layer in ONE GEMM: [B*L,768] x [X*1536,768]^T (they depend only on txt_embeds).  Issued FIRST: it is
+  // the one node-independent GEMM of the call, so a host may still be producing gmap_img_fts on another stream
+  // (img_ready_event) while it runs, on the SMs side_sm_reserve leaves to that stream.
+  if (X > 0 && kv_cache == nullptr) {
+    const int prev = get_sm_reserve();
+    if (in.side_sm_reserve > 0) set_sm_reserve(prev + in.side_sm_reserve);
+    const int rc = linear(txtb, B * L, kH, w.xkv_all_w, X * 2 * kH, w.xkv_all_b, 0, nullptr, nullptr, rec.kv_all, nullptr, s);
+    set_sm_reserve(prev);
+    ETP_TRY(rc);
+  }
+  if (in.img_ready_event) ETP_CHECK_CUDA(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(in.img_ready_event), 0));
   NodePackArgs np;
   np.rows = rows; np.img_fts = in.gmap_img_fts; np.step_ids = in.gmap_step_ids; np.pos_fts = in.gmap_pos_fts;
   np.pos_w = w.pos_w; np.pos_b = w.pos_b; np.pos_g = w.pos_g; np.pos_bb = w.pos_bb; np.step_emb = w.step_emb;
   np.x_f32 = X > 0 ? rec.xf : gmap_embeds; np.x_bf16 = rec.x0b;
   np.pos_lin = training ? rec.pos_lin : nullptr; np.stats = rec.pos_stats;
   ETP_TRY(node_pack_fwd(np, s));
-
-  // text K|V of every layer in ONE GEMM: [B*L,768] x [X*1536,768]^T (they depend only on txt_embeds)
-  if (X > 0 && kv_cache == nullptr)
-    ETP_TRY(linear(txtb, B * L, kH, w.xkv_all_w, X * 2 * kH, w.xkv_all_b, 0, nullptr, nullptr, rec.kv_all, nullptr, s));
   const float* x_f32 = np.x_f32;
   const bf16* x_bf16 = rec.x0b;
   for (int i = 0; i < X; ++i) {

@@ -268,19 +268,26 @@ int backward_navigation(const etp_nav_weights& w, const etp_nav_weights& g, cons
     if (in.layer_done_events && in.layer_done_events[i])
       ETP_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(in.layer_done_events[i]), s));
   }
-  // text side, all layers at once: kv_all = txt . Wkv_all^T + b  ->  one wgrad, one dgrad (bias grads: above)
-  if (X > 0) {
-    const bf16* txtb = in.txt_embeds_bf16 ? static_cast<const bf16*>(in.txt_embeds_bf16) : rec.txtb;
-    ETP_TRY(wgrad(sc.dkv, kv_rows, ldkv, ldkv, txtb, kH, kH, const_cast<void*>(g.xkv_all_w), s));
-    if (d_txt_embeds) ETP_TRY(dgrad(sc.dkv, kv_rows, ldkv, ldkv, w.xkv_all_w, kH, nullptr, dtxt, nullptr, 0, nullptr, s));
-  } else if (d_txt_embeds) {
-    ETP_CHECK_CUDA(cudaMemsetAsync(d_txt_embeds, 0, static_cast<size_t>(kv_rows) * kH * 4, s));
-  }
-  // node packing: x0 = img_fts + E_step[ids] + LN(pos_fts.W^T + b)
+  // node packing: x0 = img_fts + E_step[ids] + LN(pos_fts.W^T + b).  Done BEFORE the text-side GEMMs: d_gmap_img_fts is
+  // what the panorama branch's backward waits for (img_grad_event), and nothing below touches it.
   ETP_TRY(node_pack_bwd(P, in.gmap_step_ids, in.gmap_pos_fts, rec.pos_lin, rec.pos_stats, w.pos_g, rows, F(g.step_emb),
                         F(g.pos_w), F(g.pos_b), F(g.pos_g), F(g.pos_bb), s));
   if (d_gmap_img_fts)
     ETP_CHECK_CUDA(cudaMemcpyAsync(d_gmap_img_fts, P, static_cast<size_t>(rows) * kH * 4, cudaMemcpyDeviceToDevice, s));
+  if (in.img_grad_event) ETP_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(in.img_grad_event), s));
+  // text side, all layers at once: kv_all = txt . Wkv_all^T + b  ->  one wgrad, one dgrad (bias grads: above); they leave
+  // side_sm_reserve SMs to the stream that now runs the panorama backward
+  if (X > 0) {
+    const bf16* txtb = in.txt_embeds_bf16 ? static_cast<const bf16*>(in.txt_embeds_bf16) : rec.txtb;
+    const int prev = get_sm_reserve();
+    if (in.side_sm_reserve > 0) set_sm_reserve(prev + in.side_sm_reserve);
+    int rc = wgrad(sc.dkv, kv_rows, ldkv, ldkv, txtb, kH, kH, const_cast<void*>(g.xkv_all_w), s);
+    if (rc == ETP_OK && d_txt_embeds) rc = dgrad(sc.dkv, kv_rows, ldkv, ldkv, w.xkv_all_w, kH, nullptr, dtxt, nullptr, 0, nullptr, s);
+    set_sm_reserve(prev);
+    ETP_TRY(rc);
+  } else if (d_txt_embeds) {
+    ETP_CHECK_CUDA(cudaMemsetAsync(d_txt_embeds, 0, static_cast<size_t>(kv_rows) * kH * 4, s));
+  }
   // entry X of the optional event array: every gradient of the navigation group is complete
   if (in.layer_done_events && in.layer_done_events[X])
     ETP_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(in.layer_done_events[X]), s));

@@ -50,7 +50,8 @@ class NavInputs(C.Structure):
         (n, p_void) for n in ("txt_embeds", "txt_masks", "gmap_step_ids", "gmap_img_fts", "gmap_pos_fts",
                               "gmap_masks", "gmap_visited_masks", "gmap_pair_dists")] + [
         ("dropout", C.POINTER(Dropout)), ("layer_done_events", C.POINTER(p_void)), ("txt_embeds_bf16", p_void),
-        ("txt_kv_all", p_void), ("txt_kv_rows", p_void), ("txt_kv_batch", i32)]
+        ("txt_kv_all", p_void), ("txt_kv_rows", p_void), ("txt_kv_batch", i32),
+        ("side_sm_reserve", i32), ("img_ready_event", p_void), ("img_grad_event", p_void)]
 
 
 class PanoLayerWeights(C.Structure):
@@ -644,11 +645,14 @@ def _nav_inputs(txt, img, aux, drop=None):
     return ni
 
 
-def _nav_forward(m, txt, img, aux, training, drop=None):
+def _nav_forward(m, txt, img, aux, training, drop=None, img_ready_event=None, side_sm_reserve=0):
     B, N = img.shape[:2]
     Lt = txt.shape[1]
     L = _L.lib()
     ni = _nav_inputs(txt, img, aux, drop)
+    if img_ready_event is not None:
+        ni.img_ready_event = C.c_void_p(img_ready_event)
+    ni.side_sm_reserve = side_sm_reserve
     embeds = torch.empty(B, N, 768, device=img.device, dtype=torch.float32)
     logits = torch.empty(B, N, device=img.device, dtype=torch.float32)
     nbytes = L.etp_nav_saved_bytes(B, N, Lt, m.config.num_x_layers, training)
@@ -696,6 +700,59 @@ def _nav_forward_hp(m, txt, img, aux):
     return embeds, logits
 
 
+def _nav_backward_raw(m, txt, img, aux, drop, saved, de, dl, want_dtxt, want_dimg, img_grad_event=None, side_sm_reserve=0):
+    """etp_backward_navigation on the current stream; parameter gradients go to m._grad_target('nav').
+    Returns (d_txt, d_img, gbuf, gstart, per_call)."""
+    L = _L.lib()
+    B, N, Lt = img.shape[0], img.shape[1], txt.shape[1]
+    gbuf, gstart, per_call = m._grad_target("nav")
+    gst = m._grad_structs_for(gbuf, gstart)
+    ni = _nav_inputs(txt, img, aux, drop)
+    if m._layer_events is not None:
+        ni.layer_done_events = m._layer_events
+    if img_grad_event is not None:
+        ni.img_grad_event = C.c_void_p(img_grad_event)
+    ni.side_sm_reserve = side_sm_reserve
+    d_txt = torch.empty(txt.shape, dtype=torch.float32, device=txt.device) if want_dtxt else None
+    d_img = torch.empty_like(img) if want_dimg else None
+    wbytes = L.etp_nav_bwd_work_bytes(B, N, Lt, m.config.num_x_layers)
+    work = torch.empty(wbytes, dtype=torch.uint8, device=img.device)
+    _L._check(L.etp_backward_navigation(C.byref(m._structs["nav"]), C.byref(gst["nav"]), C.byref(ni), _L.ptr(de),
+                                        _L.ptr(dl), _L.ptr(saved), saved.numel(), _L.ptr(work), wbytes,
+                                        _L.ptr(d_txt), _L.ptr(d_img), _L.stream_ptr()), "etp_backward_navigation")
+    return d_txt, d_img, gbuf, gstart, per_call
+
+
+def _pano_backward_raw(m, rgb, dep, loc, nt, vl, masks, drop, saved, d_out, want_drgb, want_ddep):
+    """etp_backward_panorama on the current stream.  Returns (d_rgb, d_dep, gbuf, gstart, per_call, tok) where ``tok`` is
+    the per-call token-type row-1 gradient (None in the trainer's direct-gradient mode)."""
+    L = _L.lib()
+    B, V = rgb.shape[:2]
+    gs, ge = m.layout.group_ranges["pano"]
+    if m._direct_grad is not None:
+        gbuf, gstart, per_call = m._direct_grad, 0, False
+        gst = m._grad_structs_for(gbuf, gstart)
+        tok = None
+        if getattr(m, "_tok_scratch", None) is not None:
+            gst["pano"].tok_emb1 = C.c_void_p(m._tok_scratch.data_ptr())
+    else:
+        # group-sized scratch + 768 extra floats for the token-type row 1, which lives in the txt group
+        gbuf = torch.zeros(ge - gs + 768, dtype=torch.float32, device=rgb.device)
+        gstart, per_call = gs, True
+        gst = m._grad_structs_for(gbuf, gstart)
+        tok = gbuf[ge - gs:]
+        gst["pano"].tok_emb1 = C.c_void_p(tok.data_ptr())
+    pi = _pano_inputs(rgb, dep, loc, nt, vl, drop)
+    d_rgb = torch.empty_like(rgb) if want_drgb else None
+    d_dep = torch.empty_like(dep) if (want_ddep and m.config.use_depth_embedding) else None
+    wbytes = L.etp_pano_bwd_work_bytes(B, V)
+    work = torch.empty(wbytes, dtype=torch.uint8, device=rgb.device)
+    _L._check(L.etp_backward_panorama(C.byref(m._structs["pano"]), C.byref(gst["pano"]), C.byref(pi), _L.ptr(masks),
+                                      _L.ptr(_f32c(d_out)), _L.ptr(saved), saved.numel(), _L.ptr(work), wbytes,
+                                      _L.ptr(d_rgb), _L.ptr(d_dep), _L.stream_ptr()), "etp_backward_panorama")
+    return d_rgb, d_dep, gbuf, gstart, per_call, tok
+
+
 # ----------------------------------------------------------------------------------------------------
 # autograd glue: one node per reference method; backward = one step-level C call
 # ----------------------------------------------------------------------------------------------------
@@ -718,24 +775,12 @@ class _NavFn(torch.autograd.Function):
     def backward(ctx, d_embeds, d_logits):
         m = ctx.m
         txt, img, aux = ctx.keep
-        L = _L.lib()
-        B, N, Lt = img.shape[0], img.shape[1], txt.shape[1]
-        gbuf, gstart, per_call = m._grad_target("nav")
-        gst = m._grad_structs_for(gbuf, gstart)
-        ni = _nav_inputs(txt, img, aux, ctx.drop)
-        if m._layer_events is not None:
-            ni.layer_done_events = m._layer_events
         de = _f32c(d_embeds) if d_embeds is not None else None
         dl = _f32c(d_logits) if d_logits is not None else None
         if dl is not None:
             dl = torch.nan_to_num(dl, nan=0.0, posinf=0.0, neginf=0.0)
-        d_txt = torch.empty(txt.shape, dtype=torch.float32, device=txt.device) if ctx.needs_input_grad[1] else None
-        d_img = torch.empty_like(img) if ctx.needs_input_grad[2] else None
-        wbytes = L.etp_nav_bwd_work_bytes(B, N, Lt, m.config.num_x_layers)
-        work = torch.empty(wbytes, dtype=torch.uint8, device=img.device)
-        _L._check(L.etp_backward_navigation(C.byref(m._structs["nav"]), C.byref(gst["nav"]), C.byref(ni), _L.ptr(de),
-                                            _L.ptr(dl), _L.ptr(ctx.saved), ctx.saved.numel(), _L.ptr(work), wbytes,
-                                            _L.ptr(d_txt), _L.ptr(d_img), _L.stream_ptr()), "etp_backward_navigation")
+        d_txt, d_img, gbuf, gstart, per_call = _nav_backward_raw(m, txt, img, aux, ctx.drop, ctx.saved, de, dl,
+                                                                 ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         pg = _param_grads(m, m._group_names("nav"), gbuf, gstart, per_call, ctx.nparams)
         if d_txt is not None and d_txt.dtype != ctx.in_dtypes[0]:
             d_txt = d_txt.to(ctx.in_dtypes[0])
@@ -759,30 +804,8 @@ class _PanoFn(torch.autograd.Function):
     def backward(ctx, d_out, _unused):
         m = ctx.m
         rgb, dep, loc, nt, vl, masks = ctx.keep
-        L = _L.lib()
-        B, V = rgb.shape[:2]
-        gs, ge = m.layout.group_ranges["pano"]
-        if m._direct_grad is not None:
-            gbuf, gstart, per_call = m._direct_grad, 0, False
-            gst = m._grad_structs_for(gbuf, gstart)
-            tok = None
-            if getattr(m, "_tok_scratch", None) is not None:
-                gst["pano"].tok_emb1 = C.c_void_p(m._tok_scratch.data_ptr())
-        else:
-            # group-sized scratch + 768 extra floats for the token-type row 1, which lives in the txt group
-            gbuf = torch.zeros(ge - gs + 768, dtype=torch.float32, device=rgb.device)
-            gstart, per_call = gs, True
-            gst = m._grad_structs_for(gbuf, gstart)
-            tok = gbuf[ge - gs:]
-            gst["pano"].tok_emb1 = C.c_void_p(tok.data_ptr())
-        pi = _pano_inputs(rgb, dep, loc, nt, vl, ctx.drop)
-        d_rgb = torch.empty_like(rgb) if ctx.needs_input_grad[1] else None
-        d_dep = torch.empty_like(dep) if (ctx.needs_input_grad[2] and m.config.use_depth_embedding) else None
-        wbytes = L.etp_pano_bwd_work_bytes(B, V)
-        work = torch.empty(wbytes, dtype=torch.uint8, device=rgb.device)
-        _L._check(L.etp_backward_panorama(C.byref(m._structs["pano"]), C.byref(gst["pano"]), C.byref(pi), _L.ptr(masks),
-                                          _L.ptr(_f32c(d_out)), _L.ptr(ctx.saved), ctx.saved.numel(), _L.ptr(work), wbytes,
-                                          _L.ptr(d_rgb), _L.ptr(d_dep), _L.stream_ptr()), "etp_backward_panorama")
+        d_rgb, d_dep, gbuf, gstart, per_call, tok = _pano_backward_raw(m, rgb, dep, loc, nt, vl, masks, ctx.drop, ctx.saved, d_out,
+                                                                       ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         pg = []
         if ctx.nparams:
             names = m._pano_param_names()
@@ -833,7 +856,7 @@ class PlannerTrainer:
     AdamW (torch.optim.AdamW defaults, :213) that also refreshes the bf16 weight image."""
 
     def __init__(self, model, lr=1e-5, world_size=1, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, groups=("pano", "nav"),
-                 grad_comm="fp32", comm_sms=0):
+                 grad_comm="fp32", comm_sms=0, overlap=True, pano_sms=28):
         """``grad_comm``: dtype the gradient buckets cross NVLink in — "fp32" (DDP's default, the reference) or "bf16"
         (each bucket is rounded to bf16 for the all-reduce and widened again: half the bytes, like DDP's bf16 compression
         hook; gradients are still ACCUMULATED and applied in fp32).  ``comm_sms``: SMs the library's persistent grids leave
@@ -842,6 +865,12 @@ class PlannerTrainer:
         if grad_comm not in ("fp32", "bf16"):
             raise ValueError("grad_comm must be 'fp32' or 'bf16'")
         self.grad_comm, self.comm_sms, self._comm_buf = grad_comm, int(comm_sms), None
+        # panorama branch on its own stream next to the instruction-side GEMMs of the navigation call
+        # (_forward_backward_overlapped); ETP_OVERLAP=0 / overlap=False runs the two calls back to back through autograd
+        import os as _os0
+        self.overlap = bool(overlap) and _os0.environ.get("ETP_OVERLAP", "1") != "0"
+        self.pano_sms = int(_os0.environ.get("ETP_PANO_SMS", pano_sms))
+        self.pano_stream, self._ev_img, self._ev_dimg = None, None, None
         dev = model._flat.device
         if world_size > 1:
             # DDP broadcasts rank 0's parameters when it wraps the module (ss_trainer_ETP.py:211-212): replicas built from
@@ -878,6 +907,12 @@ class PlannerTrainer:
         self.side, self._events = None, []
         if dev.type == "cuda":
             self.side = torch.cuda.Stream(dev)
+            self.pano_stream = torch.cuda.Stream(dev)
+            _Le = _L.lib()
+            _Le.etp_event_create.restype = p_void
+            _Le.etp_event_record.argtypes = [p_void, p_void]
+            _Le.etp_stream_wait_event.argtypes = [p_void, p_void]
+            self._ev_img, self._ev_dimg = _Le.etp_event_create(), _Le.etp_event_create()
             L0 = _L.lib()
             L0.etp_event_create.restype = p_void
             L0.etp_event_destroy.argtypes = [p_void]
@@ -924,6 +959,8 @@ class PlannerTrainer:
             self.m._tok_scratch.zero_()
 
     def forward_backward(self, d):
+        if self.pano_stream is not None and self.overlap:
+            return self._forward_backward_overlapped(d)
         m = self.m
         pano, pmask = m.forward_panorama(d["rgb_fts"], d["dep_fts"], d["loc_fts"], d["nav_types"], d["view_lens"])
         # the trainer feeds the masked mean of the view embeddings back into the map as a node feature
@@ -940,6 +977,52 @@ class PlannerTrainer:
         # nll / nan_to_num chain; the gradient enters autograd at the logits
         loss_sum, dlogits, self.last_action, _ = _L.step_loss(logits, d["labels"], grad_scale=1.0 / logits.shape[0])
         logits.backward(dlogits)
+        return logits, loss_sum / logits.shape[0]
+
+    def _forward_backward_overlapped(self, d):
+        """The same step with the panorama branch on its OWN stream.  Its 768 view rows keep ~130 SMs idle whatever the
+        kernel; the only node-independent GEMMs of the navigation call are the instruction's all-layer K|V projection
+        (forward) and its weight gradient (backward).  So: forward_panorama (and the masked mean into the map feature)
+        runs next to the K|V projection, which leaves ``pano_sms`` SMs free (etp_nav_inputs.side_sm_reserve,
+        img_ready_event); backward_panorama starts as soon as d_gmap_img_fts is final (img_grad_event) and runs next to
+        the text-side weight gradient.  No autograd graph is built: the step-level C calls are issued directly, in the
+        order and with the dropout seeds forward_backward() uses (same results)."""
+        m = self.m
+        main, S2 = torch.cuda.current_stream(), self.pano_stream
+        L0, s2_ptr = _L.lib(), C.c_void_p(self.pano_stream.cuda_stream)
+        m._refresh_cache()
+        rgb, dep, loc = _f32c(d["rgb_fts"]), _f32c(d["dep_fts"]), _f32c(d["loc_fts"])
+        nt, vl = d["nav_types"].contiguous().long(), d["view_lens"].contiguous().long()
+        aux = (m._mask_u8(d["txt_masks"]), d["gmap_step_ids"].contiguous().long(), _f32c(d["gmap_pos_fts"]),
+               m._mask_u8(d["gmap_masks"]), m._mask_u8(d["gmap_visited_masks"]), _f32c(d["gmap_pair_dists"]))
+        txt, img_in = _txtc(d["txt_embeds"]), _f32c(d["gmap_img_fts"])
+        drop_p, drop_n = m._next_dropout(), m._next_dropout()     # panorama call first, as in forward_backward()
+        # ---- forward: panorama branch on S2, navigation on the compute stream
+        S2.wait_stream(main)
+        with torch.cuda.stream(S2):
+            pano, pmask_u8, saved_p, _ = _pano_forward(m, rgb, dep, loc, nt, vl, 1, drop_p)
+            w = pmask_u8.unsqueeze(-1).float()
+            wn = w / w.sum(1, keepdim=True)
+            img = img_in.clone()
+            img[:, 1] += (pano * wn).sum(1)
+            _L._check(L0.etp_event_record(C.c_void_p(self._ev_img), s2_ptr), "etp_event_record")
+        img.record_stream(main)
+        for t in (rgb, dep, loc, nt, vl):
+            t.record_stream(S2)
+        ni_extra = dict(img_ready_event=self._ev_img, side_sm_reserve=self.pano_sms)
+        embeds, logits, saved_n, _ = _nav_forward(m, txt, img, aux, 1, drop_n, **ni_extra)
+        loss_sum, dlogits, self.last_action, _ = _L.step_loss(logits, d["labels"], grad_scale=1.0 / logits.shape[0])
+        # ---- backward: navigation on the compute stream; panorama on S2 from the moment d_gmap_img_fts is final
+        _, d_img, _, _, _ = _nav_backward_raw(m, txt, img, aux, drop_n, saved_n, None, dlogits, False, True,
+                                              img_grad_event=self._ev_dimg, side_sm_reserve=self.pano_sms)
+        d_img.record_stream(S2)
+        _L._check(L0.etp_stream_wait_event(s2_ptr, C.c_void_p(self._ev_dimg)), "etp_stream_wait_event")
+        with torch.cuda.stream(S2):
+            d_pano = wn * d_img[:, 1].unsqueeze(1)                # backward of the masked mean into node 1
+            _pano_backward_raw(m, rgb, dep, loc, nt, vl, pmask_u8, drop_p, saved_p, d_pano, False, False)
+        # the panorama gradients are part of this call's result: the compute stream joins (it has nothing else queued;
+        # the bucketed update on the side stream is unaffected)
+        main.wait_stream(S2)
         return logits, loss_sum / logits.shape[0]
 
     def _bucket_runs(self, a, b):
@@ -984,7 +1067,9 @@ class PlannerTrainer:
                 ev = self._events[X if nm == "nav_head" else int(nm.split("_")[-1])]
                 _L._check(L0.etp_stream_wait_event(side_ptr, C.c_void_p(ev)), "etp_stream_wait_event")
             else:
-                self.side.wait_stream(main)       # final only when the whole backward is
+                self.side.wait_stream(main)       # final only when the whole backward is ...
+                if self.pano_stream is not None:
+                    self.side.wait_stream(self.pano_stream)   # ... including the panorama branch on its own stream
             with torch.cuda.stream(self.side):
                 if self.world > 1:
                     import torch.distributed as dist

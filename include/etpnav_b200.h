@@ -48,6 +48,7 @@ int etp_check_device(void);
 /* thin CUDA event helpers for hosts without their own bindings (used for the gradient-bucket overlap) */
 void* etp_event_create(void);                       /* cudaEventCreateWithFlags(disable timing); NULL on error */
 void etp_event_destroy(void* event);
+int etp_event_record(void* event, void* stream);        /* cudaEventRecord */
 int etp_stream_wait_event(void* stream, void* event);   /* cudaStreamWaitEvent */
 /* Leave `n` SMs to other kernels: the library's persistent grids (one CTA or CTA pair per SM) size themselves for the
  * remaining ones.  A data-parallel host sets this to the CTA count of its gradient all-reduce (NCCL_MAX_CTAS) so the
@@ -264,6 +265,18 @@ typedef struct {
   const void* txt_kv_all;
   const int32_t* txt_kv_rows;
   int32_t txt_kv_batch;
+  /* optional, for a host that runs the panorama branch on a second stream next to the instruction-side work of this
+   * call (the 768 view rows keep ~130 SMs idle; the text K|V projection and its weight gradient are the only node-
+   * independent GEMMs of the step):
+   *   side_sm_reserve  SMs the text-side GEMMs of this call (all-layer K|V projection forward; its weight / data
+   *                    gradient backward) leave free for that other stream (0 = none)
+   *   img_ready_event  forward: cudaEvent_t the stream waits for right before gmap_img_fts is first read (node packing),
+   *                    i.e. AFTER the text K|V projection has been issued
+   *   img_grad_event   backward: cudaEvent_t recorded as soon as d_gmap_img_fts is final, BEFORE the text-side gradient
+   *                    GEMMs are issued */
+  int32_t side_sm_reserve;
+  void* img_ready_event;
+  void* img_grad_event;
 } etp_nav_inputs;
 
 /* Bytes of the activation record forward_navigation writes (and backward reads) when training != 0;

@@ -104,3 +104,41 @@ def test_adamw_ex_matches_torch_param_groups_and_clipping():
     assert (p[1280:1920] - tb_.detach()).abs().max().item() < 2e-6
     assert torch.equal(p[1920:], p0[1920:])                                 # frozen: no update, no decay
     assert torch.equal(pb[:1920], p[:1920].bfloat16())
+
+
+def test_overlapped_trainer_step_equals_the_sequential_one():
+    """PlannerTrainer runs the panorama branch on its own stream next to the instruction-side GEMMs of the navigation
+    call (no autograd graph, events for gmap_img_fts / d_gmap_img_fts).  Same dropout seeds, same kernels: logits and the
+    whole flat gradient must agree with the autograd-driven sequential step up to the re-association of the masked mean
+    (and fp32 atomics order); repeated steps keep agreeing (no stream race that would only show up later)."""
+    from etpnav_b200.config import PlannerConfig
+    from etpnav_b200.planner import B200Planner
+    from etpnav_b200.synth import make_inputs, make_weights
+    cfg = PlannerConfig(vocab_size=2048, num_l_layers=0, num_x_layers=3)       # dropout on (the reference's 0.1)
+    sd = make_weights(cfg, seed=17)
+    d = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in make_inputs(cfg, 16, 12, 40, 90, seed=17, ragged=True).items()}
+    outs = []
+    for overlap in (False, True):
+        m = B200Planner(cfg, device="cuda")
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        m.set_dropout_seed(99)
+        tr = m.make_trainer(lr=1e-4, overlap=overlap)
+        assert tr.overlap == overlap
+        rec = []
+        for _ in range(3):
+            tr.zero_grad()
+            logits, loss = tr.forward_backward(d)
+            torch.cuda.synchronize()
+            rec.append((logits.detach().clone(), m._direct_grad[tr.lo:tr.hi].clone(), loss.clone()))
+            tr.optimizer_step()
+        torch.cuda.synchronize()
+        outs.append((rec, m._flat[tr.lo:tr.hi].clone()))
+    (seq, p_seq), (ovl, p_ovl) = outs
+    for (lg_a, g_a, loss_a), (lg_b, g_b, loss_b) in zip(seq, ovl):
+        fin = ~torch.isinf(lg_a)
+        assert torch.equal(torch.isinf(lg_a), torch.isinf(lg_b))
+        assert (lg_a[fin] - lg_b[fin]).abs().max().item() < 5e-3
+        assert abs(loss_a.item() - loss_b.item()) < 1e-3
+        assert ((g_a - g_b).norm() / g_a.norm()).item() < 2e-2
+    assert ((p_seq - p_ovl).norm() / p_seq.norm()).item() < 1e-4
