@@ -274,20 +274,6 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
         }
       };
       if (e.resid) load_resid(0, R);  // lands while the main loop of this tile is still running
-      // the bf16 side input of the epilogue (saved GELU' / activation for the derivative), same transposed layout
-      uint32_t ax[16];
-      auto load_aux = [&](int c, uint32_t (&dst)[16]) {
-        const int col = colbase + c * 32;
-        const char* ap = reinterpret_cast<const char*>(e.aux + static_cast<size_t>(row0) * e.ld_aux + col);
-        const int64_t pitch = static_cast<int64_t>(e.ld_aux) * 2;
-        const bool ok = col < e.N;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          dst[k] = (ok && k < nrows) ? __ldg(reinterpret_cast<const unsigned int*>(ap)) : 0u;
-          ap += pitch;
-        }
-      };
-      if (e.aux_mode) load_aux(0, ax);  // chunk 0 in flight behind the main loop, like the residual
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -301,9 +287,19 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
         float2 Rn[16];
         if constexpr (EW == 8) {
           if (e.resid && c + 1 < kChunks) load_resid(c + 1, Rn);  // next chunk's residual while this one is processed
+        } else {
+          if (e.resid && c > 0) load_resid(c, R);  // (chunk 0 was requested before the accumulator was ready)
         }
-        // (16-warp variant: chunk c's residual / side input were requested one chunk ahead, right after chunk c-1 had
-        // consumed its own — see below — so their DRAM round trip hides behind that chunk's stores and this TMEM read)
+        uint32_t ax[16];
+        if (e.aux_mode) {
+          const char* ap = reinterpret_cast<const char*>(e.aux + static_cast<size_t>(row0) * e.ld_aux + col);
+          const int64_t pitch = static_cast<int64_t>(e.ld_aux) * 2;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            ax[k] = (colok && k < nrows) ? __ldg(reinterpret_cast<const unsigned int*>(ap)) : 0u;
+            ap += pitch;
+          }
+        }
         tmem_ld_wait();
         if (c == kChunks - 1) {
           // accumulator stage drained: hand it back to the leader's MMA thread before the math and stores
@@ -392,7 +388,6 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
               v[2 * k + 1] *= __uint_as_float(ax[k] & 0xffff0000u);
             }
           }
-          if (e.aux_mode && c + 1 < kChunks) load_aux(c + 1, ax);  // this chunk's side input is consumed: request the next
           if (e.drop_thr) {
             const Drop dr{e.drop_key, e.drop_thr, e.drop_scale};
 #pragma unroll
@@ -406,9 +401,6 @@ ETP_DEVICE void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
           if (e.resid) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) { v[2 * k] += R[k].x; v[2 * k + 1] += R[k].y; }
-            if constexpr (EW != 8) {
-              if (c + 1 < kChunks) load_resid(c + 1, R);  // registers free again: the next chunk's residual flies during the stores
-            }
           }
           if (e.out_f32) {
             float* o = e.out_f32 + static_cast<size_t>(row0) * e.ld_f32 + col;
