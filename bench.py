@@ -667,6 +667,18 @@ def main():
     h2d_before = h2d_alone_gbps()
     e2e_run(3)
     e2e_ms_overlap = timed(lambda: e2e_run(a.steps), 1) / a.steps
+    # one more overlapped pass with a timing event on either side of every copy: how long the copies themselves took under
+    # the step (ms, min / median / max) — a starved copy shows here, a late one does not
+    stager.trace = []
+    ref_ev = torch.cuda.Event(enable_timing=True)
+    ref_ev.record()
+    e2e_run(min(a.steps, 10))
+    torch.cuda.synchronize()
+    dur = sorted(t0.elapsed_time(t1) for t0, t1 in stager.trace)
+    start = [ref_ev.elapsed_time(t0) for t0, _ in stager.trace]
+    copy_trace = {"copy_ms_min_med_max": [round(dur[0], 3), round(dur[len(dur) // 2], 3), round(dur[-1], 3)],
+                  "copy_start_ms": [round(x, 2) for x in start]}
+    stager.trace = None
     e2e_run_serial(2)
     e2e_ms_serial = timed(lambda: e2e_run_serial(a.steps), 1) / a.steps
     e2e_ms = min(e2e_ms_overlap, e2e_ms_serial)
@@ -807,7 +819,7 @@ def main():
                         "policy": "overlapped" if e2e_ms_overlap <= e2e_ms_serial else "serial",
                         "ms_per_step_by_policy": {"overlapped (copy of step t+1 on a side stream under step t)": e2e_ms_overlap,
                                                   "serial (copy on the compute stream at the start of its step)": e2e_ms_serial},
-                        "numa": numa, "h2d_alone_gbps": [round(h2d_before, 2), round(h2d_after, 2)]},
+                        "overlapped_copy_trace": copy_trace, "numa": numa, "h2d_alone_gbps": [round(h2d_before, 2), round(h2d_after, 2)]},
                 "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clk.summary(),
                 "roofline": roof, "cpu_baseline": cpu}
         if soak:

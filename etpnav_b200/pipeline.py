@@ -116,6 +116,7 @@ class HostBatchStager:
         self.ready = [torch.cuda.Event() for _ in range(slots)]
         self.meta = [None] * slots
         self.head = self.tail = self.pending = 0
+        self.trace = None   # set to a list to collect (start, end) timing events of every copy (diagnostics)
 
     def layout(self, host: dict):
         """[(key, offset, nbytes, dtype, shape)] + passthrough dict + total bytes."""
@@ -150,7 +151,13 @@ class HostBatchStager:
         main = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(main)   # the slot's previous reader (enqueued before the last get()) must be done
         with torch.cuda.stream(self.stream):
+            if self.trace is not None:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(self.stream)
             self.dev_blobs[i][:total].copy_(blob[:total], non_blocking=True)
+            if self.trace is not None:
+                t1.record(self.stream)
+                self.trace.append((t0, t1))
             self.ready[i].record(self.stream)
         self.meta[i] = meta
         self.head = (i + 1) % self.nslots
