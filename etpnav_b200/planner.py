@@ -1002,9 +1002,9 @@ class PlannerTrainer:
         with torch.cuda.stream(S2):
             pano, pmask_u8, saved_p, _ = _pano_forward(m, rgb, dep, loc, nt, vl, 1, drop_p)
             w = pmask_u8.unsqueeze(-1).float()
-            wn = w / w.sum(1, keepdim=True)
+            ws = w.sum(1)
             img = img_in.clone()
-            img[:, 1] += (pano * wn).sum(1)
+            img[:, 1] = img[:, 1] + (pano * w).sum(1) / ws      # the very operations of forward_backward(): same bits
             _L._check(L0.etp_event_record(C.c_void_p(self._ev_img), s2_ptr), "etp_event_record")
         img.record_stream(main)
         for t in (rgb, dep, loc, nt, vl):
@@ -1018,7 +1018,7 @@ class PlannerTrainer:
         d_img.record_stream(S2)
         _L._check(L0.etp_stream_wait_event(s2_ptr, C.c_void_p(self._ev_dimg)), "etp_stream_wait_event")
         with torch.cuda.stream(S2):
-            d_pano = wn * d_img[:, 1].unsqueeze(1)                # backward of the masked mean into node 1
+            d_pano = w * (d_img[:, 1] / ws).unsqueeze(1)          # backward of the masked mean into node 1
             _pano_backward_raw(m, rgb, dep, loc, nt, vl, pmask_u8, drop_p, saved_p, d_pano, False, False)
         # the panorama gradients are part of this call's result: the compute stream joins (it has nothing else queued;
         # the bucketed update on the side stream is unaffected)

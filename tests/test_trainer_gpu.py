@@ -135,11 +135,13 @@ def test_overlapped_trainer_step_equals_the_sequential_one():
         torch.cuda.synchronize()
         outs.append((rec, m._flat[tr.lo:tr.hi].clone()))
     (seq, p_seq), (ovl, p_ovl) = outs
+    assert torch.equal(seq[0][0], ovl[0][0])        # first step: same weights, inputs, masks, kernels -> the same logits, bit for bit
+    assert ((seq[0][1] - ovl[0][1]).norm() / seq[0][1].norm()).item() < 1e-4   # gradients up to the order of fp32 atomics
     for (lg_a, g_a, loss_a), (lg_b, g_b, loss_b) in zip(seq, ovl):
         fin = ~torch.isinf(lg_a)
         assert torch.equal(torch.isinf(lg_a), torch.isinf(lg_b))
-        assert (lg_a[fin] - lg_b[fin]).abs().max().item() < 5e-3
-        assert abs(loss_a.item() - loss_b.item()) < 1e-3
+        assert (lg_a[fin] - lg_b[fin]).abs().max().item() < 2e-2      # later steps: bf16 rounding flips after tiny parameter differences
+        assert abs(loss_a.item() - loss_b.item()) < 5e-3
         assert ((g_a - g_b).norm() / g_a.norm()).item() < 5e-2
     # (AdamW's first steps move every element by ~lr whatever the gradient's size: elements whose tiny gradients differ in
     # the last bits may move apart by 2 lr; the parameters as a whole stay together)
