@@ -700,7 +700,8 @@ def _nav_forward_hp(m, txt, img, aux):
     return embeds, logits
 
 
-def _nav_backward_raw(m, txt, img, aux, drop, saved, de, dl, want_dtxt, want_dimg, img_grad_event=None, side_sm_reserve=0):
+def _nav_backward_raw(m, txt, img, aux, drop, saved, de, dl, want_dtxt, want_dimg, img_grad_event=None, side_sm_reserve=0,
+                      d_img_out=None):
     """etp_backward_navigation on the current stream; parameter gradients go to m._grad_target('nav').
     Returns (d_txt, d_img, gbuf, gstart, per_call)."""
     L = _L.lib()
@@ -714,7 +715,7 @@ def _nav_backward_raw(m, txt, img, aux, drop, saved, de, dl, want_dtxt, want_dim
         ni.img_grad_event = C.c_void_p(img_grad_event)
     ni.side_sm_reserve = side_sm_reserve
     d_txt = torch.empty(txt.shape, dtype=torch.float32, device=txt.device) if want_dtxt else None
-    d_img = torch.empty_like(img) if want_dimg else None
+    d_img = (d_img_out if d_img_out is not None else torch.empty_like(img)) if want_dimg else None
     wbytes = L.etp_nav_bwd_work_bytes(B, N, Lt, m.config.num_x_layers)
     work = torch.empty(wbytes, dtype=torch.uint8, device=img.device)
     _L._check(L.etp_backward_navigation(C.byref(m._structs["nav"]), C.byref(gst["nav"]), C.byref(ni), _L.ptr(de),
@@ -871,6 +872,7 @@ class PlannerTrainer:
         self.overlap = bool(overlap) and _os0.environ.get("ETP_OVERLAP", "1") != "0"
         self.pano_sms = int(_os0.environ.get("ETP_PANO_SMS", pano_sms))
         self.pano_stream, self._ev_img, self._ev_dimg = None, None, None
+        self._bufs, self._seen_inputs = {}, set()
         dev = model._flat.device
         if world_size > 1:
             # DDP broadcasts rank 0's parameters when it wraps the module (ss_trainer_ETP.py:211-212): replicas built from
@@ -924,7 +926,7 @@ class PlannerTrainer:
             # slots the persistent GEMM CTA pairs need (ETP_ADAMW_CTAS overrides: 16 = the stand-alone roofline grid)
             import os as _os
             L0.etp_set_adamw_ctas_per_sm.argtypes = [i32]
-            L0.etp_set_adamw_ctas_per_sm(int(_os.environ.get("ETP_ADAMW_CTAS", "2")))
+            L0.etp_set_adamw_ctas_per_sm(int(_os.environ.get("ETP_ADAMW_CTAS", "4")))
             if world_size > 1:
                 L0.etp_set_sm_reserve.argtypes = [i32]
                 L0.etp_set_sm_reserve(self.comm_sms)
@@ -979,6 +981,13 @@ class PlannerTrainer:
         logits.backward(dlogits)
         return logits, loss_sum / logits.shape[0]
 
+    def _persistent(self, name, like):
+        buf = self._bufs.get(name)
+        if buf is None or buf.shape != like.shape or buf.device != like.device:
+            buf = torch.empty(like.shape, dtype=torch.float32, device=like.device)
+            self._bufs[name] = buf
+        return buf
+
     def _forward_backward_overlapped(self, d):
         """The same step with the panorama branch on its OWN stream.  Its 768 view rows keep ~130 SMs idle whatever the
         kernel; the only node-independent GEMMs of the navigation call are the instruction's all-layer K|V projection
@@ -1003,19 +1012,24 @@ class PlannerTrainer:
             pano, pmask_u8, saved_p, _ = _pano_forward(m, rgb, dep, loc, nt, vl, 1, drop_p)
             w = pmask_u8.unsqueeze(-1).float()
             ws = w.sum(1)
-            img = img_in.clone()
+            # the two tensors that cross streams live in buffers the trainer keeps (ordering by the events below and the
+            # stream joins at the step boundaries): a per-step allocation would need record_stream(), whose deferred
+            # reuse makes the caching allocator grow by one block per step the host runs ahead
+            img = self._persistent("img", img_in)
+            img.copy_(img_in)
             img[:, 1] = img[:, 1] + (pano * w).sum(1) / ws      # the very operations of forward_backward(): same bits
             _L._check(L0.etp_event_record(C.c_void_p(self._ev_img), s2_ptr), "etp_event_record")
-        img.record_stream(main)
         for t in (rgb, dep, loc, nt, vl):
-            t.record_stream(S2)
+            if t.data_ptr() not in self._seen_inputs:   # caller-owned inputs: tell the allocator once that S2 reads them
+                t.record_stream(S2)
+                self._seen_inputs.add(t.data_ptr())
         ni_extra = dict(img_ready_event=self._ev_img, side_sm_reserve=self.pano_sms)
         embeds, logits, saved_n, _ = _nav_forward(m, txt, img, aux, 1, drop_n, **ni_extra)
         loss_sum, dlogits, self.last_action, _ = _L.step_loss(logits, d["labels"], grad_scale=1.0 / logits.shape[0])
         # ---- backward: navigation on the compute stream; panorama on S2 from the moment d_gmap_img_fts is final
         _, d_img, _, _, _ = _nav_backward_raw(m, txt, img, aux, drop_n, saved_n, None, dlogits, False, True,
-                                              img_grad_event=self._ev_dimg, side_sm_reserve=self.pano_sms)
-        d_img.record_stream(S2)
+                                              img_grad_event=self._ev_dimg, side_sm_reserve=self.pano_sms,
+                                              d_img_out=self._persistent("d_img", img))
         _L._check(L0.etp_stream_wait_event(s2_ptr, C.c_void_p(self._ev_dimg)), "etp_stream_wait_event")
         with torch.cuda.stream(S2):
             d_pano = w * (d_img[:, 1] / ws).unsqueeze(1)          # backward of the masked mean into node 1
