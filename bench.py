@@ -145,21 +145,53 @@ def workload_name(a, mode):
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------------
 class Clocks:
+    """SM clock / throttle reasons sampled every 50 ms by a thread WHILE the timed regions run.  NVML is called in-process
+    (pynvml: the library behind nvidia-smi): spawning an nvidia-smi process ten times a second means fork()ing a process
+    that holds gigabytes of pinned and CUDA-mapped memory — each fork stalls the launching thread for tens of
+    milliseconds, which showed up as sporadic 2-3x slow timed regions.  Falls back to the nvidia-smi command line (the
+    recipe of B200_PROFILING.md) when pynvml is not importable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.samples, self.stop, self.th = index, [], False, None
+        self.nvml, self.handle, self.source = None, None, "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:    # the CUDA device's own PCI address (robust to CUDA_VISIBLE_DEVICES re-numbering)
+                p = torch.cuda.get_device_properties(index)
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0")
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        act = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(sm), str(mx), act(n.nvmlClocksEventReasonHwSlowdown), act(n.nvmlClocksEventReasonHwThermalSlowdown),
+                act(n.nvmlClocksEventReasonSwThermalSlowdown), act(n.nvmlClocksEventReasonSwPowerCap)]
 
     def _run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    self.samples.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -176,7 +208,7 @@ class Clocks:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].startswith("Active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
