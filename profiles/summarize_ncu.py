@@ -48,7 +48,8 @@ def main(src, dst, traffic_json=None):
         a["rd"] += d.get("dram__bytes_read.sum", 0.0)
         a["wr"] += d.get("dram__bytes_write.sum", 0.0)
         a["l2"] += d.get("lts__t_bytes.sum", 0.0)
-        a["tp"] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0) * d.get("gpu__time_duration.sum", 0.0)
+        a["tp"] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                         d.get("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", 0.0)) * d.get("gpu__time_duration.sum", 0.0)
         a["tpe"] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * d.get("gpu__time_duration.sum", 0.0)
     tot = sum(a["us"] for a in agg.values()) or 1.0
     with open(dst, "w") as f:
@@ -66,9 +67,11 @@ def main(src, dst, traffic_json=None):
                "mean_dram_bytes_per_launch": sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in g) / n,
                "mean_us_under_ncu": sum(d.get("gpu__time_duration.sum", 0) for d in g) / n,
                "tensor_pipe_active_pct_time_weighted":
-                   sum(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0) * d.get("gpu__time_duration.sum", 0) for d in g)
+                   sum(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                             d.get("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", 0))
+                       * d.get("gpu__time_duration.sum", 0) for d in g)
                    / (sum(d.get("gpu__time_duration.sum", 0) for d in g) or 1),
-               "source": src}
+               "source": src.replace("gpurun_out/step_metrics.csv", "profiles/r02_step_metrics.csv")}
         json.dump(out, open(traffic_json, "w"), indent=1)
     print(open(dst).read())
 
