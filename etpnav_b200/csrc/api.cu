@@ -23,7 +23,20 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 #define ETP_API __attribute__((visibility("default")))
 extern "C" {
 
-ETP_API int etp_version(void) { return 100; }
+ETP_API int etp_version(void) { return 200; }
+/* sizeof() of the public structs, in the order: gemm_args, attn_args, attn_bwd_args, pano_pack_args, node_pack_args,
+ * dropout, layer_weights, nav_weights, nav_inputs, pano_layer_weights, pano_weights, pano_inputs, txt_weights — lets a
+ * binding check its own struct mirrors (tests/test_host_cpu.py does it for the ctypes ones). */
+ETP_API int etp_struct_sizes(int32_t* out, int32_t n) {
+  const int32_t v[] = {(int32_t)sizeof(etp_gemm_args), (int32_t)sizeof(etp_attn_args), (int32_t)sizeof(etp_attn_bwd_args),
+                       (int32_t)sizeof(etp_pano_pack_args), (int32_t)sizeof(etp_node_pack_args), (int32_t)sizeof(etp_dropout),
+                       (int32_t)sizeof(etp_layer_weights), (int32_t)sizeof(etp_nav_weights), (int32_t)sizeof(etp_nav_inputs),
+                       (int32_t)sizeof(etp_pano_layer_weights), (int32_t)sizeof(etp_pano_weights), (int32_t)sizeof(etp_pano_inputs),
+                       (int32_t)sizeof(etp_txt_weights)};
+  const int32_t m = static_cast<int32_t>(sizeof(v) / sizeof(v[0]));
+  for (int32_t i = 0; i < n && i < m; ++i) out[i] = v[i];
+  return m;
+}
 ETP_API const char* etp_last_error(void) { return last_error_cstr(); }
 
 ETP_API long long etp_launch_count(void) { return g_launches.load(); }

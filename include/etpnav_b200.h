@@ -42,6 +42,10 @@ extern "C" {
  * library
  * ------------------------------------------------------------------------------------------- */
 int etp_version(void);                /* 100 * major + minor */
+/* sizeof() of the public structs of this header (gemm_args, attn_args, attn_bwd_args, pano_pack_args, node_pack_args,
+ * dropout, layer_weights, nav_weights, nav_inputs, pano_layer_weights, pano_weights, pano_inputs, txt_weights): returns how
+ * many there are and fills out[0..n); a binding compares them with its own struct mirrors. */
+int etp_struct_sizes(int32_t* out, int32_t n);
 const char* etp_last_error(void);     /* text of the last error on this thread */
 /* 0 if the current CUDA device is sm_100 (B200); ETP_ERR_NO_DEVICE otherwise. */
 int etp_check_device(void);

@@ -198,3 +198,20 @@ def test_pretraining_state_dict_survives_wrapping():
     assert at("lang_encoder.layer.0.attention.self.query.weight") == 3
     assert at("lang_encoder.layer.0.attention.self.query.bias") == 1
     assert at("lang_encoder.layer.0.attention.output.LayerNorm.weight") == 1
+
+
+def test_ctypes_struct_mirrors_match_the_header():
+    """The ctypes mirrors in etpnav_b200/lib.py and planner.py have the sizes the compiled header has (a field added on
+    one side only would shift every later pointer)."""
+    import ctypes as C
+    from etpnav_b200 import lib as L
+    from etpnav_b200 import planner as P
+    lib = C.CDLL(L.LIB_PATH)
+    lib.etp_struct_sizes.argtypes = [C.POINTER(C.c_int32), C.c_int32]
+    out = (C.c_int32 * 16)()
+    n = lib.etp_struct_sizes(out, 16)
+    mirrors = [L.GemmArgs, L.AttnArgs, L.AttnBwdArgs, L.PanoPackArgs, L.NodePackArgs, P.Dropout, P.LayerWeights, P.NavWeights,
+               P.NavInputs, P.PanoLayerWeights, P.PanoWeights, P.PanoInputs, P.TxtWeights]
+    assert n == len(mirrors)
+    for i, m in enumerate(mirrors):
+        assert C.sizeof(m) == out[i], (m.__name__, C.sizeof(m), out[i])
