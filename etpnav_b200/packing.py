@@ -201,3 +201,274 @@ def pack_vp_features(obs, device="cuda"):
                 dep_fts=gather(obs["cand_depth"], obs["pano_depth"], False),
                 loc_fts=gather(obs["cand_angle_fts"], obs["pano_angle_fts"], True),
                 nav_types=torch.from_numpy(nav).to(device), view_lens=torch.tensor(lens, dtype=torch.long, device=device))
+
+
+class _EnvMirror:
+    """Array-backed mirror of ONE GraphMap (models/graph_utils.py:133), brought up to date by ``sync``.
+
+    What ``GraphMap.update_graph`` (:185-250) can change between two packs, and what is re-read for it:
+      * one node is appended (ids are never reused, positions / step ids of older nodes never change): the new row of
+        ``node_pos`` / ``node_stepId`` / ``node_embeds`` only;
+      * ``shortest_dist`` / ``shortest_path`` are rebuilt as NEW dictionaries (so an unchanged object = no update since
+        the last pack = nothing to read).  If the new node has degree 1 in ``graph_nx`` no path between two older nodes
+        can run through it, so only its row and column are read; a loop closure (degree > 1) re-reads the n x n tables;
+      * ghosts are created, gain a front (``ghost_fronts`` / ``ghost_embeds`` / ``ghost_pos`` grow together) or are
+        deleted (``delete_ghost`` :178-183): detected from the id list and the per-ghost front counts, both compared at C
+        speed; only the ghosts whose count moved have their embedding pointer / weight refreshed;
+      * ``ghost_aug_pos`` is redrawn for every ghost inside ``update_graph`` (:238-244): re-read after an update."""
+    __slots__ = ("gm", "sd_obj", "nid", "ix", "n", "cap", "npos", "steps", "sd", "spl", "gids", "flens", "fcum", "fidx",
+                 "gpos", "nptr", "nkeep", "gl", "gp", "gw", "gkeep", "gptr", "gwt", "img_ok", "img_gids", "img_lens", "vp_ids")
+
+    def __init__(self, gm, cap=16):
+        self.gm, self.sd_obj, self.nid, self.ix, self.n = gm, None, [], {}, 0
+        self._alloc(cap)
+        self.gids, self.flens = None, None
+        self.fcum = self.fidx = np.zeros(0, dtype=np.int32)
+        self.gpos = np.zeros((0, 3), dtype=np.float64)
+        self.nptr, self.nkeep, self.gl, self.gp, self.gw, self.gkeep, self.gptr, self.gwt = [], [], {}, {}, {}, {}, [], []
+        self.img_ok, self.img_gids, self.img_lens, self.vp_ids = True, None, None, None
+
+    def _alloc(self, cap):
+        old = (self.npos, self.steps, self.sd, self.spl) if self.n else None
+        self.cap = cap
+        self.npos = np.zeros((cap, 3), dtype=np.float64)
+        self.steps = np.zeros(cap + 1, dtype=np.int32)          # [n] stays 0: front_ptr[0] of the i32 layout
+        self.sd = np.zeros((cap, cap), dtype=np.float64)
+        self.spl = np.zeros((cap, cap), dtype=np.int32)
+        if old is not None:
+            n = self.n
+            self.npos[:n], self.steps[:n], self.sd[:n, :n], self.spl[:n, :n] = old[0][:n], old[1][:n], old[2][:n, :n], old[3][:n, :n]
+
+    def sync(self, gm, want_img, width, device):
+        sd = gm.shortest_dist
+        updated = sd is not self.sd_obj
+        if updated:
+            nid = list(gm.node_pos)
+            n0, n = self.n, len(nid)
+            if n0 and nid[:n0] != self.nid:     # not the append-only history update_graph produces: start over
+                self.__init__(gm, self.cap)
+                n0 = 0
+            if n > self.cap:
+                self._alloc(max(n, 2 * self.cap))
+            npos, nstep, ix = gm.node_pos, gm.node_stepId, self.ix
+            for k in range(n0, n):
+                v = nid[k]
+                ix[v] = k
+                self.npos[k] = npos[v]
+                self.steps[k] = nstep[v]
+            self.steps[n] = 0
+            sp = gm.shortest_path
+            G = getattr(gm, "graph_nx", None)
+            if n0 and n == n0 + 1 and G is not None and len(G[nid[n0]]) == 1:
+                v, old = nid[n0], self.nid
+                row = itemgetter(*nid)
+                self.sd[n0, :n] = row(sd[v])
+                self.sd[:n0, n0] = [sd[a][v] for a in old]
+                self.spl[n0, :n] = list(map(len, row(sp[v])))
+                self.spl[:n0, n0] = [len(sp[a][v]) for a in old]
+            else:
+                row = itemgetter(*nid) if n > 1 else (lambda d, k=nid[0]: (d[k],))
+                self.sd[:n, :n] = [row(sd[a]) for a in nid]
+                self.spl[:n, :n] = [list(map(len, row(sp[a]))) for a in nid]
+            self.nid, self.n, self.sd_obj = nid, n, sd
+        n = self.n
+        gids = list(gm.ghost_pos)
+        g = len(gids)
+        if g:
+            fronts = itemgetter(*gids)(gm.ghost_fronts) if g > 1 else (gm.ghost_fronts[gids[0]],)
+            lens = list(map(len, fronts))
+        else:
+            fronts, lens = (), []
+        same_ids = gids == self.gids
+        ghosts_changed = not same_ids or lens != self.flens
+        if ghosts_changed:
+            self.fcum = np.fromiter(accumulate(lens), dtype=np.int32, count=g)
+            self.fidx = np.fromiter(map(self.ix.__getitem__, chain.from_iterable(fronts)), dtype=np.int32)
+        if updated or not same_ids:
+            self.gpos = np.array(itemgetter(*gids)(gm.ghost_aug_pos) if g > 1 else
+                                 [gm.ghost_aug_pos[v] for v in gids], dtype=np.float64).reshape(g, 3)
+        if updated or not same_ids or self.vp_ids is None:
+            self.vp_ids = [None] + self.nid + gids
+        if want_img and self.img_ok:
+            grad = torch.is_grad_enabled()
+
+            def usable(t):
+                return (t.device == device and t.dtype == torch.float32 and t.dim() == 1 and t.shape[0] == width
+                        and t.is_contiguous() and not (grad and t.requires_grad))
+            ne = gm.node_embeds
+            for k in range(len(self.nptr), n):
+                t = ne[self.nid[k]]
+                if not usable(t):
+                    self.img_ok = False
+                    break
+                self.nptr.append(t.data_ptr())
+                self.nkeep.append(t)
+            if self.img_ok and (gids != self.img_gids or lens != self.img_lens):
+                ge, gl, gp, gw, keep = gm.ghost_embeds, self.gl, self.gp, self.gw, self.gkeep
+                for v, l in zip(gids, lens):
+                    if gl.get(v) != l:
+                        t, c = ge[v]
+                        if not usable(t):
+                            self.img_ok = False
+                            break
+                        gp[v], gw[v], gl[v], keep[v] = t.data_ptr(), 1.0 / c, l, t
+                if self.img_ok:
+                    self.gptr = list(map(gp.__getitem__, gids)) if g else []
+                    self.gwt = list(map(gw.__getitem__, gids)) if g else []
+                    self.img_gids, self.img_lens = gids, lens
+        self.gids, self.flens = gids, lens
+        return g
+
+
+class GmapPacker:
+    """``pack_gmap`` with memory: drop-in for ``ETPTrainer._nav_gmap_variable`` (ss_trainer_ETP.py:344-417) that keeps an
+    array-backed mirror of every environment's GraphMap between calls (``_EnvMirror``), so a step re-reads only what
+    ``update_graph`` / ``delete_ghost`` changed instead of walking every dictionary of every map again.  Same outputs,
+    bit for bit, as the stateless ``pack_gmap`` (tests/test_packing_incremental_cpu.py, tests/test_packing_gpu.py).
+
+    Per call: the mirrors are synced, the blobs ``etp_gmap_pack`` documents are concatenated straight into ONE pinned
+    staging buffer (two buffers alternate, so the host never waits for the previous copy), one H2D copy moves it, and two
+    launches (``etp_gmap_pack``, ``etp_segment_gather_rows`` over the cached row-pointer table) write the six tensors.
+    Mirrors follow the GraphMap OBJECTS (environments finish and drop out of the batch; a new episode builds new maps)."""
+
+    def __init__(self, device="cuda", width=768):
+        self.device, self.width = torch.device(device), width
+        self._mirrors = {}
+        self._pin, self._pin_np, self._pin_ev, self._turn = [None, None], [None, None], [None, None], 0
+
+    def reset(self):
+        self._mirrors = {}
+
+    # ---- host side -------------------------------------------------------------------------------------------------
+    def _sync(self, gmaps, want_img):
+        old, new, sts = self._mirrors, {}, []
+        for gm in gmaps:
+            st = old.get(id(gm))
+            if st is None or st.gm is not gm:
+                st = _EnvMirror(gm)
+            st.sync(gm, want_img, self.width, self.device)
+            new[id(gm)] = st
+            sts.append(st)
+        self._mirrors = new            # maps that left the batch are forgotten (and their kept tensors released)
+        return sts
+
+    @staticmethod
+    def _layout(sts, cur_vp):
+        B = len(sts)
+        ns = np.fromiter((st.n for st in sts), dtype=np.int64, count=B)
+        gs = np.fromiter((len(st.gids) for st in sts), dtype=np.int64, count=B)
+        nnz = np.fromiter((len(st.fidx) for st in sts), dtype=np.int64, count=B)
+        f_len = 4 + 3 * ns + 3 * gs + ns * ns
+        i_len = ns + 1 + gs + nnz + ns * ns
+        meta = np.zeros((B, 8), dtype=np.int32)
+        meta[:, 0], meta[:, 1], meta[:, 5] = ns, gs, nnz
+        meta[:, 2] = [st.ix[v] for st, v in zip(sts, cur_vp)]
+        meta[1:, 3], meta[1:, 4] = np.cumsum(f_len)[:-1], np.cumsum(i_len)[:-1]
+        return meta, int(f_len.sum()), int(i_len.sum()), int(max(1, (1 + ns + gs).max())), int(gs.max())
+
+    @staticmethod
+    def _fill(sts, meta, fout, iout, cur_pos, cur_ori):
+        """Write every environment's slice of the two blobs (layout: include/etpnav_b200.h, etp_gmap_pack) in place."""
+        offs_f, offs_i = meta[:, 3].tolist(), meta[:, 4].tolist()
+        for e, st in enumerate(sts):
+            n, g, cp = st.n, len(st.gids), cur_pos[e]
+            a = offs_f[e]
+            fout[a:a + 4] = (float(cp[0]), float(cp[1]), float(cp[2]), heading_from_quaternion(cur_ori[e]))
+            a += 4
+            fout[a:a + 3 * n] = st.npos[:n].reshape(-1)
+            a += 3 * n
+            if g:
+                fout[a:a + 3 * g] = st.gpos.reshape(-1)
+                a += 3 * g
+            fout[a:a + n * n].reshape(n, n)[...] = st.sd[:n, :n]
+            a = offs_i[e]
+            iout[a:a + n + 1] = st.steps[:n + 1]
+            a += n + 1
+            if g:
+                k = len(st.fidx)
+                iout[a:a + g] = st.fcum
+                iout[a + g:a + g + k] = st.fidx
+                a += g + k
+            iout[a:a + n * n].reshape(n, n)[...] = st.spl[:n, :n]
+
+    def flatten(self, gmaps, cur_vp, cur_pos, cur_ori):
+        """Host half only: the tuple ``flatten_gmaps`` returns (used by the CPU tests to compare the two)."""
+        sts = self._sync(gmaps, False)
+        meta, nf, ni, n_max, max_g = self._layout(sts, cur_vp)
+        fout, iout = np.empty(nf, dtype=np.float64), np.empty(ni, dtype=np.int32)
+        self._fill(sts, meta, fout, iout, cur_pos, cur_ori)
+        return meta, fout, iout, [list(st.vp_ids) for st in sts], n_max, max_g
+
+    def img_tables(self, sts, n_max):
+        """Row-pointer table + CSR (``etp_segment_gather_rows``) of ``gmap_img_fts``: [stop] (empty segment), one row per
+        node (weight 1) and ghost (weight 1 / count, ``get_node_embeds`` graph_utils.py:272-276), empty padding."""
+        B = len(sts)
+        k = np.fromiter((len(st.nptr) + len(st.gptr) for st in sts), dtype=np.int64, count=B)
+        base = np.concatenate([[0], np.cumsum(k)])
+        total = int(base[-1])
+        table = np.fromiter(chain.from_iterable(chain(st.nptr, st.gptr) for st in sts), dtype=np.int64, count=total)
+        wt = np.ones(total, dtype=np.float32)
+        for e, st in enumerate(sts):
+            if st.gwt:
+                wt[base[e] + len(st.nptr):base[e + 1]] = st.gwt
+        j = np.arange(n_max, dtype=np.int64)[None, :] - 1
+        ptr = np.empty(B * n_max + 1, dtype=np.int32)
+        ptr[:-1] = (base[:-1, None] + np.clip(j, 0, k[:, None])).ravel()
+        ptr[-1] = total
+        return table, ptr, np.arange(total, dtype=np.int32), wt
+
+    # ---- device side -----------------------------------------------------------------------------------------------
+    def _staging(self, nbytes):
+        t = self._turn = self._turn ^ 1
+        if self._pin[t] is None or self._pin[t].numel() < nbytes:
+            self._pin[t] = torch.empty(max(nbytes * 2, 1 << 20), dtype=torch.uint8).pin_memory()
+            self._pin_np[t] = self._pin[t].numpy()
+            self._pin_ev[t] = torch.cuda.Event()
+        else:
+            self._pin_ev[t].synchronize()      # the copy issued two packs ago has long finished
+        return self._pin[t], self._pin_np[t], self._pin_ev[t]
+
+    def pack(self, gmaps, cur_vp, cur_pos, cur_ori):
+        _L.require_device()
+        _declare()
+        dev, B, W = self.device, len(gmaps), self.width
+        sts = self._sync(gmaps, True)
+        meta, nf, ni, n_max, max_g = self._layout(sts, cur_vp)
+        img_fast = all(st.img_ok for st in sts)
+        if img_fast:
+            table, ptr, idx, wt = self.img_tables(sts, n_max)
+        else:
+            table, ptr, idx, wt = (np.zeros(0, dtype=t) for t in (np.int64, np.int32, np.int32, np.float32))
+        # one blob: 8-byte sections first
+        sizes = [nf * 8, table.nbytes, meta.nbytes, ni * 4, ptr.nbytes, idx.nbytes, wt.nbytes]
+        offs = [0]
+        for s in sizes:
+            offs.append((offs[-1] + s + 15) // 16 * 16)
+        pin, pnp, ev = self._staging(offs[-1])
+        self._fill(sts, meta, pnp[offs[0]:offs[0] + nf * 8].view(np.float64), pnp[offs[3]:offs[3] + ni * 4].view(np.int32),
+                   cur_pos, cur_ori)
+        for o, a in ((offs[1], table), (offs[2], meta), (offs[4], ptr), (offs[5], idx), (offs[6], wt)):
+            pnp[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+        blob = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
+        blob.copy_(pin[:offs[-1]], non_blocking=True)
+        ev.record()
+        base = blob.data_ptr()
+        P = lambda k: C.c_void_p(base + offs[k])
+        step_ids = torch.empty(B, n_max, dtype=torch.int64, device=dev)
+        visited = torch.empty(B, n_max, dtype=torch.uint8, device=dev)
+        masks = torch.empty(B, n_max, dtype=torch.uint8, device=dev)
+        pos = torch.empty(B, n_max, 7, dtype=torch.float32, device=dev)
+        pd = torch.empty(B, n_max, n_max, dtype=torch.float32, device=dev)
+        lib, sp = _L.lib(), _L.stream_ptr()
+        _L._check(lib.etp_gmap_pack(P(2), P(0), P(3), B, n_max, max_g, _L.ptr(step_ids), _L.ptr(visited), _L.ptr(masks),
+                                    _L.ptr(pos), _L.ptr(pd), sp), "etp_gmap_pack")
+        if img_fast:
+            img = torch.empty(B, n_max, W, dtype=torch.float32, device=dev)
+            _L._check(lib.etp_segment_gather_rows(P(1), P(4), P(5), P(6), B * n_max, W, _L.ptr(img), sp),
+                      "etp_segment_gather_rows")
+        else:   # some embedding needs a gradient (training) or lives elsewhere: the differentiable gather of pack_gmap
+            img = pack_gmap_img_fts(gmaps, n_max, dev)
+        self._last_blob = blob     # stays referenced until the next pack: the launches above read it asynchronously
+        return dict(gmap_step_ids=step_ids, gmap_visited_masks=visited.view(torch.bool), gmap_masks=masks.view(torch.bool),
+                    gmap_pos_fts=pos, gmap_pair_dists=pd, gmap_vp_ids=[list(st.vp_ids) for st in sts], gmap_img_fts=img,
+                    no_vp_left=[not st.gids for st in sts])

@@ -90,3 +90,61 @@ def test_pack_gmap_large_random_maps_properties():
         want = PK.get_pos_fts(ms, ms.node_ids.index(cur_vp[e]), cur_pos[e], cur_ori[e])
         got = out["gmap_pos_fts"][e, :L].cpu().numpy()
         assert np.array_equal(got[:, 4:], want[:, 4:]) and np.abs(got[:, :4] - want[:, :4]).max() <= 2.4e-7
+
+
+@pytest.mark.parametrize("name", gmap_names())
+def test_stateful_packer_matches_reference_fixtures(name):
+    """GmapPacker (incremental mirror, one H2D, two launches) on the reference's fixtures: same gate as pack_gmap."""
+    from etpnav_b200 import packing
+    gold = load(name)
+    gms, cur_vp, cur_pos, cur_ori = fake_gmaps(gold)
+    for gm in gms:
+        gm.node_embeds = {k: v.cuda() for k, v in gm.node_embeds.items()}
+        gm.ghost_embeds = {k: [v[0].cuda(), v[1]] for k, v in gm.ghost_embeds.items()}
+    pk = packing.GmapPacker("cuda")
+    ref = gold["out"]
+    for _ in range(2):            # second call: nothing changed, everything comes from the mirror
+        out = pk.pack(gms, cur_vp, cur_pos, cur_ori)
+        torch.cuda.synchronize()
+        assert out["gmap_vp_ids"] == ref["gmap_vp_ids"] and out["no_vp_left"] == ref["no_vp_left"]
+        for k in ("gmap_step_ids", "gmap_masks", "gmap_visited_masks", "gmap_pair_dists"):
+            assert out[k].dtype == ref[k].dtype and torch.equal(out[k].cpu(), ref[k]), k
+        pos, rp = out["gmap_pos_fts"].cpu(), ref["gmap_pos_fts"]
+        assert torch.equal(pos[..., 4:], rp[..., 4:])
+        assert (pos[..., :4] - rp[..., :4]).abs().max().item() <= 2.4e-7
+        torch.testing.assert_close(out["gmap_img_fts"].cpu(), ref["gmap_img_fts"], rtol=1e-6, atol=1e-6)
+
+
+def test_stateful_packer_follows_evolving_maps_bit_for_bit():
+    """Evolving maps (tests/gmap_sim.py): at every step the stateful packer's six tensors equal the stateless
+    pack_gmap's; an embedding that needs a gradient sends the image features through the differentiable gather."""
+    from etpnav_b200 import packing
+    from tests.gmap_sim import SimGraphMap
+    rng = np.random.default_rng(3)
+    gms = [SimGraphMap(40 + e, device="cuda").step() for e in range(8)]
+    pk = packing.GmapPacker("cuda")
+    keys = ("gmap_step_ids", "gmap_visited_masks", "gmap_masks", "gmap_pos_fts", "gmap_pair_dists", "gmap_img_fts")
+    for t in range(14):
+        cur_vp, cur_pos, cur_ori = (list(x) for x in zip(*[gm.pose() for gm in gms]))
+        with torch.no_grad():
+            out = pk.pack(gms, cur_vp, cur_pos, cur_ori)
+            ref = packing.pack_gmap(gms, cur_vp, cur_pos, cur_ori, "cuda")
+        for k in keys:
+            assert torch.equal(out[k], ref[k]), (t, k)
+        assert out["gmap_vp_ids"] == ref["gmap_vp_ids"] and out["no_vp_left"] == ref["no_vp_left"]
+        for gm in gms:
+            if rng.random() < 0.8:
+                gm.step()
+        if t == 6:
+            gms.pop(3)
+        if t == 9:
+            gms[0] = SimGraphMap(777, device="cuda").step()
+    gm = gms[1]
+    v = next(iter(gm.node_embeds))
+    gm.step()
+    new = list(gm.node_embeds)[-1]
+    gm.node_embeds[new] = gm.node_embeds[new].clone().requires_grad_(True)
+    cur_vp, cur_pos, cur_ori = (list(x) for x in zip(*[g.pose() for g in gms]))
+    out = pk.pack(gms, cur_vp, cur_pos, cur_ori)
+    out["gmap_img_fts"].sum().backward()
+    assert torch.equal(gm.node_embeds[new].grad.cpu(), torch.ones(768))

@@ -1,0 +1,86 @@
+"""CPU: the stateful packer (etpnav_b200/packing.py: GmapPacker, the array-backed mirror of GraphMap that is updated
+incrementally) must hand ``etp_gmap_pack`` / ``etp_segment_gather_rows`` exactly what the stateless flatten does — which
+tests/test_packing_host_cpu.py pins to the reference's fixtures — at every step of evolving maps: node appends, loop
+closures (full table re-read), leaf appends (row / column only), ghost creation / merge / deletion, idle environments,
+environments that leave the batch and new episodes."""
+import numpy as np
+import pytest
+import torch
+
+from etpnav_b200 import packing
+from tests.gmap_sim import SimGraphMap
+from tests.test_packing_cpu import cpu_gmap_names, load
+from tests.test_packing_host_cpu import fake_gmaps
+
+
+def expected_img_tables(gms, n_max):
+    table, wt, ptr = [], [], [0]
+    for gm in gms:
+        k = 1
+        ptr.append(len(table))
+        for v in gm.node_pos:
+            table.append(gm.node_embeds[v].data_ptr()); wt.append(1.0); ptr.append(len(table)); k += 1
+        for v in gm.ghost_pos:
+            table.append(gm.ghost_embeds[v][0].data_ptr()); wt.append(1.0 / gm.ghost_embeds[v][1]); ptr.append(len(table)); k += 1
+        ptr.extend([len(table)] * (n_max - k))
+    return (np.asarray(table, dtype=np.int64), np.asarray(ptr, dtype=np.int32), np.arange(len(table), dtype=np.int32),
+            np.asarray(wt, dtype=np.float32))
+
+
+def check_same(pk, gms, poses):
+    cur_vp, cur_pos, cur_ori = (list(x) for x in zip(*poses))
+    ref = packing.flatten_gmaps(gms, cur_vp, cur_pos, cur_ori)
+    got = pk.flatten(gms, cur_vp, cur_pos, cur_ori)
+    assert np.array_equal(got[0], ref[0])
+    assert got[1].dtype == ref[1].dtype and np.array_equal(got[1], ref[1])
+    assert got[2].dtype == ref[2].dtype and np.array_equal(got[2], ref[2])
+    assert got[3] == ref[3] and got[4:] == ref[4:]
+    sts = pk._sync(gms, True)
+    assert all(st.img_ok for st in sts)
+    for a, b in zip(pk.img_tables(sts, ref[4]), expected_img_tables(gms, ref[4])):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("ghost_aug", [0.0, 0.1])
+def test_incremental_mirror_follows_evolving_maps(ghost_aug):
+    rng = np.random.default_rng(7)
+    gms = [SimGraphMap(100 + e, ghost_aug=ghost_aug, width=8).step() for e in range(6)]
+    pk = packing.GmapPacker(device="cpu", width=8)
+    closures = leaves = 0
+    for t in range(22):
+        check_same(pk, gms, [gm.pose() for gm in gms])
+        for gm in gms:
+            if rng.random() < 0.75:          # the others idle this step (finished-but-kept environments)
+                gm.step()
+                deg = len(gm.graph_nx[gm.cur_vp])
+                closures += deg > 1
+                leaves += deg == 1
+        if t == 8:
+            gms.pop(2)                        # an environment finishes and leaves the batch
+        if t == 12:
+            gms[1] = SimGraphMap(999, ghost_aug=ghost_aug, width=8).step()   # a new episode in the same slot
+        if t == 15:
+            gms[0].delete_ghost(next(iter(gms[0].ghost_pos)))                # deletion without an update
+    check_same(pk, gms, [gm.pose() for gm in gms])
+    assert closures >= 5 and leaves >= 20          # both table paths were exercised
+
+
+@pytest.mark.parametrize("name", cpu_gmap_names())
+def test_packer_first_call_equals_flatten_on_reference_fixtures(name):
+    gms, cur_vp, cur_pos, cur_ori = fake_gmaps(load(name))
+    ref = packing.flatten_gmaps(gms, cur_vp, cur_pos, cur_ori)
+    got = packing.GmapPacker(device="cpu").flatten(gms, cur_vp, cur_pos, cur_ori)
+    for a, b in zip(got[:3], ref[:3]):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    assert got[3:] == ref[3:]
+
+
+def test_packer_falls_back_when_an_embedding_needs_a_gradient():
+    gm = SimGraphMap(5, width=8).step().step()
+    v = next(iter(gm.node_embeds))
+    gm.node_embeds[v] = gm.node_embeds[v].clone().requires_grad_(True)
+    pk = packing.GmapPacker(device="cpu", width=8)
+    sts = pk._sync([gm], True)
+    assert not sts[0].img_ok                         # pack() then takes the differentiable gather of pack_gmap
+    with torch.no_grad():
+        assert packing.GmapPacker(device="cpu", width=8)._sync([gm], True)[0].img_ok
