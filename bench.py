@@ -77,8 +77,10 @@ def parse():
     ap.add_argument("--text-kv", action="store_true",
                     help="fwd mode: the instruction's key|value projections are computed once per episode "
                          "(B200Planner.encode_text_kv, outside the timed step) and reused by every step, as in an eval rollout")
-    ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"],
-                    help="N > 1: dtype of the gradient buckets on the wire (fp32 = DDP default; bf16 = compressed all-reduce)")
+    ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16", "peer"],
+                    help="N > 1: fp32 = NCCL all-reduce of the gradient buckets (DDP default) | bf16 = the same in bf16 | "
+                         "peer = reduce-scatter + AdamW + parameter all-gather fused in one kernel over NVLink peer memory")
+    ap.add_argument("--peer-ctas", type=int, default=0, help="N > 1, --grad-comm peer: grid of the fused update kernel (default 64)")
     ap.add_argument("--comm-sms", type=int, default=0,
                     help="N > 1: SMs the persistent grids leave to the collective (etp_set_sm_reserve)")
     ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: NCCL_MAX_CTAS for this run (0 = NCCL's default)")
@@ -607,6 +609,8 @@ def main():
 
     if mode == "train":
         model.train()
+        if a.peer_ctas > 0:
+            os.environ["ETP_PEER_CTAS"] = str(a.peer_ctas)
         trainer = model.make_trainer(lr=1e-5, world_size=world, grad_comm=a.grad_comm, comm_sms=a.comm_sms)
 
         def step(d):
@@ -816,20 +820,26 @@ def main():
             m2.train()
             m2.set_dropout_seed(777)
             t2 = m2.make_trainer(lr=1e-5, world_size=w_, grad_comm=a.grad_comm, comm_sms=a.comm_sms)
+            if getattr(t2, "_peer", None) is not None:
+                t2._peer_write_reduced = 1     # the owner leaves the summed gradient in its own buffer: that is what is checked
             m2.set_dropout_seed(777)
             t2.step(same)
             torch.cuda.synchronize()
+            if w_ > 1:
+                owned, perr = t2.owned_ranges(), t2.peer_error()
             res.append((m2._direct_grad[t2.lo:t2.hi].clone() * (1.0 / w_), m2._flat[t2.lo:t2.hi].clone()))
             del m2, t2
         (g_dp, p_dp), (g_1, p_1) = res
         gmax = g_1.abs().max().clamp_min(1e-30)
-        stats = torch.stack([(g_dp - g_1).abs().max() / gmax, (p_dp - p_1).abs().max()]).double()
+        # peer mode: a rank holds the reduced gradient of the sub-slices it owns (the ranks together cover the buffer)
+        gerr = torch.stack([(g_dp[x:y] - g_1[x:y]).abs().max() for x, y in owned if y > x]).max()
+        stats = torch.stack([gerr / gmax, (p_dp - p_1).abs().max()]).double()
         pmin, pmax = p_dp.clone(), p_dp.clone()
         dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dp = {"dp_check_grad_max_rel": float(stats[0]), "dp_check_max_abs": float(stats[1]),
-              "dp_check_cross_rank_param_max_abs": float((pmax - pmin).abs().max()),
+              "dp_check_cross_rank_param_max_abs": float((pmax - pmin).abs().max()), "peer_wait_error": perr,
               "what": "one step, identical data / weights / dropout seed on all ranks: all-reduced gradient / N vs the "
                       "collective-free gradient (max |d| / max |g|), updated parameters vs the collective-free step and across ranks"}
 
@@ -869,6 +879,9 @@ def main():
             line["sustained"] = soak
         if dp:
             line["dp_check"] = dp
+        if world > 1 and mode == "train":
+            line["dp_update"] = {"requested": a.grad_comm, "effective": trainer.grad_comm,
+                                 "peer_fallback": trainer.peer_fallback, "peer_wait_error": trainer.peer_error()}
         if eager:
             line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)

@@ -430,6 +430,8 @@ int backward_panorama(const etp_pano_weights& w, const etp_pano_weights& g, cons
     ETP_TRY(layernorm_bwd(Bf, x, lw.n1_g, r.st1, r.st1 + rows, rows, kH, A, 1, sc.gb, F(lg.n1_g), F(lg.n1_b), s,
                           i > 0 ? F(g.layers[i - 1].l2_b) : nullptr,
                           i > 0 ? dc.hidden(drop_site(kSitePano, i - 1, kDropPFfnOut)) : DropHost{0u, 0u, 1.0f}));  // A = dx (= dx_out of layer i-1)
+    if (i > 0 && in.layer_done_events && in.layer_done_events[i])   // layer i's gradient slice is final: its exchange may start
+      ETP_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(in.layer_done_events[i]), s));
   }
   PanoPackBwdArgs pb;
   pb.rows = rows; pb.dx = A; pb.rgb_lin = rec.rgb_lin; pb.dep_lin = w.dep_w ? rec.dep_lin : nullptr; pb.loc_lin = rec.loc_lin;

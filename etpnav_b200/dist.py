@@ -30,7 +30,8 @@ def gradient_buckets(layout, cfg, lo, hi):
     x-layer X-1 (with the SAP head that follows it in the layout), X-2, ..., 0, then the rest (panorama group,
     node-packing parameters and the stacked text key|value projections, all finished last).  Each x-layer's own
     parameters are one contiguous run of the layout (etpnav_b200/layout.py).  When the slice also holds the panorama
-    group, the remainder is split into ``nav_head`` (final at the end of the navigation backward) and ``rest``."""
+    group, the remainder is split into ``nav_head`` (final at the end of the navigation backward), ``pano_layer_i`` for
+    the panorama layers above 0 (the last one carries pano_encoder.norm) and ``rest``."""
     X = cfg.num_x_layers
     buckets = []
     if X == 0:
@@ -42,7 +43,15 @@ def gradient_buckets(layout, cfg, lo, hi):
     nav_lo = layout.group_ranges["nav"][0]
     if lo < nav_lo < starts[0]:
         buckets.append(("nav_head", nav_lo, starts[0]))   # node packing + stacked text K|V: done when the nav backward is
-        buckets.append(("rest", lo, nav_lo))              # panorama group: done last
+        # panorama group, finished last and in the order layer P-1 ... 0: every layer above 0 is its own bucket (final at
+        # the event etp_backward_panorama records for it), layer 0 + the view embeddings are the exposed remainder
+        P, end = cfg.num_pano_layers, nav_lo
+        for i in range(P - 1, 0, -1):
+            st = layout.offset(f"img_embeddings.pano_encoder.layers.{i}.self_attn.in_proj_weight")
+            if lo < st < end:
+                buckets.append((f"pano_layer_{i}", st, end))
+                end = st
+        buckets.append(("rest", lo, end))
     elif starts[0] > lo:
         buckets.append(("rest", lo, starts[0]))
     return buckets

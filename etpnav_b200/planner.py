@@ -67,7 +67,7 @@ class PanoWeights(C.Structure):
 
 class PanoInputs(C.Structure):
     _fields_ = [("B", i32), ("V", i32)] + [(n, p_void) for n in ("rgb_fts", "dep_fts", "loc_fts", "nav_types", "view_lens")] + [
-        ("dropout", C.POINTER(Dropout))]
+        ("dropout", C.POINTER(Dropout)), ("layer_done_events", C.POINTER(p_void))]
 
 
 class TxtWeights(C.Structure):
@@ -744,6 +744,8 @@ def _pano_backward_raw(m, rgb, dep, loc, nt, vl, masks, drop, saved, d_out, want
         tok = gbuf[ge - gs:]
         gst["pano"].tok_emb1 = C.c_void_p(tok.data_ptr())
     pi = _pano_inputs(rgb, dep, loc, nt, vl, drop)
+    if getattr(m, "_pano_layer_events", None) is not None:
+        pi.layer_done_events = m._pano_layer_events
     d_rgb = torch.empty_like(rgb) if want_drgb else None
     d_dep = torch.empty_like(dep) if (want_ddep and m.config.use_depth_embedding) else None
     wbytes = L.etp_pano_bwd_work_bytes(B, V)
@@ -849,6 +851,23 @@ class _TxtFn(torch.autograd.Function):
         return (None, None, None, None, None, *pg)
 
 
+class PeerGroup(C.Structure):
+    """etp_peer_group (include/etpnav_b200.h): every rank's flat gradient / parameter / bf16-image / flag buffers."""
+    _fields_ = [("world", i32), ("rank", i32), ("grad", p_void * 8), ("param", p_void * 8), ("image", p_void * 8),
+                ("flags", p_void * 8)]
+
+
+PEER_FLAG_WORDS = 2 * 32 * 8
+
+
+def peer_partition(x, y, world, rank):
+    """Sub-slice of the trainable run [x, y) that `rank` owns in the peer-memory update: `world` equal chunks, rounded up
+    to the 64-element granule of the flat layout; trailing ranks may own nothing."""
+    chunk = (-(-(y - x) // world) + 63) // 64 * 64
+    x0 = min(y, x + rank * chunk)
+    return x0, min(y, x0 + chunk)
+
+
 class PlannerTrainer:
     """Fused training step for the planner hot path: forward_panorama + forward_navigation, the caller-side loss of
     ss_trainer_ETP.py:890-892 (cross-entropy, sum over the batch, divided by the number of actions as :1055),
@@ -863,8 +882,11 @@ class PlannerTrainer:
         hook; gradients are still ACCUMULATED and applied in fp32).  ``comm_sms``: SMs the library's persistent grids leave
         to the collective's CTAs while training data-parallel (etp_set_sm_reserve; pair it with NCCL_MAX_CTAS)."""
         self.m, self.lr, self.world, self.betas, self.eps, self.wd = model, lr, world_size, betas, eps, weight_decay
-        if grad_comm not in ("fp32", "bf16"):
-            raise ValueError("grad_comm must be 'fp32' or 'bf16'")
+        if grad_comm not in ("fp32", "bf16", "peer"):
+            raise ValueError("grad_comm must be 'fp32', 'bf16' or 'peer'")
+        if grad_comm == "peer" and world_size == 1:
+            grad_comm = "fp32"
+        self._peer, self._peer_plan, self._peer_bases, self.peer_fallback = None, None, [], None
         self.grad_comm, self.comm_sms, self._comm_buf = grad_comm, int(comm_sms), None
         # panorama branch on its own stream next to the instruction-side GEMMs of the navigation call
         # (_forward_backward_overlapped); ETP_OVERLAP=0 / overlap=False runs the two calls back to back through autograd
@@ -889,8 +911,6 @@ class PlannerTrainer:
         self.lo = min(model.layout.group_ranges[g][0] for g in groups)
         self.hi = max(model.layout.group_ranges[g][1] for g in groups)
         n = self.hi - self.lo
-        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.t = 0
         # torch.optim.AdamW skips parameters without a gradient (frozen by fix_pano_embedding / fix_lang_embedding,
         # vilmodel_cmt.py:675-682): only the runs of the slice whose parameters require a gradient are stepped (one run
@@ -922,6 +942,9 @@ class PlannerTrainer:
             X = model.config.num_x_layers
             self._events = [L0.etp_event_create() for _ in range(X + 1)]   # one per x-layer + "nav group complete"
             model._layer_events = (p_void * (X + 1))(*self._events)
+            Pn = model.config.num_pano_layers
+            self._pano_events = [None] + [L0.etp_event_create() for _ in range(1, Pn)]
+            model._pano_layer_events = (p_void * max(Pn, 1))(*self._pano_events) if Pn > 1 else None
             # the update runs UNDER the backward: a small grid-striding grid, so it does not take the registers / thread
             # slots the persistent GEMM CTA pairs need (ETP_ADAMW_CTAS overrides: 16 = the stand-alone roofline grid)
             import os as _os
@@ -930,11 +953,152 @@ class PlannerTrainer:
             if world_size > 1:
                 L0.etp_set_sm_reserve.argtypes = [i32]
                 L0.etp_set_sm_reserve(self.comm_sms)
-                if grad_comm == "bf16":
+                if self.grad_comm == "peer":
+                    self._peer_setup()
+                if self.grad_comm == "bf16":
                     self._comm_buf = torch.empty(n, dtype=torch.bfloat16, device=dev)
+        elif self.grad_comm == "peer":
+            raise RuntimeError("grad_comm='peer' needs CUDA devices (peer memory over NVLink)")
+        if self._peer is None:
+            self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         L = _L.lib()
         L.etp_adamw_step.argtypes = [p_void, p_void, p_void, p_void, p_void, C.c_int64, f32, f32, f32, f32, f32, i32, f32,
                                      p_void]
+
+    # ---- data-parallel update over NVLink peer memory (csrc/peer.cu) -------------------------------------------------
+    def _peer_setup(self):
+        """Map every rank's flat gradient / parameter / bf16-image buffers and flag block (CUDA IPC), cut every bucket's
+        trainable runs into per-rank sub-slices and allocate the optimizer state of the OWNED sub-slices only.  If any
+        rank cannot export / map (IPC not permitted in this container, no peer access) all ranks fall back to the NCCL
+        all-reduce path together; ``peer_fallback`` keeps the reason."""
+        import torch.distributed as dist
+        m, L0 = self.m, _L.lib()
+        rank, world, dev = dist.get_rank(), self.world, m._flat.device
+        L0.etp_ipc_export.argtypes = [p_void, p_void, C.POINTER(C.c_int64)]
+        L0.etp_ipc_open.argtypes = [p_void, C.POINTER(p_void)]
+        L0.etp_ipc_close.argtypes = [p_void]
+        L0.etp_peer_signal.argtypes = [C.POINTER(PeerGroup), i32, i32, C.c_uint32, p_void]
+        L0.etp_peer_wait.argtypes = [C.POINTER(PeerGroup), i32, i32, i32, C.c_uint32, C.c_double, p_void]
+        L0.etp_peer_reduce_adamw.argtypes = [C.POINTER(PeerGroup), C.c_int64, C.c_int64, p_void, p_void, f32, f32, f32, f32,
+                                             f32, i32, i32, i32, p_void]
+        L0.etp_peer_error.argtypes = [C.POINTER(i32)]
+        self._peer_flags = torch.zeros(PEER_FLAG_WORDS, dtype=torch.int32, device=dev)
+        bufs = {"grad": m._direct_grad, "param": m._flat, "image": m._flat_bf16, "flags": self._peer_flags}
+        torch.cuda.synchronize(dev)
+        mine, why = {}, None
+        try:
+            if world > 8:
+                raise RuntimeError("more than 8 ranks")
+            for k, t in bufs.items():
+                h, off = (C.c_ubyte * 64)(), C.c_int64()
+                _L._check(L0.etp_ipc_export(C.c_void_p(t.data_ptr()), h, C.byref(off)), "etp_ipc_export")
+                mine[k] = (bytes(h), off.value)
+        except Exception as e:  # noqa: BLE001 - reported, and every rank takes the same fallback
+            why = f"rank {rank}: {e}"
+        allh = [None] * world
+        dist.all_gather_object(allh, (mine, why))
+        g = PeerGroup()
+        g.world, g.rank = world, rank
+        opened = {}
+        if not any(w for _, w in allh):
+            try:
+                for r in range(world):
+                    for k, t in bufs.items():
+                        if r == rank:
+                            ptr = t.data_ptr()
+                        else:
+                            hb, off = allh[r][0][k]
+                            if (r, hb) not in opened:
+                                base = p_void()
+                                _L._check(L0.etp_ipc_open(hb, C.byref(base)), "etp_ipc_open")
+                                opened[(r, hb)] = base.value
+                            ptr = opened[(r, hb)] + off
+                        getattr(g, k)[r] = ptr
+            except Exception as e:  # noqa: BLE001
+                why = f"rank {rank}: {e}"
+        ok = torch.tensor([0 if (why or any(w for _, w in allh)) else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        self._peer_bases = list(opened.values())
+        if int(ok.item()) == 0:
+            self.peer_fallback = why or next((w for _, w in allh if w), "another rank could not map peer memory")
+            self._peer_close()
+            self.grad_comm = "fp32"
+            return
+        self._peer = g
+        self._peer_ptrs = tuple(t.data_ptr() for t in bufs.values())
+        plan, so = [], 0
+        for _, a, b in self.buckets:
+            runs = []
+            for x, y in self._bucket_runs(a, b):
+                x0, x1 = peer_partition(x, y, world, rank)
+                if x1 > x0:
+                    runs.append((x0, x1 - x0, so))
+                    so += x1 - x0
+            plan.append(runs)
+        assert len(plan) <= 32, "more gradient buckets than flag slots"
+        self._peer_plan = plan
+        self.exp_avg = torch.zeros(max(so, 4), dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(max(so, 4), dtype=torch.float32, device=dev)
+        import os as _os
+        self._peer_ctas = int(_os.environ.get("ETP_PEER_CTAS", "64"))
+        self._peer_write_reduced = 0
+        dist.barrier()
+
+    def _peer_close(self):
+        for base in self._peer_bases:
+            try:
+                _L.lib().etp_ipc_close(C.c_void_p(base))
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+        self._peer_bases = []
+
+    def __del__(self):
+        if getattr(self, "_peer_bases", None):
+            self._peer_close()
+
+    def owned_ranges(self):
+        """[(a, b)] relative to the trainer's slice: what this rank reduces and updates (everything, unless peer mode)."""
+        if self._peer is None:
+            return [(0, self.hi - self.lo)]
+        return [(x0 - self.lo, x0 - self.lo + n) for runs in self._peer_plan for x0, n, _ in runs]
+
+    def peer_error(self):
+        """0, or 1 + kind of a flag wait that gave up (synchronises the device)."""
+        if self._peer is None:
+            return 0
+        v = i32(0)
+        _L._check(_L.lib().etp_peer_error(C.byref(v)), "etp_peer_error")
+        return int(v.value)
+
+    def _optimizer_step_peer(self):
+        m, L0, g = self.m, _L.lib(), C.byref(self._peer)
+        if (m._direct_grad.data_ptr(), m._flat.data_ptr(), m._flat_bf16.data_ptr()) != self._peer_ptrs[:3]:
+            raise RuntimeError("the flat buffers moved after the peer group was built (rebuild the trainer)")
+        main = torch.cuda.current_stream()
+        side_ptr = C.c_void_p(self.side.cuda_stream)
+        X, t = m.config.num_x_layers, self.t
+        for bi, (nm, a, b) in enumerate(self.buckets):
+            if nm.startswith("x_layer_") or nm == "nav_head" or nm.startswith("pano_layer_"):
+                ev = (self._pano_events[int(nm.split("_")[-1])] if nm.startswith("pano_layer_") else
+                      self._events[X if nm == "nav_head" else int(nm.split("_")[-1])])
+                _L._check(L0.etp_stream_wait_event(side_ptr, C.c_void_p(ev)), "etp_stream_wait_event")
+            else:
+                self.side.wait_stream(main)
+                if self.pano_stream is not None:
+                    self.side.wait_stream(self.pano_stream)
+            _L._check(L0.etp_peer_signal(g, 0, bi, t, side_ptr), "etp_peer_signal")
+            _L._check(L0.etp_peer_wait(g, 0, bi, bi + 1, t, 30.0, side_ptr), "etp_peer_wait")
+            for x0, n, so in self._peer_plan[bi]:
+                _L._check(L0.etp_peer_reduce_adamw(
+                    g, x0, n, C.c_void_p(self.exp_avg.data_ptr() + 4 * so), C.c_void_p(self.exp_avg_sq.data_ptr() + 4 * so),
+                    self.lr, self.betas[0], self.betas[1], self.eps, self.wd, t, self._peer_write_reduced, self._peer_ctas,
+                    side_ptr), "etp_peer_reduce_adamw")
+            _L._check(L0.etp_peer_signal(g, 1, bi, t, side_ptr), "etp_peer_signal")
+        main.wait_stream(self.side)
+        # nobody may zero its gradients / read its weights for the next step before EVERY owner is done with every bucket
+        _L._check(L0.etp_peer_wait(g, 1, 0, len(self.buckets), t, 30.0, C.c_void_p(main.cuda_stream)), "etp_peer_wait")
+        m._bf16_fresh = True
 
     @staticmethod
     def _active_ranges(model, lo, hi):
@@ -1072,13 +1236,16 @@ class PlannerTrainer:
                 self._adamw(a, b, scale, _L.stream_ptr())
             m._bf16_fresh = True
             return
+        if self._peer is not None:
+            return self._optimizer_step_peer()
         L0 = _L.lib()
         main = torch.cuda.current_stream()
         side_ptr = C.c_void_p(self.side.cuda_stream)
         X = m.config.num_x_layers
         for nm, a, b in self.buckets:
-            if nm.startswith("x_layer_") or nm == "nav_head":
-                ev = self._events[X if nm == "nav_head" else int(nm.split("_")[-1])]
+            if nm.startswith("x_layer_") or nm == "nav_head" or nm.startswith("pano_layer_"):
+                ev = (self._pano_events[int(nm.split("_")[-1])] if nm.startswith("pano_layer_") else
+                      self._events[X if nm == "nav_head" else int(nm.split("_")[-1])])
                 _L._check(L0.etp_stream_wait_event(side_ptr, C.c_void_p(ev)), "etp_stream_wait_event")
             else:
                 self.side.wait_stream(main)       # final only when the whole backward is ...

@@ -21,7 +21,8 @@
  * Two further groups at the end of the file cover the rows SURVEY.md §8f calls "next":
  *   (3) the pre-training twin GlocalTextPathCMT (pretrain_src/pretrain_src/model/vilmodel.py:656-754):
  *       etp_segment_gather(_rows), etp_forward_lang2visn / etp_backward_lang2visn;
- *   (4) the trainer's per-step map packing (vlnce_baselines/ss_trainer_ETP.py:344-417): etp_gmap_pack.
+ *   (4) the trainer's per-step map packing (vlnce_baselines/ss_trainer_ETP.py:344-417): etp_gmap_pack;
+ *   (5) the data-parallel update over NVLink peer memory (ss_trainer_ETP.py:211-213): etp_ipc_*, etp_peer_*.
  */
 #ifndef ETPNAV_B200_H_
 #define ETPNAV_B200_H_
@@ -327,6 +328,10 @@ typedef struct {
   const int64_t* nav_types;   /* [B,V]     */
   const int64_t* view_lens;   /* [B]       */
   const etp_dropout* dropout; /* train() mode dropout, or NULL */
+  /* optional, etp_backward_panorama: num_pano_layers cudaEvent_t; event i (i >= 1) is recorded on the stream when every
+   * parameter gradient of pano layer i (and, for the last layer, of pano_encoder.norm) is complete — layers finish in
+   * the order P-1 ... 1; layer 0 and the view embeddings are final when the call is.  Entry 0 is ignored. */
+  void* const* layer_done_events;
 } etp_pano_inputs;
 
 size_t etp_pano_saved_bytes(int32_t B, int32_t V, int32_t num_pano_layers, int32_t training);
@@ -466,6 +471,44 @@ int etp_backward_lang2visn(const etp_nav_weights* w, const etp_nav_weights* grad
 int etp_gmap_pack(const int32_t* meta, const double* f64_blob, const int32_t* i32_blob, int32_t B, int32_t n_max,
                   int32_t max_ghosts, int64_t* gmap_step_ids, uint8_t* gmap_visited_masks, uint8_t* gmap_masks,
                   float* gmap_pos_fts, float* gmap_pair_dists, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * data-parallel update over NVLink peer memory: the exchange step of the reference's
+ * DistributedDataParallel + torch.optim.AdamW (vlnce_baselines/ss_trainer_ETP.py:211-213) as ONE kernel per gradient
+ * bucket — reduce-scatter (peer loads), AdamW on the owned 1/world sub-slice, all-gather of the new parameters and their
+ * bf16 image (peer stores).  One process per GPU; every rank maps the other ranks' flat buffers through CUDA IPC.
+ * ------------------------------------------------------------------------------------------- */
+/* IPC plumbing for hosts without their own: handle (64 bytes) + byte offset of `ptr` inside its allocation;
+ * etp_ipc_open maps a peer's allocation (peer access enabled lazily) and returns its base in this process. */
+int etp_ipc_export(const void* ptr, void* handle64, int64_t* offset);
+int etp_ipc_open(const void* handle64, void** base_out);
+int etp_ipc_close(void* base);
+
+#define ETP_PEER_MAX_RANKS 8
+#define ETP_PEER_MAX_BUCKETS 32
+#define ETP_PEER_FLAG_WORDS (2 * ETP_PEER_MAX_BUCKETS * ETP_PEER_MAX_RANKS)
+typedef struct {
+  int32_t world, rank;
+  float* grad[ETP_PEER_MAX_RANKS];      /* base of every rank's flat fp32 gradient buffer (own entry = local pointer) */
+  float* param[ETP_PEER_MAX_RANKS];     /* ... flat fp32 parameter buffer */
+  uint16_t* image[ETP_PEER_MAX_RANKS];  /* ... bf16 image of the parameters (what the GEMMs read) */
+  uint32_t* flags[ETP_PEER_MAX_RANKS];  /* ... flag block, ETP_PEER_FLAG_WORDS zero-initialised words: [kind][bucket][rank] */
+} etp_peer_group;
+/* kind 0 = READY (this rank's gradients of `bucket` are final for step `value`), 1 = DONE (this rank has read the bucket's
+ * gradients from, and written its new parameters to, every rank).  Signal: this rank's word at EVERY rank := value, after
+ * all work already in `stream`.  Wait: spin (device side, own flag block) until the words of all ranks for buckets
+ * [bucket_lo, bucket_hi) reach `value`; after `timeout_s` (<= 0: 10 s) the wait gives up and etp_peer_error reports it. */
+int etp_peer_signal(const etp_peer_group* g, int32_t kind, int32_t bucket, uint32_t value, void* stream);
+int etp_peer_wait(const etp_peer_group* g, int32_t kind, int32_t bucket_lo, int32_t bucket_hi, uint32_t value,
+                  double timeout_s, void* stream);
+/* The fused kernel over this rank's OWNED sub-slice [offset, offset + n) of the flat buffers (elements, multiples of 4):
+ * g = sum_r grad_r (rank order), AdamW with grad_scale 1/world (torch.optim.AdamW, as etp_adamw_step) on exp_avg /
+ * exp_avg_sq [n] (owner-local), result stored to param_r / image_r of every rank.  write_reduced != 0 also leaves the
+ * summed gradient in the owner's own gradient buffer (self-checks).  ctas: grid size (<= 0: 64). */
+int etp_peer_reduce_adamw(const etp_peer_group* g, int64_t offset, int64_t n, float* exp_avg, float* exp_avg_sq, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, int32_t step, int32_t write_reduced,
+                          int32_t ctas, void* stream);
+int etp_peer_error(int32_t* out);   /* 0, or 1 + kind of a wait that timed out (synchronises the device) */
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,9 @@ run_one() {
     benchn)    # benchn <N> <name> [bench args]: torchrun over N GPUs of this box
       n=$1; name=$2; shift; shift
       timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $n --no-cpu-baseline --no-gpu-eager "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; echo "bench $name rc=$?"; cat gpurun_out/bench_$name.json; tail -2 gpurun_out/bench_$name.err ;;
+    peer)      # peer <N>: the fused peer-memory update against the NCCL path on N GPUs (tests/dp_peer_worker.py)
+      n=$1; shift
+      timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29561 tests/dp_peer_worker.py > gpurun_out/peer_n$n.json 2> gpurun_out/peer_n$n.err; echo "peer n=$n rc=$?"; cat gpurun_out/peer_n$n.json; tail -5 gpurun_out/peer_n$n.err ;;
     report)
       timeout 900 python bench.py --no-cpu-baseline --no-gpu-eager --kernel-report gpurun_out/kernel_report.txt "$@" > gpurun_out/bench_report.json 2> gpurun_out/bench_report.err
       echo "report rc=$?"; cat gpurun_out/bench_report.json; head -40 gpurun_out/kernel_report.txt ;;

@@ -52,7 +52,7 @@ def test_two_rank_gradient_mean_and_distinct_shards(tmp_path):
     assert torch.allclose(r0["g"][10:], torch.full((990,), 1.5))  # mean of 1 and 2
     assert not torch.equal(r0["img"], r1["img"])              # ranks drew different shards
     # buckets: completion order (last x-layer first, "rest" last), disjoint, covering the whole slice; mean of x and 2x
-    assert r0["names"] == ["x_layer_2", "x_layer_1", "x_layer_0", "nav_head", "rest"]
+    assert r0["names"] == ["x_layer_2", "x_layer_1", "x_layer_0", "nav_head", "pano_layer_1", "rest"]
     cov = r0["cover"]
     assert cov[0][0] == 0 and cov[-1][1] == r0["n"] and all(cov[i][1] == cov[i + 1][0] for i in range(len(cov) - 1))
     assert torch.equal(r0["gb"], r1["gb"])

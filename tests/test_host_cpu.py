@@ -215,3 +215,16 @@ def test_ctypes_struct_mirrors_match_the_header():
     assert n == len(mirrors)
     for i, m in enumerate(mirrors):
         assert C.sizeof(m) == out[i], (m.__name__, C.sizeof(m), out[i])
+
+
+def test_peer_partition_covers_every_run_with_aligned_disjoint_sub_slices():
+    """Owner sub-slices of the peer-memory update (planner.peer_partition): disjoint, in rank order, 64-element aligned
+    starts, covering the trainable run exactly; trailing ranks of a short run own nothing."""
+    from etpnav_b200.planner import peer_partition
+    for x, y in [(0, 64), (128, 128 + 64 * 3), (4096, 4096 + 64 * 1001), (64, 64 + 7_077_888), (0, 0)]:
+        for world in (2, 4, 8):
+            parts = [peer_partition(x, y, world, r) for r in range(world)]
+            assert parts[0][0] == x and parts[-1][1] == y
+            assert all(a <= b and (a - x) % 64 == 0 for a, b in parts)
+            assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+            assert sum(b - a for a, b in parts) == y - x
