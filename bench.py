@@ -823,7 +823,7 @@ def main():
             if getattr(t2, "_peer", None) is not None:
                 t2._peer_write_reduced = 1     # the owner leaves the summed gradient in its own buffer: that is what is checked
             m2.set_dropout_seed(777)
-            t2.step(same)
+            t2.step(same, keep_grads=True)
             torch.cuda.synchronize()
             if w_ > 1:
                 owned, perr = t2.owned_ranges(), t2.peer_error()

@@ -887,6 +887,7 @@ class PlannerTrainer:
         if grad_comm == "peer" and world_size == 1:
             grad_comm = "fp32"
         self._peer, self._peer_plan, self._peer_bases, self.peer_fallback = None, None, [], None
+        self._grads_clean, self._clear_after_update = False, False
         self.grad_comm, self.comm_sms, self._comm_buf = grad_comm, int(comm_sms), None
         # panorama branch on its own stream next to the instruction-side GEMMs of the navigation call
         # (_forward_backward_overlapped); ETP_OVERLAP=0 / overlap=False runs the two calls back to back through autograd
@@ -1120,6 +1121,7 @@ class PlannerTrainer:
         return runs
 
     def zero_grad(self):
+        self._grads_clean = False
         self.m._direct_grad[self.lo:self.hi].zero_()
         if self.m._tok_scratch is not None:
             self.m._tok_scratch.zero_()
@@ -1263,13 +1265,25 @@ class PlannerTrainer:
                         dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM)
                 for x, y in self._bucket_runs(a, b):
                     self._adamw(x, y, scale, side_ptr)
+                if self._clear_after_update:
+                    g[a:b].zero_()
+        if self._clear_after_update and m._tok_scratch is not None:
+            with torch.cuda.stream(self.side):
+                m._tok_scratch.zero_()
         main.wait_stream(self.side)
         m._bf16_fresh = True  # AdamW rewrote the flat parameters and their bf16 image (a high-precision image is now stale)
 
-    def step(self, d):
-        self.zero_grad()
+    def step(self, d, keep_grads=False):
+        """zero_grad + forward_backward + optimizer_step.  Unless ``keep_grads``, each bucket's gradient slice is cleared on
+        the update stream right behind its AdamW (under the rest of the backward), so the next step does not start with a
+        300 MB memset on the compute stream: after step() the gradient buffer reads zero, as after the reference's
+        ``optimizer.zero_grad()`` (ss_trainer_ETP.py:499)."""
+        if not self._grads_clean:
+            self.zero_grad()
         logits, _ = self.forward_backward(d)
+        self._clear_after_update = not keep_grads and self.side is not None and self._peer is None
         self.optimizer_step()
+        self._grads_clean, self._clear_after_update = self._clear_after_update, False
         return logits
 
 

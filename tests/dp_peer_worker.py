@@ -40,7 +40,7 @@ def main():
             tr._peer_write_reduced = 1        # owners leave the summed gradient in their own buffer (compared below)
         m.set_dropout_seed(1234 + rank)
         p0 = m._flat[tr.lo:tr.hi].clone()
-        tr.step(data[0])
+        tr.step(data[0], keep_grads=True)
         torch.cuda.synchronize()
         g1, p1 = m._direct_grad[tr.lo:tr.hi].clone(), m._flat[tr.lo:tr.hi].clone()
         for d in data[1:]:

@@ -146,3 +146,43 @@ def test_overlapped_trainer_step_equals_the_sequential_one():
     # (AdamW's first steps move every element by ~lr whatever the gradient's size: elements whose tiny gradients differ in
     # the last bits may move apart by 2 lr; the parameters as a whole stay together)
     assert ((p_seq - p_ovl).norm() / p_seq.norm()).item() < 5e-3
+
+
+def test_step_clears_gradients_behind_the_update():
+    """PlannerTrainer.step() clears every bucket's gradient slice on the update stream right behind its AdamW instead of
+    starting the next step with a memset on the compute stream: the buffer reads zero after step(), and the gradient the
+    NEXT step accumulates equals the one a fresh trainer computes from the same weights (nothing stale, nothing cleared
+    late)."""
+    from etpnav_b200.config import PlannerConfig
+    from etpnav_b200.planner import B200Planner
+    from etpnav_b200.synth import make_inputs, make_weights
+    cfg = PlannerConfig(vocab_size=2048, num_l_layers=0, num_x_layers=2)
+    d = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in make_inputs(cfg, 8, 12, 30, 50, seed=3, ragged=True).items()}
+    m = B200Planner(cfg, device="cuda")
+    m.load_state_dict(make_weights(cfg, seed=3), strict=True)
+    m.train()
+    m.set_dropout_seed(11)
+    tr = m.make_trainer(lr=1e-4)
+    tr.step(d)
+    tr.step(d)
+    torch.cuda.synchronize()
+    assert tr._grads_clean and m._direct_grad[tr.lo:tr.hi].abs().max().item() == 0.0
+    w1 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m.set_dropout_seed(5)
+    tr.step(d, keep_grads=True)
+    torch.cuda.synchronize()
+    g2 = m._direct_grad[tr.lo:tr.hi].clone()
+    assert not tr._grads_clean and g2.abs().max().item() > 0
+    m3 = B200Planner(cfg, device="cuda")
+    m3.load_state_dict(w1, strict=True)
+    m3.train()
+    tr3 = m3.make_trainer(lr=1e-4)
+    m3.set_dropout_seed(5)
+    tr3.zero_grad()
+    tr3.forward_backward(d)
+    torch.cuda.synchronize()
+    g3 = m3._direct_grad[tr3.lo:tr3.hi]
+    assert ((g2 - g3).norm() / g3.norm()).item() < 1e-4
+    tr.step(d)           # a kept gradient is cleared explicitly before the next accumulation
+    torch.cuda.synchronize()
+    assert m._direct_grad[tr.lo:tr.hi].abs().max().item() == 0.0
