@@ -77,10 +77,11 @@ def parse():
     ap.add_argument("--text-kv", action="store_true",
                     help="fwd mode: the instruction's key|value projections are computed once per episode "
                          "(B200Planner.encode_text_kv, outside the timed step) and reused by every step, as in an eval rollout")
-    ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16", "peer"],
-                    help="N > 1: fp32 = NCCL all-reduce of the gradient buckets (DDP default) | bf16 = the same in bf16 | "
-                         "peer = reduce-scatter + AdamW + parameter all-gather fused in one kernel over NVLink peer memory")
-    ap.add_argument("--peer-ctas", type=int, default=0, help="N > 1, --grad-comm peer: grid of the fused update kernel (default 64)")
+    ap.add_argument("--grad-comm", default="peer", choices=["fp32", "bf16", "peer"],
+                    help="N > 1: peer (default) = reduce-scatter + AdamW + parameter all-gather fused in one kernel per bucket "
+                         "over NVLink peer memory (falls back to fp32 when CUDA IPC / peer access is unavailable) | fp32 = NCCL "
+                         "all-reduce of the gradient buckets + replicated AdamW (DDP's arithmetic) | bf16 = the same in bf16")
+    ap.add_argument("--peer-ctas", type=int, default=128, help="N > 1, --grad-comm peer: grid of the fused update kernel")
     ap.add_argument("--comm-sms", type=int, default=0,
                     help="N > 1: SMs the persistent grids leave to the collective (etp_set_sm_reserve)")
     ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: NCCL_MAX_CTAS for this run (0 = NCCL's default)")
