@@ -615,8 +615,13 @@ def main():
         trainer = model.make_trainer(lr=1e-5, world_size=world, grad_comm=a.grad_comm, comm_sms=a.comm_sms)
 
         def step(d):
-            return trainer.step(d)
+            # training-loop form of the step: the compute stream returns once the navigation buckets are updated, the
+            # panorama buckets finish under the next step's first GEMM; every timed region ends with trainer.join()
+            return trainer.step(d, pipelined=True)
+
+        step_done = trainer.join
     else:
+        step_done = lambda: None
         model.eval().set_precision(a.precision)
         text_kv = None
         if a.text_kv:   # once per episode, like forward_txt: not part of the per-step path
@@ -642,6 +647,7 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        step_done()          # nothing of the last step is left running outside the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)

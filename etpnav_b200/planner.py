@@ -888,6 +888,7 @@ class PlannerTrainer:
             grad_comm = "fp32"
         self._peer, self._peer_plan, self._peer_bases, self.peer_fallback = None, None, [], None
         self._grads_clean, self._clear_after_update = False, False
+        self._pipelined, self._pending_join, self._ev_nav, self._k_nav = False, False, None, -1
         self.grad_comm, self.comm_sms, self._comm_buf = grad_comm, int(comm_sms), None
         # panorama branch on its own stream next to the instruction-side GEMMs of the navigation call
         # (_forward_backward_overlapped); ETP_OVERLAP=0 / overlap=False runs the two calls back to back through autograd
@@ -928,7 +929,12 @@ class PlannerTrainer:
         self.buckets = [(nm, a - self.lo, b - self.lo) for nm, a, b in
                         gradient_buckets(model.layout, model.config, self.lo, self.hi)]
         self.side, self._events = None, []
+        # index of the last bucket of the navigation group (x-layers, then node packing / text K|V): the compute stream of a
+        # pipelined step() only waits for the update up to here; the panorama buckets finish under the next step's start
+        self._k_nav = max((i for i, (nm, _, _) in enumerate(self.buckets) if nm.startswith("x_layer_") or nm == "nav_head"),
+                          default=-1)
         if dev.type == "cuda":
+            self._ev_nav = torch.cuda.Event()
             self.side = torch.cuda.Stream(dev)
             self.pano_stream = torch.cuda.Stream(dev)
             _Le = _L.lib()
@@ -1072,13 +1078,33 @@ class PlannerTrainer:
         _L._check(_L.lib().etp_peer_error(C.byref(v)), "etp_peer_error")
         return int(v.value)
 
+    def _join_after_update(self, main):
+        """End of optimizer_step: a pipelined step() makes the compute stream wait for the navigation buckets only (the next
+        step's first kernels read those weights; its panorama branch, on its own stream, waits for the rest)."""
+        if self._pipelined and self._k_nav >= 0 and self._k_nav < len(self.buckets) - 1:
+            main.wait_event(self._ev_nav)
+            self._pending_join = True
+        else:
+            main.wait_stream(self.side)
+            self._pending_join = False
+
     def _optimizer_step_peer(self):
         m, L0, g = self.m, _L.lib(), C.byref(self._peer)
         if (m._direct_grad.data_ptr(), m._flat.data_ptr(), m._flat_bf16.data_ptr()) != self._peer_ptrs[:3]:
             raise RuntimeError("the flat buffers moved after the peer group was built (rebuild the trainer)")
         main = torch.cuda.current_stream()
         side_ptr = C.c_void_p(self.side.cuda_stream)
-        X, t = m.config.num_x_layers, self.t
+        X, t, nb = m.config.num_x_layers, self.t, len(self.buckets)
+        gsl = m._direct_grad[self.lo:self.hi]
+
+        def finish(bi):
+            # nobody may clear (or, next step, accumulate into) a gradient slice before EVERY owner has read it, nor read a
+            # bucket's weights before every owner has written them: DONE of all ranks, then the slice is cleared right here
+            _L._check(L0.etp_peer_wait(g, 1, bi, bi + 1, t, 30.0, side_ptr), "etp_peer_wait")
+            if self._clear_after_update:
+                with torch.cuda.stream(self.side):
+                    gsl[self.buckets[bi][1]:self.buckets[bi][2]].zero_()
+
         for bi, (nm, a, b) in enumerate(self.buckets):
             if nm.startswith("x_layer_") or nm == "nav_head" or nm.startswith("pano_layer_"):
                 ev = (self._pano_events[int(nm.split("_")[-1])] if nm.startswith("pano_layer_") else
@@ -1096,9 +1122,18 @@ class PlannerTrainer:
                     self.lr, self.betas[0], self.betas[1], self.eps, self.wd, t, self._peer_write_reduced, self._peer_ctas,
                     side_ptr), "etp_peer_reduce_adamw")
             _L._check(L0.etp_peer_signal(g, 1, bi, t, side_ptr), "etp_peer_signal")
-        main.wait_stream(self.side)
-        # nobody may zero its gradients / read its weights for the next step before EVERY owner is done with every bucket
-        _L._check(L0.etp_peer_wait(g, 1, 0, len(self.buckets), t, 30.0, C.c_void_p(main.cuda_stream)), "etp_peer_wait")
+            # the previous bucket is finished one bucket late (its owners had the time of this bucket's kernel to get done);
+            # the last bucket of the navigation group and the very last one are finished at once
+            if bi > 0 and bi - 1 != self._k_nav:
+                finish(bi - 1)
+            if bi == self._k_nav or bi == nb - 1:
+                finish(bi)
+            if bi == self._k_nav:
+                self._ev_nav.record(self.side)
+        if self._clear_after_update and m._tok_scratch is not None:
+            with torch.cuda.stream(self.side):
+                m._tok_scratch.zero_()
+        self._join_after_update(main)
         m._bf16_fresh = True
 
     @staticmethod
@@ -1120,7 +1155,16 @@ class PlannerTrainer:
             runs.append((cur[0], hi))
         return runs
 
+    def join(self):
+        """Make the current stream wait for everything a pipelined step() left running on the update stream (the panorama
+        buckets' exchange / AdamW).  Call it before reading parameters or gradients, evaluating, or checkpointing."""
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self._pending_join = False
+
     def zero_grad(self):
+        if self._pending_join:
+            self.join()
         self._grads_clean = False
         self.m._direct_grad[self.lo:self.hi].zero_()
         if self.m._tok_scratch is not None:
@@ -1129,6 +1173,8 @@ class PlannerTrainer:
     def forward_backward(self, d):
         if self.pano_stream is not None and self.overlap:
             return self._forward_backward_overlapped(d)
+        if self._pending_join:
+            self.join()
         m = self.m
         pano, pmask = m.forward_panorama(d["rgb_fts"], d["dep_fts"], d["loc_fts"], d["nav_types"], d["view_lens"])
         # the trainer feeds the masked mean of the view embeddings back into the map as a node feature
@@ -1174,6 +1220,9 @@ class PlannerTrainer:
         drop_p, drop_n = m._next_dropout(), m._next_dropout()     # panorama call first, as in forward_backward()
         # ---- forward: panorama branch on S2, navigation on the compute stream
         S2.wait_stream(main)
+        if self._pending_join:      # pipelined step(): the panorama weights / gradient slices are final when the update stream is
+            S2.wait_stream(self.side)
+            self._pending_join = False
         with torch.cuda.stream(S2):
             pano, pmask_u8, saved_p, _ = _pano_forward(m, rgb, dep, loc, nt, vl, 1, drop_p)
             w = pmask_u8.unsqueeze(-1).float()
@@ -1244,7 +1293,7 @@ class PlannerTrainer:
         main = torch.cuda.current_stream()
         side_ptr = C.c_void_p(self.side.cuda_stream)
         X = m.config.num_x_layers
-        for nm, a, b in self.buckets:
+        for bi, (nm, a, b) in enumerate(self.buckets):
             if nm.startswith("x_layer_") or nm == "nav_head" or nm.startswith("pano_layer_"):
                 ev = (self._pano_events[int(nm.split("_")[-1])] if nm.startswith("pano_layer_") else
                       self._events[X if nm == "nav_head" else int(nm.split("_")[-1])])
@@ -1267,25 +1316,31 @@ class PlannerTrainer:
                     self._adamw(x, y, scale, side_ptr)
                 if self._clear_after_update:
                     g[a:b].zero_()
+                if bi == self._k_nav:
+                    self._ev_nav.record(self.side)
         if self._clear_after_update and m._tok_scratch is not None:
             with torch.cuda.stream(self.side):
                 m._tok_scratch.zero_()
-        main.wait_stream(self.side)
+        self._join_after_update(main)
         m._bf16_fresh = True  # AdamW rewrote the flat parameters and their bf16 image (a high-precision image is now stale)
 
-    def step(self, d, keep_grads=False):
+    def step(self, d, keep_grads=False, pipelined=False):
         """zero_grad + forward_backward + optimizer_step.  Unless ``keep_grads``, each bucket's gradient slice is cleared on
-        the update stream right behind its AdamW (under the rest of the backward), so the next step does not start with a
+        the update stream right behind its update (under the rest of the backward), so the next step does not start with a
         300 MB memset on the compute stream: after step() the gradient buffer reads zero, as after the reference's
-        ``optimizer.zero_grad()`` (ss_trainer_ETP.py:499)."""
+        ``optimizer.zero_grad()`` (ss_trainer_ETP.py:499).
+        ``pipelined=True`` (training loops): the compute stream returns as soon as the NAVIGATION buckets are updated; the
+        panorama buckets — last to finish in the backward, first to be needed by the next forward, but on the panorama
+        branch's own stream — complete under the next step's instruction-side GEMM.  The caller's next call must be another
+        step() / forward_backward() / zero_grad() (they pick the pending join up) or ``join()``."""
         if not self._grads_clean:
             self.zero_grad()
         logits, _ = self.forward_backward(d)
-        self._clear_after_update = not keep_grads and self.side is not None and self._peer is None
+        self._clear_after_update = not keep_grads and self.side is not None
+        self._pipelined = bool(pipelined) and self.overlap and self.pano_stream is not None
         self.optimizer_step()
-        self._grads_clean, self._clear_after_update = self._clear_after_update, False
+        self._grads_clean, self._clear_after_update, self._pipelined = self._clear_after_update, False, False
         return logits
-
 
 
 

@@ -44,7 +44,8 @@ def main():
         torch.cuda.synchronize()
         g1, p1 = m._direct_grad[tr.lo:tr.hi].clone(), m._flat[tr.lo:tr.hi].clone()
         for d in data[1:]:
-            tr.step(d)
+            tr.step(d, pipelined=True)        # training-loop form: panorama buckets finish under the next step
+        tr.join()
         torch.cuda.synchronize()
         p = m._flat[tr.lo:tr.hi].clone()
         pb = m._flat_bf16[tr.lo:tr.hi].clone()

@@ -186,3 +186,36 @@ def test_step_clears_gradients_behind_the_update():
     tr.step(d)           # a kept gradient is cleared explicitly before the next accumulation
     torch.cuda.synchronize()
     assert m._direct_grad[tr.lo:tr.hi].abs().max().item() == 0.0
+
+
+def test_pipelined_steps_match_plain_steps():
+    """step(pipelined=True): the compute stream returns after the navigation buckets' update, the panorama buckets finish
+    under the next step (picked up by its panorama stream) — the logits of every step and the final parameters must stay
+    with those of plain steps (same seeds; differences = fp32 atomics order only), and join() must leave nothing pending."""
+    from etpnav_b200.config import PlannerConfig
+    from etpnav_b200.planner import B200Planner
+    from etpnav_b200.synth import make_inputs, make_weights
+    cfg = PlannerConfig(vocab_size=2048, num_l_layers=0, num_x_layers=3)
+    sd = make_weights(cfg, seed=23)
+    ds = [{k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in make_inputs(cfg, 16, 12, 40, 90, seed=23 + i, ragged=True).items()}
+          for i in range(2)]
+    outs = []
+    for pipelined in (False, True):
+        m = B200Planner(cfg, device="cuda")
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        m.set_dropout_seed(7)
+        tr = m.make_trainer(lr=1e-4)
+        lgs = [tr.step(ds[i % 2], pipelined=pipelined).detach().clone() for i in range(6)]
+        assert tr._pending_join == pipelined
+        tr.join()
+        assert not tr._pending_join
+        torch.cuda.synchronize()
+        assert m._direct_grad[tr.lo:tr.hi].abs().max().item() == 0.0
+        outs.append((lgs, m._flat[tr.lo:tr.hi].clone()))
+    (la, pa), (lb, pb) = outs
+    assert torch.equal(la[0], lb[0])
+    for x, y in zip(la, lb):
+        fin = ~torch.isinf(x)
+        assert torch.equal(torch.isinf(x), torch.isinf(y)) and (x[fin] - y[fin]).abs().max().item() < 2e-2
+    assert ((pa - pb).norm() / pa.norm()).item() < 5e-3
