@@ -889,6 +889,7 @@ class PlannerTrainer:
         self._peer, self._peer_plan, self._peer_bases, self.peer_fallback = None, None, [], None
         self._grads_clean, self._clear_after_update = False, False
         self._pipelined, self._pending_join, self._ev_nav, self._k_nav = False, False, None, -1
+        self._debug_pano_start = None
         self.grad_comm, self.comm_sms, self._comm_buf = grad_comm, int(comm_sms), None
         # panorama branch on its own stream next to the instruction-side GEMMs of the navigation call
         # (_forward_backward_overlapped); ETP_OVERLAP=0 / overlap=False runs the two calls back to back through autograd
@@ -1223,6 +1224,8 @@ class PlannerTrainer:
         if self._pending_join:      # pipelined step(): the panorama weights / gradient slices are final when the update stream is
             S2.wait_stream(self.side)
             self._pending_join = False
+        if self._debug_pano_start is not None:     # tests: when the panorama branch of this step was allowed to start
+            self._debug_pano_start.record(S2)
         with torch.cuda.stream(S2):
             pano, pmask_u8, saved_p, _ = _pano_forward(m, rgb, dep, loc, nt, vl, 1, drop_p)
             w = pmask_u8.unsqueeze(-1).float()
