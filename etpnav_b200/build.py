@@ -55,7 +55,27 @@ def build(force: bool = False, verbose: bool = True) -> str:
             list(ex.map(run, jobs))
     if jobs or not os.path.exists(LIB):
         run([NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-Xlinker", "--no-undefined"])
+    build_host_helper(force, verbose)
     return LIB
+
+
+PY_HELPER_SRC = os.path.join(HERE, "csrc_py", "gmap_mirror.c")
+PY_HELPER = os.path.join(HERE, "_gmap_mirror.so")
+
+
+def build_host_helper(force: bool = False, verbose: bool = True) -> str:
+    """etpnav_b200/_gmap_mirror.so: the map packer's host half against the CPython API (csrc_py/gmap_mirror.c), loaded with
+    ctypes.PyDLL.  Plain gcc; the packer falls back to its pure-Python twin when this file is absent."""
+    import sysconfig
+    if force or not os.path.exists(PY_HELPER) or os.path.getmtime(PY_HELPER) < os.path.getmtime(PY_HELPER_SRC):
+        cmd = [os.environ.get("CC", "gcc"), "-O2", "-Wall", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"],
+               PY_HELPER_SRC, "-o", PY_HELPER]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return PY_HELPER
 
 
 if __name__ == "__main__":

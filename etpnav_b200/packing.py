@@ -331,13 +331,49 @@ class GmapPacker:
     launches (``etp_gmap_pack``, ``etp_segment_gather_rows`` over the cached row-pointer table) write the six tensors.
     Mirrors follow the GraphMap OBJECTS (environments finish and drop out of the batch; a new episode builds new maps)."""
 
-    def __init__(self, device="cuda", width=768):
-        self.device, self.width = torch.device(device), width
+    def __init__(self, device="cuda", width=768, impl=None):
+        """``impl``: "c" = the CPython-API host half (etpnav_b200/_gmap_mirror.so, csrc_py/gmap_mirror.c: the same mirror,
+        dictionary walks in C, one call per pack), "py" = the pure-Python twin (``_EnvMirror``); None picks "c" when the
+        helper is built.  Both produce the same bytes (tests/test_packing_incremental_cpu.py)."""
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())      # tensors report cuda:N, never bare "cuda"
+        self.device, self.width = dev, width
+        self._c = _load_mirror_helper() if impl in (None, "c") else None
+        if impl == "c" and self._c is None:
+            raise RuntimeError("etpnav_b200/_gmap_mirror.so is not built (python -m etpnav_b200.build)")
+        self.impl = "c" if self._c is not None else "py"
         self._mirrors = {}
         self._pin, self._pin_np, self._pin_ev, self._turn = [None, None], [None, None], [None, None], 0
+        self._ptr_of_cb = C.py_object(self._ptr_of)
 
     def reset(self):
         self._mirrors = {}
+
+    def _ptr_of(self, t):
+        """Device pointer of an embedding row the image gather may read in place, or -1 (needs a gradient / lives
+        elsewhere / not a contiguous fp32 row: the differentiable gather of pack_gmap is used instead)."""
+        ok = (t.device == self.device and t.dtype == torch.float32 and t.dim() == 1 and t.shape[0] == self.width
+              and t.is_contiguous() and not (torch.is_grad_enabled() and t.requires_grad))
+        return t.data_ptr() if ok else -1
+
+    def _sync_c(self, gmaps, want_img):
+        old, new, caps = self._mirrors, {}, []
+        for gm in gmaps:
+            ent = old.get(id(gm))
+            if ent is None or ent[0] is not gm:
+                ent = (gm, self._c.etp_pm_new())
+            new[id(gm)] = ent
+            caps.append(ent[1])
+        self._mirrors = new
+        return caps, self._c.etp_pm_sync(caps, list(gmaps), int(want_img), self._ptr_of_cb)
+
+    @staticmethod
+    def _poses(cur_pos, cur_ori):
+        out = np.empty((len(cur_pos), 4), dtype=np.float64)
+        for e, cp in enumerate(cur_pos):
+            out[e] = (float(cp[0]), float(cp[1]), float(cp[2]), heading_from_quaternion(cur_ori[e]))
+        return out
 
     # ---- host side -------------------------------------------------------------------------------------------------
     def _sync(self, gmaps, want_img):
@@ -393,11 +429,40 @@ class GmapPacker:
 
     def flatten(self, gmaps, cur_vp, cur_pos, cur_ori):
         """Host half only: the tuple ``flatten_gmaps`` returns (used by the CPU tests to compare the two)."""
+        if self._c is not None:
+            caps, (n_max, max_g, nf, ni, _rows, _ok) = self._sync_c(gmaps, False)
+            meta = np.zeros((len(gmaps), 8), dtype=np.int32)
+            fout, iout = np.empty(nf, dtype=np.float64), np.empty(ni, dtype=np.int32)
+            poses = self._poses(cur_pos, cur_ori)
+            self._c.etp_pm_fill(caps, list(cur_vp), poses.ctypes.data, meta.ctypes.data, fout.ctypes.data, iout.ctypes.data,
+                                None, None, None, None, n_max)
+            return meta, fout, iout, self._c.etp_pm_vp_ids(caps)[0], n_max, max_g
         sts = self._sync(gmaps, False)
         meta, nf, ni, n_max, max_g = self._layout(sts, cur_vp)
         fout, iout = np.empty(nf, dtype=np.float64), np.empty(ni, dtype=np.int32)
         self._fill(sts, meta, fout, iout, cur_pos, cur_ori)
         return meta, fout, iout, [list(st.vp_ids) for st in sts], n_max, max_g
+
+    def host_tables(self, gmaps, cur_vp, cur_pos, cur_ori):
+        """(meta, f64 blob, i32 blob, row-pointer table, csr ptr, csr idx, csr weights, all-fast flag) as numpy arrays: what
+        ``pack`` stages for the device, without a device (tests)."""
+        B = len(gmaps)
+        if self._c is not None:
+            caps, (n_max, max_g, nf, ni, rows, ok) = self._sync_c(gmaps, True)
+            meta, fout, iout = np.zeros((B, 8), dtype=np.int32), np.empty(nf, dtype=np.float64), np.empty(ni, dtype=np.int32)
+            table, cptr = np.empty(rows, dtype=np.int64), np.empty(B * n_max + 1, dtype=np.int32)
+            cidx, cwt = np.empty(rows, dtype=np.int32), np.empty(rows, dtype=np.float32)
+            poses = self._poses(cur_pos, cur_ori)
+            tb = (table.ctypes.data, cptr.ctypes.data, cidx.ctypes.data, cwt.ctypes.data) if ok else (None,) * 4
+            self._c.etp_pm_fill(caps, list(cur_vp), poses.ctypes.data, meta.ctypes.data, fout.ctypes.data, iout.ctypes.data,
+                                *tb, n_max)
+            return meta, fout, iout, table, cptr, cidx, cwt, bool(ok)
+        sts = self._sync(gmaps, True)
+        meta, nf, ni, n_max, max_g = self._layout(sts, cur_vp)
+        fout, iout = np.empty(nf, dtype=np.float64), np.empty(ni, dtype=np.int32)
+        self._fill(sts, meta, fout, iout, cur_pos, cur_ori)
+        ok = all(st.img_ok for st in sts)
+        return (meta, fout, iout) + (self.img_tables(sts, n_max) if ok else (None,) * 4) + (ok,)
 
     def img_tables(self, sts, n_max):
         """Row-pointer table + CSR (``etp_segment_gather_rows``) of ``gmap_img_fts``: [stop] (empty segment), one row per
@@ -432,23 +497,36 @@ class GmapPacker:
         _L.require_device()
         _declare()
         dev, B, W = self.device, len(gmaps), self.width
-        sts = self._sync(gmaps, True)
-        meta, nf, ni, n_max, max_g = self._layout(sts, cur_vp)
-        img_fast = all(st.img_ok for st in sts)
-        if img_fast:
-            table, ptr, idx, wt = self.img_tables(sts, n_max)
+        if self._c is not None:
+            caps, (n_max, max_g, nf, ni, rows, img_fast) = self._sync_c(gmaps, True)
+            nrow = rows if img_fast else 0
+            sizes = [nf * 8, nrow * 8, B * 32, ni * 4, (B * n_max + 1) * 4 if img_fast else 0, nrow * 4, nrow * 4]
         else:
-            table, ptr, idx, wt = (np.zeros(0, dtype=t) for t in (np.int64, np.int32, np.int32, np.float32))
-        # one blob: 8-byte sections first
-        sizes = [nf * 8, table.nbytes, meta.nbytes, ni * 4, ptr.nbytes, idx.nbytes, wt.nbytes]
+            sts = self._sync(gmaps, True)
+            meta, nf, ni, n_max, max_g = self._layout(sts, cur_vp)
+            img_fast = all(st.img_ok for st in sts)
+            if img_fast:
+                table, ptr, idx, wt = self.img_tables(sts, n_max)
+            else:
+                table, ptr, idx, wt = (np.zeros(0, dtype=t) for t in (np.int64, np.int32, np.int32, np.float32))
+            sizes = [nf * 8, table.nbytes, meta.nbytes, ni * 4, ptr.nbytes, idx.nbytes, wt.nbytes]
+        # one blob (8-byte sections first): f64 | row pointers | meta | i32 | csr ptr | csr idx | csr weights
         offs = [0]
-        for s in sizes:
-            offs.append((offs[-1] + s + 15) // 16 * 16)
+        for sz in sizes:
+            offs.append((offs[-1] + sz + 15) // 16 * 16)
         pin, pnp, ev = self._staging(offs[-1])
-        self._fill(sts, meta, pnp[offs[0]:offs[0] + nf * 8].view(np.float64), pnp[offs[3]:offs[3] + ni * 4].view(np.int32),
-                   cur_pos, cur_ori)
-        for o, a in ((offs[1], table), (offs[2], meta), (offs[4], ptr), (offs[5], idx), (offs[6], wt)):
-            pnp[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+        if self._c is not None:
+            base = pin.data_ptr()
+            poses = self._poses(cur_pos, cur_ori)
+            tb = [base + offs[k] for k in (1, 4, 5, 6)] if img_fast else [None] * 4
+            self._c.etp_pm_fill(caps, list(cur_vp), poses.ctypes.data, base + offs[2], base + offs[0], base + offs[3], *tb, n_max)
+            vp_ids, no_vp_left = self._c.etp_pm_vp_ids(caps)
+        else:
+            self._fill(sts, meta, pnp[offs[0]:offs[0] + nf * 8].view(np.float64), pnp[offs[3]:offs[3] + ni * 4].view(np.int32),
+                       cur_pos, cur_ori)
+            for o, a in ((offs[1], table), (offs[2], meta), (offs[4], ptr), (offs[5], idx), (offs[6], wt)):
+                pnp[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+            vp_ids, no_vp_left = [list(st.vp_ids) for st in sts], [not st.gids for st in sts]
         blob = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
         blob.copy_(pin[:offs[-1]], non_blocking=True)
         ev.record()
@@ -470,5 +548,26 @@ class GmapPacker:
             img = pack_gmap_img_fts(gmaps, n_max, dev)
         self._last_blob = blob     # stays referenced until the next pack: the launches above read it asynchronously
         return dict(gmap_step_ids=step_ids, gmap_visited_masks=visited.view(torch.bool), gmap_masks=masks.view(torch.bool),
-                    gmap_pos_fts=pos, gmap_pair_dists=pd, gmap_vp_ids=[list(st.vp_ids) for st in sts], gmap_img_fts=img,
-                    no_vp_left=[not st.gids for st in sts])
+                    gmap_pos_fts=pos, gmap_pair_dists=pd, gmap_vp_ids=vp_ids, gmap_img_fts=img, no_vp_left=no_vp_left)
+
+
+_mirror_helper = None
+
+
+def _load_mirror_helper():
+    """ctypes.PyDLL handle of etpnav_b200/_gmap_mirror.so (the functions take and return Python objects and run under the
+    GIL), or None when it has not been built."""
+    global _mirror_helper
+    if _mirror_helper is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_gmap_mirror.so")
+        if not os.path.exists(path):
+            return None
+        h = C.PyDLL(path)
+        h.etp_pm_new.restype, h.etp_pm_new.argtypes = C.py_object, []
+        h.etp_pm_sync.restype, h.etp_pm_sync.argtypes = C.py_object, [C.py_object, C.py_object, C.c_int, C.py_object]
+        h.etp_pm_fill.restype = C.py_object
+        h.etp_pm_fill.argtypes = [C.py_object, C.py_object] + [C.c_void_p] * 8 + [C.c_int]
+        h.etp_pm_vp_ids.restype, h.etp_pm_vp_ids.argtypes = C.py_object, [C.py_object]
+        _mirror_helper = h
+    return _mirror_helper

@@ -35,17 +35,24 @@ def check_same(pk, gms, poses):
     assert got[1].dtype == ref[1].dtype and np.array_equal(got[1], ref[1])
     assert got[2].dtype == ref[2].dtype and np.array_equal(got[2], ref[2])
     assert got[3] == ref[3] and got[4:] == ref[4:]
-    sts = pk._sync(gms, True)
-    assert all(st.img_ok for st in sts)
-    for a, b in zip(pk.img_tables(sts, ref[4]), expected_img_tables(gms, ref[4])):
+    # what pack() stages for the device (a second sync of the same state, now with the image rows)
+    meta, f64, i32b, table, cptr, cidx, cwt, ok = pk.host_tables(gms, cur_vp, cur_pos, cur_ori)
+    assert ok and np.array_equal(meta, ref[0]) and np.array_equal(f64, ref[1]) and np.array_equal(i32b, ref[2])
+    for a, b in zip((table, cptr, cidx, cwt), expected_img_tables(gms, ref[4])):
         assert a.dtype == b.dtype and np.array_equal(a, b)
 
 
+def impls():
+    return ["py", "c"] if packing._load_mirror_helper() is not None else ["py"]
+
+
+@pytest.mark.parametrize("impl", impls())
 @pytest.mark.parametrize("ghost_aug", [0.0, 0.1])
-def test_incremental_mirror_follows_evolving_maps(ghost_aug):
+def test_incremental_mirror_follows_evolving_maps(ghost_aug, impl):
     rng = np.random.default_rng(7)
     gms = [SimGraphMap(100 + e, ghost_aug=ghost_aug, width=8).step() for e in range(6)]
-    pk = packing.GmapPacker(device="cpu", width=8)
+    pk = packing.GmapPacker(device="cpu", width=8, impl=impl)
+    assert pk.impl == impl
     closures = leaves = 0
     for t in range(22):
         check_same(pk, gms, [gm.pose() for gm in gms])
@@ -65,22 +72,30 @@ def test_incremental_mirror_follows_evolving_maps(ghost_aug):
     assert closures >= 5 and leaves >= 20          # both table paths were exercised
 
 
+def test_c_helper_is_built_and_default():
+    """build() compiles csrc_py/gmap_mirror.c; the packer then takes the C host half by default."""
+    assert packing._load_mirror_helper() is not None, "etpnav_b200/_gmap_mirror.so missing: python -m etpnav_b200.build"
+    assert packing.GmapPacker(device="cpu").impl == "c"
+
+
 @pytest.mark.parametrize("name", cpu_gmap_names())
 def test_packer_first_call_equals_flatten_on_reference_fixtures(name):
     gms, cur_vp, cur_pos, cur_ori = fake_gmaps(load(name))
     ref = packing.flatten_gmaps(gms, cur_vp, cur_pos, cur_ori)
-    got = packing.GmapPacker(device="cpu").flatten(gms, cur_vp, cur_pos, cur_ori)
-    for a, b in zip(got[:3], ref[:3]):
-        assert a.dtype == b.dtype and np.array_equal(a, b)
-    assert got[3:] == ref[3:]
+    for impl in impls():
+        got = packing.GmapPacker(device="cpu", impl=impl).flatten(gms, cur_vp, cur_pos, cur_ori)
+        for a, b in zip(got[:3], ref[:3]):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+        assert got[3:] == ref[3:]
 
 
-def test_packer_falls_back_when_an_embedding_needs_a_gradient():
+@pytest.mark.parametrize("impl", impls())
+def test_packer_falls_back_when_an_embedding_needs_a_gradient(impl):
     gm = SimGraphMap(5, width=8).step().step()
     v = next(iter(gm.node_embeds))
     gm.node_embeds[v] = gm.node_embeds[v].clone().requires_grad_(True)
-    pk = packing.GmapPacker(device="cpu", width=8)
-    sts = pk._sync([gm], True)
-    assert not sts[0].img_ok                         # pack() then takes the differentiable gather of pack_gmap
+    pose = [gm.pose()]
+    args = [[gm]] + [list(x) for x in zip(*pose)]
+    assert not packing.GmapPacker(device="cpu", width=8, impl=impl).host_tables(*args)[-1]   # pack() takes pack_gmap's gather
     with torch.no_grad():
-        assert packing.GmapPacker(device="cpu", width=8)._sync([gm], True)[0].img_ok
+        assert packing.GmapPacker(device="cpu", width=8, impl=impl).host_tables(*args)[-1]
