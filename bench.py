@@ -482,7 +482,7 @@ def run_packing_workload(a):
     from tests.gmap_sim import SimGraphMap     # synthetic map generator (test infrastructure), not a checker
     torch.cuda.set_device(0)
     L.require_device()
-    B, grow, timed = a.batch, 9, 6
+    B, grow, timed = a.batch, 6, 6     # 7 -> 14 visited nodes over the run, ~80 map rows at the end (the c3 shape)
     gms = [SimGraphMap(e, width=768, device="cuda", ghost_aug=0.0, p_node=0.03, p_ghost=0.15) for e in range(B)]
     for gm in gms:
         for _ in range(grow):
