@@ -228,3 +228,26 @@ def test_peer_partition_covers_every_run_with_aligned_disjoint_sub_slices():
             assert all(a <= b and (a - x) % 64 == 0 for a, b in parts)
             assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
             assert sum(b - a for a, b in parts) == y - x
+
+
+def test_peer_entry_points_validate_their_arguments_without_a_device():
+    """etp_peer_* / etp_ipc_* (include/etpnav_b200.h) reject malformed groups and ranges before anything is launched."""
+    import ctypes as C
+    from etpnav_b200 import lib as L
+    from etpnav_b200.planner import PeerGroup
+    lib = L.lib()
+    lib.etp_last_error.restype = C.c_char_p
+    lib.etp_peer_signal.argtypes = [C.POINTER(PeerGroup), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]
+    lib.etp_peer_wait.argtypes = [C.POINTER(PeerGroup), C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_double, C.c_void_p]
+    lib.etp_peer_reduce_adamw.argtypes = [C.POINTER(PeerGroup), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 5 + \
+        [C.c_int32] * 3 + [C.c_void_p]
+    g = PeerGroup()
+    g.world, g.rank = 9, 0                                  # more ranks than a flag row holds
+    assert lib.etp_peer_signal(C.byref(g), 0, 0, 1, None) == -1 and b"world" in lib.etp_last_error()
+    g.world, g.rank = 2, 2                                  # rank outside the group
+    assert lib.etp_peer_wait(C.byref(g), 0, 0, 1, 1, 1.0, None) == -1
+    g.world, g.rank = 2, 0                                  # buffers never mapped
+    assert lib.etp_peer_signal(C.byref(g), 0, 0, 1, None) == -1 and b"null buffer" in lib.etp_last_error()
+    assert lib.etp_peer_reduce_adamw(C.byref(g), 0, 64, None, None, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 0, 0, None) == -1
+    assert lib.etp_ipc_export(None, None, None) == -1 and lib.etp_ipc_open(None, None) == -1
+    assert C.sizeof(PeerGroup) == 8 + 4 * 8 * 8             # the struct of the header: 2 x int32 + 4 arrays of 8 pointers
