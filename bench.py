@@ -657,6 +657,19 @@ def main():
 
     for _ in range(max(3, a.warmup)):
         step(resident)
+    peer_runtime_fallback = None
+    if world > 1 and mode == "train" and trainer.grad_comm == "peer":
+        # a flag wait of the peer-memory update that gave up (a rank far behind, a mapping that does not behave) would make
+        # every later number meaningless: all ranks then agree to redo the warm-up on the NCCL path and say so
+        trainer.join()
+        err = torch.tensor([trainer.peer_error()], device=dev)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if int(err.item()) != 0:
+            peer_runtime_fallback = f"peer flag wait timed out during warm-up (code {int(err.item())}): NCCL path used instead"
+            trainer = model.make_trainer(lr=1e-5, world_size=world, grad_comm="fp32", comm_sms=a.comm_sms)
+            step_done = trainer.join
+            for _ in range(max(3, a.warmup)):
+                step(resident)
     lib = L.lib()
     lib.etp_launch_count.restype = __import__("ctypes").c_longlong
     n0 = lib.etp_launch_count()
@@ -888,7 +901,8 @@ def main():
             line["dp_check"] = dp
         if world > 1 and mode == "train":
             line["dp_update"] = {"requested": a.grad_comm, "effective": trainer.grad_comm,
-                                 "peer_fallback": trainer.peer_fallback, "peer_wait_error": trainer.peer_error()}
+                                 "peer_fallback": trainer.peer_fallback or peer_runtime_fallback,
+                                 "peer_wait_error": trainer.peer_error()}
         if eager:
             line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)
