@@ -846,7 +846,8 @@ def main():
             t2.step(same, keep_grads=True)
             torch.cuda.synchronize()
             if w_ > 1:
-                owned, perr = t2.owned_ranges(), t2.peer_error()
+                owned, perr, dp_path = t2.owned_ranges(), t2.peer_error(), t2.grad_comm + (
+                    f" (peer unavailable: {t2.peer_fallback})" if t2.peer_fallback else "")
             res.append((m2._direct_grad[t2.lo:t2.hi].clone() * (1.0 / w_), m2._flat[t2.lo:t2.hi].clone()))
             del m2, t2
         (g_dp, p_dp), (g_1, p_1) = res
@@ -860,6 +861,7 @@ def main():
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dp = {"dp_check_grad_max_rel": float(stats[0]), "dp_check_max_abs": float(stats[1]),
               "dp_check_cross_rank_param_max_abs": float((pmax - pmin).abs().max()), "peer_wait_error": perr,
+              "update_path_checked": dp_path,
               "what": "one step, identical data / weights / dropout seed on all ranks: all-reduced gradient / N vs the "
                       "collective-free gradient (max |d| / max |g|), updated parameters vs the collective-free step and across ranks"}
 

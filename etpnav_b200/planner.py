@@ -858,6 +858,29 @@ class PeerGroup(C.Structure):
 
 
 PEER_FLAG_WORDS = 2 * 32 * 8
+# peer allocations this process has mapped: (peer rank, IPC handle) -> [base pointer, users].  Two trainers of one process
+# can see the same peer allocation (small tensors share an allocator segment); a handle is opened once and closed with
+# its last user.
+_IPC_OPEN = {}
+
+
+def _ipc_open(rank, handle):
+    ent = _IPC_OPEN.get((rank, handle))
+    if ent is None:
+        base = p_void()
+        _L._check(_L.lib().etp_ipc_open(handle, C.byref(base)), "etp_ipc_open")
+        ent = _IPC_OPEN[(rank, handle)] = [base.value, 0]
+    ent[1] += 1
+    return ent[0]
+
+
+def _ipc_release(rank, handle):
+    ent = _IPC_OPEN.get((rank, handle))
+    if ent is not None:
+        ent[1] -= 1
+        if ent[1] <= 0:
+            del _IPC_OPEN[(rank, handle)]
+            _L.lib().etp_ipc_close(C.c_void_p(ent[0]))
 
 
 def peer_partition(x, y, world, rank):
@@ -1018,16 +1041,14 @@ class PlannerTrainer:
                         else:
                             hb, off = allh[r][0][k]
                             if (r, hb) not in opened:
-                                base = p_void()
-                                _L._check(L0.etp_ipc_open(hb, C.byref(base)), "etp_ipc_open")
-                                opened[(r, hb)] = base.value
+                                opened[(r, hb)] = _ipc_open(r, hb)
                             ptr = opened[(r, hb)] + off
                         getattr(g, k)[r] = ptr
             except Exception as e:  # noqa: BLE001
                 why = f"rank {rank}: {e}"
         ok = torch.tensor([0 if (why or any(w for _, w in allh)) else 1], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        self._peer_bases = list(opened.values())
+        self._peer_bases = list(opened.keys())
         if int(ok.item()) == 0:
             self.peer_fallback = why or next((w for _, w in allh if w), "another rank could not map peer memory")
             self._peer_close()
@@ -1054,9 +1075,9 @@ class PlannerTrainer:
         dist.barrier()
 
     def _peer_close(self):
-        for base in self._peer_bases:
+        for r, hb in self._peer_bases:
             try:
-                _L.lib().etp_ipc_close(C.c_void_p(base))
+                _ipc_release(r, hb)
             except Exception:  # noqa: BLE001 - interpreter shutdown
                 pass
         self._peer_bases = []
