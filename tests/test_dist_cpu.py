@@ -197,3 +197,70 @@ def test_two_rank_planner_trainer_update_pipeline(tmp_path):
     assert spans[0][0] == r0["nav"][0] and spans[-1][1] == r0["nav"][1]
     assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
     assert all(abs(s - 0.5) < 1e-7 for _, _, s in r0["calls"]) and len(r0["calls"]) >= 1   # (per bucket on a CUDA device)
+
+
+def _adamw_ref(p, g, m, v, lr, b1, b2, eps, wd, t):
+    """torch.optim.AdamW's update (the arithmetic of adamw_kernel / peer_reduce_adamw_kernel)."""
+    p = p * (1.0 - lr * wd)
+    m = b1 * m + (1.0 - b1) * g
+    v = b2 * v + (1.0 - b2) * g * g
+    denom = v.sqrt() / (1.0 - b2 ** t) ** 0.5 + eps
+    return p - (lr / (1.0 - b1 ** t)) * (m / denom), m, v
+
+
+def _peer_scheme_worker(rank, world, port, out):
+    """The owner-computes scheme of the peer-memory update (csrc/peer.cu), restated with gloo collectives: every rank sums
+    the sub-slices it OWNS (planner.peer_partition) from all ranks' gradients in rank order, applies AdamW there with
+    owner-local state, and every rank receives the owners' values — against all-reduce + the same AdamW everywhere."""
+    from etpnav_b200.planner import peer_partition
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, runs = 64 * 40, [(0, 64 * 11), (64 * 12, 64 * 30), (64 * 30, 64 * 31)]       # a frozen gap and a one-granule run
+    torch.manual_seed(7)
+    p0 = torch.randn(n)
+    g = torch.randn(n, generator=torch.Generator().manual_seed(100 + rank))
+    hyper = dict(lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, wd=1e-2)
+    # replicated path: all-reduce, 1/world, AdamW on every rank (two steps)
+    pr, mr, vr = p0.clone(), torch.zeros(n), torch.zeros(n)
+    # owner path
+    po, mo, vo = p0.clone(), torch.zeros(n), torch.zeros(n)      # mo / vo are only ever touched on owned sub-slices
+    owned_total = 0
+    for t in (1, 2):
+        gs = g * t
+        red = gs.clone()
+        dist.all_reduce(red)
+        for x, y in runs:
+            pr[x:y], mr[x:y], vr[x:y] = _adamw_ref(pr[x:y], red[x:y] / world, mr[x:y], vr[x:y], t=t, **hyper)
+        every = [torch.empty(n) for _ in range(world)]
+        dist.all_gather(every, gs)                               # "peer loads": what the owner reads from each rank
+        new = po.clone()
+        for x, y in runs:
+            a, b = peer_partition(x, y, world, rank)
+            if b > a:
+                acc = every[0][a:b].clone()
+                for r in range(1, world):
+                    acc += every[r][a:b]
+                new[a:b], mo[a:b], vo[a:b] = _adamw_ref(po[a:b], acc / world, mo[a:b], vo[a:b], t=t, **hyper)
+                owned_total += (b - a) if t == 1 else 0
+        allp = [torch.empty(n) for _ in range(world)]
+        dist.all_gather(allp, new)                               # "peer stores": every rank ends up with the owners' values
+        for x, y in runs:
+            for r in range(world):
+                a, b = peer_partition(x, y, world, r)
+                po[a:b] = allp[r][a:b]
+    torch.save({"pr": pr, "po": po, "p0": p0, "owned": owned_total, "runs": runs}, f"{out}/r{rank}.pt")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_owner_computes_update_equals_allreduce_plus_replicated_adamw(tmp_path):
+    world = 2
+    mp.spawn(_peer_scheme_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    assert torch.equal(r0["po"], r1["po"])                                  # replicas end bit-identical
+    assert torch.allclose(r0["po"], r0["pr"], rtol=0, atol=1e-6)            # same update as the replicated path
+    assert r0["owned"] + r1["owned"] == sum(y - x for x, y in r0["runs"])   # the sub-slices partition the trainable runs
+    frozen = torch.ones(64 * 40, dtype=torch.bool)
+    for x, y in r0["runs"]:
+        frozen[x:y] = False
+    assert torch.equal(r0["po"][frozen], r0["p0"][frozen])                  # nothing outside the runs moved
