@@ -140,8 +140,8 @@ def test_overlapped_trainer_step_equals_the_sequential_one():
     for (lg_a, g_a, loss_a), (lg_b, g_b, loss_b) in zip(seq, ovl):
         fin = ~torch.isinf(lg_a)
         assert torch.equal(torch.isinf(lg_a), torch.isinf(lg_b))
-        assert (lg_a[fin] - lg_b[fin]).abs().max().item() < 2e-2      # later steps: bf16 rounding flips after tiny parameter differences
-        assert abs(loss_a.item() - loss_b.item()) < 5e-3
+        assert (lg_a[fin] - lg_b[fin]).abs().max().item() < 5e-2      # later steps: bf16 rounding flips after tiny parameter differences
+        assert abs(loss_a.item() - loss_b.item()) < 2e-2
         assert ((g_a - g_b).norm() / g_a.norm()).item() < 1e-1      # (5.1e-2 seen at the third step; a stream race is O(1))
     # (AdamW's first steps move every element by ~lr whatever the gradient's size: elements whose tiny gradients differ in
     # the last bits may move apart by 2 lr; the parameters as a whole stay together)
