@@ -7,7 +7,8 @@
  *   - node ids are append-only; a new node of degree 1 in graph_nx only adds its own row / column to the two all-pairs
  *     tables, anything else re-reads them;
  *   - ghosts are compared by id sequence and per-ghost front count; ghost_aug_pos is re-read after an update;
- *   - embedding pointers are asked from Python (ptr_of) for new nodes and for ghosts whose front count moved only.
+ *   - embedding pointers are read (row_pointer: device / dtype / shape / contiguity / no-gradient check) for new nodes and
+ *     for ghosts whose front count moved only.
  * No arithmetic on the values happens here (pure re-layout into the blobs etp_gmap_pack documents). */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
@@ -173,6 +174,49 @@ static int read_row(Env* s, PyObject* sd, PyObject* sp, int i, int j0, int j1) {
   return 0;
 }
 
+/* Device pointer of an embedding row the image gather may read in place, or -1: ctx = (device, dtype, width, grad enabled).
+ * The row must live on that device, be a contiguous 1-D tensor of `width` elements of that dtype, and — while autograd is
+ * recording — not require a gradient (`usable` in packing._EnvMirror.sync is the same rule in Python). */
+static long long row_pointer(PyObject* t, PyObject* ctx) {
+  static PyObject *s_dtype, *s_device, *s_ndim, *s_shape, *s_contig, *s_rg, *s_ptr;
+  if (!s_ptr) {
+    s_dtype = PyUnicode_InternFromString("dtype"); s_device = PyUnicode_InternFromString("device");
+    s_ndim = PyUnicode_InternFromString("ndim"); s_shape = PyUnicode_InternFromString("shape");
+    s_contig = PyUnicode_InternFromString("is_contiguous"); s_rg = PyUnicode_InternFromString("requires_grad");
+    s_ptr = PyUnicode_InternFromString("data_ptr");
+  }
+  long long out = -1;
+  PyObject *a = NULL, *b = NULL;
+  a = PyObject_GetAttr(t, s_dtype);
+  if (!a || a != PyTuple_GET_ITEM(ctx, 1)) goto no;
+  Py_CLEAR(a);
+  a = PyObject_GetAttr(t, s_device);
+  if (!a) goto no;
+  { int eq = PyObject_RichCompareBool(a, PyTuple_GET_ITEM(ctx, 0), Py_EQ); if (eq != 1) goto no; }
+  Py_CLEAR(a);
+  a = PyObject_GetAttr(t, s_ndim);
+  if (!a || PyLong_AsLong(a) != 1) goto no;
+  Py_CLEAR(a);
+  a = PyObject_GetAttr(t, s_shape);
+  b = a ? PySequence_GetItem(a, 0) : NULL;
+  if (!b || PyLong_AsLong(b) != PyLong_AsLong(PyTuple_GET_ITEM(ctx, 2))) goto no;
+  Py_CLEAR(a); Py_CLEAR(b);
+  a = PyObject_CallMethodNoArgs(t, s_contig);
+  if (!a || a != Py_True) goto no;
+  Py_CLEAR(a);
+  if (PyTuple_GET_ITEM(ctx, 3) == Py_True) {
+    a = PyObject_GetAttr(t, s_rg);
+    if (!a || a != Py_False) goto no;
+    Py_CLEAR(a);
+  }
+  a = PyObject_CallMethodNoArgs(t, s_ptr);
+  if (a) out = PyLong_AsLongLong(a);
+no:
+  Py_XDECREF(a); Py_XDECREF(b);
+  if (PyErr_Occurred()) { PyErr_Clear(); out = -1; }
+  return out;
+}
+
 static int sync_env(Env* s, PyObject* gm, int want_img, PyObject* ptr_of) {
   int rc = -1, updated;
   PyObject *sd = NULL, *sp = NULL, *node_pos = NULL, *node_step = NULL, *gpos_d = NULL, *fronts_d = NULL, *aug_d = NULL,
@@ -223,8 +267,18 @@ static int sync_env(Env* s, PyObject* gm, int want_img, PyObject* ptr_of) {
     int leaf = 0;
     if (n0 > 0 && n == n0 + 1 && PyObject_HasAttrString(gm, "graph_nx")) {
       G = PyObject_GetAttrString(gm, "graph_nx");
-      PyObject* adj = G ? PyObject_GetItem(G, s->nid[n0]) : NULL;
-      if (adj) { leaf = (PyObject_Size(adj) == 1); Py_DECREF(adj); }
+      /* degree of the new node: networkx keeps {node: {neighbour: attrs}} in Graph._adj (read directly: G[v] builds a view
+       * object in Python for every call); any other graph type goes through G[v] */
+      PyObject* adjd = G ? PyObject_GetAttrString(G, "_adj") : NULL;
+      PyObject* nb = (adjd && PyDict_Check(adjd)) ? PyDict_GetItemWithError(adjd, s->nid[n0]) : NULL;   /* borrowed */
+      if (nb && PyDict_Check(nb)) {
+        leaf = (PyDict_Size(nb) == 1);
+      } else {
+        if (PyErr_Occurred()) PyErr_Clear();
+        PyObject* adj = G ? PyObject_GetItem(G, s->nid[n0]) : NULL;
+        if (adj) { leaf = (PyObject_Size(adj) == 1); Py_DECREF(adj); }
+      }
+      Py_XDECREF(adjd);
       if (PyErr_Occurred()) PyErr_Clear();
     }
     if (leaf) {
@@ -317,10 +371,8 @@ static int sync_env(Env* s, PyObject* gm, int want_img, PyObject* ptr_of) {
         if (!nemb) { free(from); goto done; }
         for (int q = s->nimg; q < s->n && s->img_ok; ++q) {
           PyObject* t = PyObject_GetItem(nemb, s->nid[q]);
-          PyObject* r = t ? PyObject_CallOneArg(ptr_of, t) : NULL;
-          if (!r) { Py_XDECREF(t); free(from); goto done; }
-          long long pv = PyLong_AsLongLong(r);
-          Py_DECREF(r);
+          if (!t) { free(from); goto done; }
+          long long pv = row_pointer(t, ptr_of);
           if (pv < 0) { s->img_ok = 0; Py_DECREF(t); break; }
           s->nptr[q] = pv;
           PyList_Append(s->nkeep, t);
@@ -342,15 +394,14 @@ static int sync_env(Env* s, PyObject* gm, int want_img, PyObject* ptr_of) {
           PyObject* ent = PyObject_GetItem(gemb, ng[i]);            /* [sum tensor, count] */
           PyObject* t = ent ? PySequence_GetItem(ent, 0) : NULL;
           PyObject* cnt = ent ? PySequence_GetItem(ent, 1) : NULL;
-          PyObject* r = (t && cnt) ? PyObject_CallOneArg(ptr_of, t) : NULL;
           double cv = 0.0;
-          if (!r || as_double(cnt, &cv)) {
-            Py_XDECREF(ent); Py_XDECREF(t); Py_XDECREF(cnt); Py_XDECREF(r);
+          if (!t || !cnt || as_double(cnt, &cv)) {
+            Py_XDECREF(ent); Py_XDECREF(t); Py_XDECREF(cnt);
             for (int q = 0; q < i; ++q) Py_CLEAR(s->gten2[q]);
             free(from); goto done;
           }
-          long long pv = PyLong_AsLongLong(r);
-          Py_DECREF(ent); Py_DECREF(cnt); Py_DECREF(r);
+          long long pv = row_pointer(t, ptr_of);
+          Py_DECREF(ent); Py_DECREF(cnt);
           if (pv < 0) { s->img_ok = 0; Py_DECREF(t); s->gten2[i] = NULL; for (int q = 0; q < i; ++q) Py_CLEAR(s->gten2[q]); reimg = 0; break; }
           s->gptr2[i] = pv;
           s->gwt2[i] = (float)(1.0 / cv);
@@ -395,8 +446,10 @@ PyObject* etp_pm_new(void) {
   return PyCapsule_New(s, "etp.gmap_mirror", env_destroy);
 }
 
-/* sync every map; returns (n_max, max_g, n_f64, n_i32, image rows, all maps image-fast) */
+/* sync every map; ctx = (device, dtype, width, grad enabled) of the rows the image gather may read in place;
+ * returns (n_max, max_g, n_f64, n_i32, image rows, all maps image-fast) */
 PyObject* etp_pm_sync(PyObject* states, PyObject* gmaps, int want_img, PyObject* ptr_of) {
+  if (!PyTuple_Check(ptr_of) || PyTuple_GET_SIZE(ptr_of) != 4) { PyErr_SetString(PyExc_TypeError, "ctx must be (device, dtype, width, grad_enabled)"); return NULL; }
   Py_ssize_t B = PyList_Size(states);
   if (B < 0 || PyList_Size(gmaps) != B) { if (!PyErr_Occurred()) PyErr_SetString(PyExc_ValueError, "states / gmaps length mismatch"); return NULL; }
   long n_max = 1, max_g = 0, nf = 0, ni = 0, rows = 0; int ok = 1;

@@ -345,17 +345,9 @@ class GmapPacker:
         self.impl = "c" if self._c is not None else "py"
         self._mirrors = {}
         self._pin, self._pin_np, self._pin_ev, self._turn = [None, None], [None, None], [None, None], 0
-        self._ptr_of_cb = C.py_object(self._ptr_of)
 
     def reset(self):
         self._mirrors = {}
-
-    def _ptr_of(self, t):
-        """Device pointer of an embedding row the image gather may read in place, or -1 (needs a gradient / lives
-        elsewhere / not a contiguous fp32 row: the differentiable gather of pack_gmap is used instead)."""
-        ok = (t.device == self.device and t.dtype == torch.float32 and t.dim() == 1 and t.shape[0] == self.width
-              and t.is_contiguous() and not (torch.is_grad_enabled() and t.requires_grad))
-        return t.data_ptr() if ok else -1
 
     def _sync_c(self, gmaps, want_img):
         old, new, caps = self._mirrors, {}, []
@@ -366,7 +358,8 @@ class GmapPacker:
             new[id(gm)] = ent
             caps.append(ent[1])
         self._mirrors = new
-        return caps, self._c.etp_pm_sync(caps, list(gmaps), int(want_img), self._ptr_of_cb)
+        ctx = (self.device, torch.float32, self.width, torch.is_grad_enabled())      # rows the image gather may read in place
+        return caps, self._c.etp_pm_sync(caps, list(gmaps), int(want_img), ctx)
 
     @staticmethod
     def _poses(cur_pos, cur_ori):
