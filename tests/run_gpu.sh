@@ -7,6 +7,8 @@
 #   ncu <kernel-regex> [skip] [count]   ncu --set full capture -> gpurun_out/prof_<regex>.ncu-rep
 #   metrics               ncu per-launch DRAM bytes / tensor-pipe / duration over one train step -> gpurun_out/step_metrics.csv
 #   smoke                 __graft_entry__.smoke()
+#   benchn <N> <name> [bench args]   torchrun over N GPUs of one box -> gpurun_out/bench_<name>.json
+#   peer <N>              fused peer-memory update vs the NCCL path on N GPUs (tests/dp_peer_worker.py) -> gpurun_out/peer_n<N>.json
 # Several <what> can be chained with '+' between argument groups:  bash tests/run_gpu.sh tests -k precision + bench --steps 20
 mkdir -p gpurun_out
 run_one() {
