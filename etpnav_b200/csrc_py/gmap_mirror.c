@@ -4,8 +4,8 @@
  * that are updated INCREMENTALLY — the rules are those of packing._EnvMirror, which stays as the pure-Python twin the
  * tests compare this file with:
  *   - shortest_dist is rebuilt as a NEW dict by update_graph (:256-257): same object = no update since the last pack;
- *   - node ids are append-only; a new node of degree 1 in graph_nx only adds its own row / column to the two all-pairs
- *     tables, anything else re-reads them;
+ *   - node ids are append-only; one new node adds its own row / column to the two all-pairs tables and makes only the
+ *     pairs of older nodes that got a route through it be read again (none for a leaf); anything else re-reads the tables;
  *   - ghosts are compared by id sequence and per-ghost front count; ghost_aug_pos is re-read after an update;
  *   - embedding pointers are read (row_pointer: device / dtype / shape / contiguity / no-gradient check) for new nodes and
  *     for ghosts whose front count moved only.
@@ -281,9 +281,38 @@ static int sync_env(Env* s, PyObject* gm, int want_img, PyObject* ptr_of) {
       Py_XDECREF(adjd);
       if (PyErr_Occurred()) PyErr_Clear();
     }
-    if (leaf) {
+    if (n0 > 0 && n == n0 + 1) {
+      /* ONE new node v: its row and its column are new.  Between two OLDER nodes a, b networkx's Dijkstra (strict `<`
+       * relaxation, _dijkstra_multisource) keeps distance, path and tie-breaks unless a route through v is not longer than
+       * what the pair had: d(a,v) + d(v,b) <= old d(a,b) (with a 1e-9 relative margin for the rounding of the two sums).
+       * Only those pairs are read again — none when v has degree 1 (no simple path passes through a leaf), a handful after a
+       * loop closure.  ETP_PACK_VERIFY=1 (tests) re-reads everything afterwards and raises on any difference. */
       if (read_row(s, sd, sp, n0, 0, n)) goto done;
       for (int i = 0; i < n0; ++i) if (read_row(s, sd, sp, i, n0, n)) goto done;
+      if (!leaf) {
+        for (int i = 0; i < n0; ++i) {
+          const double av = s->sd[(size_t)i * s->cap + n0];
+          for (int j = 0; j < n0; ++j) {
+            if (i == j) continue;
+            const double cand = av + s->sd[(size_t)n0 * s->cap + j], was = s->sd[(size_t)i * s->cap + j];
+            if (!(cand > was * (1.0 + 1e-9)) && read_row(s, sd, sp, i, j, j + 1)) goto done;
+          }
+        }
+      }
+      const char* vf = getenv("ETP_PACK_VERIFY");
+      if (vf && vf[0] == '1') {
+        double* keep_d = (double*)malloc((size_t)n * n * 8);
+        int32_t* keep_l = (int32_t*)malloc((size_t)n * n * 4);
+        if (!keep_d || !keep_l) { free(keep_d); free(keep_l); PyErr_NoMemory(); goto done; }
+        for (int i = 0; i < n; ++i) { memcpy(keep_d + (size_t)i * n, s->sd + (size_t)i * s->cap, (size_t)n * 8); memcpy(keep_l + (size_t)i * n, s->spl + (size_t)i * s->cap, (size_t)n * 4); }
+        int bad = 0;
+        for (int i = 0; i < n && !bad; ++i) if (read_row(s, sd, sp, i, 0, n)) bad = -1;
+        for (int i = 0; i < n && !bad; ++i)
+          if (memcmp(keep_d + (size_t)i * n, s->sd + (size_t)i * s->cap, (size_t)n * 8) || memcmp(keep_l + (size_t)i * n, s->spl + (size_t)i * s->cap, (size_t)n * 4)) bad = 1;
+        free(keep_d); free(keep_l);
+        if (bad < 0) goto done;
+        if (bad) { PyErr_SetString(PyExc_RuntimeError, "gmap mirror: the selective table update differs from a full read"); goto done; }
+      }
     } else {
       for (int i = 0; i < n; ++i) if (read_row(s, sd, sp, i, 0, n)) goto done;
     }

@@ -99,3 +99,49 @@ def test_packer_falls_back_when_an_embedding_needs_a_gradient(impl):
     assert not packing.GmapPacker(device="cpu", width=8, impl=impl).host_tables(*args)[-1]   # pack() takes pack_gmap's gather
     with torch.no_grad():
         assert packing.GmapPacker(device="cpu", width=8, impl=impl).host_tables(*args)[-1]
+
+
+class _GridMap(SimGraphMap):
+    """Positions on an integer grid — exact distance ties between alternative paths, zero-length edges between coincident
+    nodes — and many extra edges from every new node to older ones: the worst case for the C mirror's selective update of
+    the all-pairs tables after a loop closure (only pairs with a route through the new node that is not longer are read
+    again; networkx relaxes with a strict `<`, so every other pair keeps distance, path and tie-breaks)."""
+
+    def step(self, n_cands=None):
+        import networkx as nx
+        rng, prev = self.rng, self.cur_vp
+        pos = np.round(rng.normal(0, 2, 3)) if prev is None else np.round(self.node_pos[prev] + rng.integers(-1, 2, 3))
+        self.t += 1
+        cur = str(len(self.node_pos))
+        self.graph_nx.add_node(cur)
+        if prev is not None:
+            self.graph_nx.add_edge(prev, cur, weight=float(np.linalg.norm(self.node_pos[prev] - pos)))
+        self.node_pos[cur], self.node_embeds[cur], self.node_stepId[cur] = pos, self._emb(), self.t
+        for v in [v for v in self.node_pos if v != cur]:
+            if rng.random() < 0.25:
+                self.graph_nx.add_edge(cur, v, weight=float(np.linalg.norm(pos - self.node_pos[v])))
+        if rng.random() < 0.7:
+            gh = f"g{self.ghost_cnt}"
+            self.ghost_cnt += 1
+            cp = pos + rng.integers(-2, 3, 3).astype(float)
+            self.ghost_pos[gh], self.ghost_mean_pos[gh] = [cp], cp
+            self.ghost_embeds[gh], self.ghost_fronts[gh] = [self._emb(), 1], [cur]
+        self.ghost_aug_pos = {g: np.asarray(p) for g, p in self.ghost_mean_pos.items()}
+        self.shortest_path = dict(nx.all_pairs_dijkstra_path(self.graph_nx))
+        self.shortest_dist = dict(nx.all_pairs_dijkstra_path_length(self.graph_nx))
+        self.cur_vp, self.cur_pos = cur, pos
+        return self
+
+
+@pytest.mark.skipif("c" not in impls(), reason="C helper not built")
+def test_selective_table_update_survives_ties_and_zero_length_edges(monkeypatch):
+    monkeypatch.setenv("ETP_PACK_VERIFY", "1")     # the helper re-reads every table after its selective update and raises on a difference
+    for seed in range(30):
+        gms = [_GridMap(seed * 10 + e, width=8).step() for e in range(3)]
+        pk = packing.GmapPacker(device="cpu", width=8, impl="c")
+        for t in range(14):
+            cur_vp, cur_pos, cur_ori = (list(x) for x in zip(*[gm.pose() for gm in gms]))
+            got, ref = pk.flatten(gms, cur_vp, cur_pos, cur_ori), packing.flatten_gmaps(gms, cur_vp, cur_pos, cur_ori)
+            assert all(np.array_equal(a, b) for a, b in zip(got[:3], ref[:3])), (seed, t)
+            for gm in gms:
+                gm.step()
