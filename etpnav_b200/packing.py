@@ -10,6 +10,10 @@ and both masks for the whole batch in one launch.  The image features of the map
 row / padding, :362-366,399) and the view features are row gathers: ``etp_segment_gather`` over a pool of the tensors
 the policy already holds on the device (differentiable, so the averaged panorama embeddings keep their graph).
 No CPU / PyTorch fallback: without the library or a B200 the calls raise.
+
+``GmapPacker`` is ``pack_gmap`` with memory: it mirrors every GraphMap of the batch in flat arrays between calls and
+re-reads only what ``update_graph`` / ``delete_ghost`` changed (pure-Python ``_EnvMirror`` or, when built, the CPython-API
+helper ``csrc_py/gmap_mirror.c``), stages one pinned blob, one H2D copy, two launches — same tensors, bit for bit.
 """
 import ctypes as C
 from itertools import accumulate, chain
